@@ -1,0 +1,124 @@
+/*
+ * pct_msda.h -- C ABI of the B200-native multi-scale deformable attention (MSDeformAttn) path.
+ *
+ * This is the drop-in boundary for PCTrans's pixel-decoder op.  It replaces the pybind11 module
+ * `MultiScaleDeformableAttention` of the reference
+ * (OPS = connectomics/model/maskformer_block/pixel_decoder/ops):
+ *
+ *   pct_msda_forward   <-  ms_deform_attn_forward   OPS/src/vision.cpp:19,
+ *                          OPS/src/ms_deform_attn.h:25-44, OPS/src/cuda/ms_deform_attn_cuda.cu:25-85
+ *   pct_msda_backward  <-  ms_deform_attn_backward  OPS/src/vision.cpp:20,
+ *                          OPS/src/ms_deform_attn.h:46-66, OPS/src/cuda/ms_deform_attn_cuda.cu:88-158
+ *
+ * Plain C: pointers and sizes only, no torch / ATen types, no C++ in the signatures.  The library
+ * links against the CUDA runtime only.  See INTEGRATION.md for the ctypes binding the reference's
+ * OPS/functions/ms_deform_attn_func.py would use.
+ *
+ * Tensor layouts (row-major, contiguous, identical to the reference, cu:45-53):
+ *   value              (N, S, M, D)         value_dtype
+ *   spatial_shapes     (L, 2) int64 rows (H_l, W_l)            DEVICE memory (cu:39)
+ *   level_start_index  (L,)   int64                             DEVICE memory (cu:40)
+ *   sampling_loc       (N, Lq, M, L, P, 2)  (x, y) in [0,1]     loc_dtype
+ *   attn_weight        (N, Lq, M, L, P)                         loc_dtype
+ *   output/grad_output (N, Lq, M*D)         value_dtype
+ * with loc_dtype = float32 for PCT_MSDA_F32 and PCT_MSDA_BF16, float64 for PCT_MSDA_F64
+ * (the reference dispatches fp32/fp64 only, cu:69; bf16 values with fp32 locations/weights and
+ * fp32 accumulation is this library's extension).
+ *
+ * Ownership: the caller allocates every buffer; the library never allocates, frees or retains
+ * device memory.  Outputs are write-only: they need not be initialised (the reference zero-fills
+ * with at::zeros, cu:59,126-128; here grad_value is cleared by the callee on `stream`).
+ *
+ * Threading / streams: every call is asynchronous on `cuda_stream` (a cudaStream_t cast to
+ * void*; NULL = legacy default stream) of the CURRENT device, never synchronises the host, is
+ * re-entrant and may be called from any host thread (cu:70,140 use the current stream too).
+ *
+ * Errors: 0 on success; 1..999 = the cudaError_t of the failing runtime call or launch
+ * (the reference only printf()s launch errors, cuh:953-957); >= 1000 = PCT_MSDA_E_* below.
+ * There is no CPU fallback of any kind.
+ */
+#ifndef PCT_MSDA_H_
+#define PCT_MSDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCT_MSDA_ABI_VERSION 1
+
+/* value_dtype */
+#define PCT_MSDA_F32 0
+#define PCT_MSDA_BF16 1
+#define PCT_MSDA_F64 2
+
+/* own error codes */
+#define PCT_MSDA_E_NULL_POINTER 1001
+#define PCT_MSDA_E_BAD_SHAPE 1002
+#define PCT_MSDA_E_BAD_DTYPE 1003
+#define PCT_MSDA_E_MISALIGNED 1004
+#define PCT_MSDA_E_WORKSPACE 1005
+#define PCT_MSDA_E_TOO_LARGE 1006
+
+/* flags for the *_ex entry points (0 = library default; used by the tuning harness) */
+#define PCT_MSDA_FLAG_FORCE_GENERIC 0x1u /* use the any-D scalar kernels even when a vector path fits */
+
+int pct_msda_abi_version(void);
+
+/* Human-readable text for a code returned by any entry point (static storage). */
+const char* pct_msda_error_string(int code);
+
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+uint64_t pct_msda_launch_count(void);
+
+/* Which kernel family a call with these dimensions runs: 0 = generic scalar, 1 = 128-bit vector
+ * path.  `backward` selects the gradient kernels. */
+int pct_msda_kernel_family(int channels, int num_levels, int num_point, int value_dtype,
+                           int backward);
+
+/* out[b,q,m,:] = sum_{l,p} attn[b,q,m,l,p] * bilinear(value_l[b,:,m,:], loc[b,q,m,l,p]).
+ * Replaces ms_deform_attn_cuda_forward (cu:25-85).  The reference's `im2col_step` has no
+ * counterpart: the whole batch is processed by one launch with 64-bit offsets. */
+int pct_msda_forward(const void* value, const int64_t* spatial_shapes,
+                     const int64_t* level_start_index, const void* sampling_loc,
+                     const void* attn_weight, void* output, int batch, int spatial_size,
+                     int num_heads, int channels, int num_levels, int num_query, int num_point,
+                     int value_dtype, void* cuda_stream);
+
+int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
+                        const int64_t* level_start_index, const void* sampling_loc,
+                        const void* attn_weight, void* output, int batch, int spatial_size,
+                        int num_heads, int channels, int num_levels, int num_query,
+                        int num_point, int value_dtype, void* cuda_stream, unsigned flags);
+
+/* Bytes of device scratch pct_msda_backward needs for these dimensions (0 for fp32/fp64: only the
+ * bf16 path accumulates grad_value in an fp32 scratch image before rounding it once). */
+size_t pct_msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
+                                         int value_dtype);
+
+/* Gradients of pct_msda_forward w.r.t. value, sampling_loc and attn_weight.
+ * Replaces ms_deform_attn_cuda_backward (cu:88-158).  grad_value (N,S,M,D) value_dtype,
+ * grad_sampling_loc / grad_attn_weight shaped like their inputs, loc_dtype; all three are fully
+ * overwritten.  `workspace` may be NULL when workspace_bytes is 0. */
+int pct_msda_backward(const void* value, const int64_t* spatial_shapes,
+                      const int64_t* level_start_index, const void* sampling_loc,
+                      const void* attn_weight, const void* grad_output, void* grad_value,
+                      void* grad_sampling_loc, void* grad_attn_weight, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, int value_dtype, void* workspace,
+                      size_t workspace_bytes, void* cuda_stream);
+
+int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
+                         const int64_t* level_start_index, const void* sampling_loc,
+                         const void* attn_weight, const void* grad_output, void* grad_value,
+                         void* grad_sampling_loc, void* grad_attn_weight, int batch,
+                         int spatial_size, int num_heads, int channels, int num_levels,
+                         int num_query, int num_point, int value_dtype, void* workspace,
+                         size_t workspace_bytes, void* cuda_stream, unsigned flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCT_MSDA_H_ */

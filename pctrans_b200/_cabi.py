@@ -1,0 +1,143 @@
+"""ctypes binding of the C ABI in ``include/pct_msda.h`` (``libpctrans_msda.so``).
+
+This is the only route from Python to the kernels.  There is no fallback: if the shared library is
+missing or a call fails, an exception is raised (the reference's module silently reroutes every
+failure to its slow PyTorch path, OPS/modules/ms_deform_attn.py:119-121 -- deliberately not
+reproduced).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "_build", "libpctrans_msda.so")
+ABI_VERSION = 1
+
+DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}
+
+EXPORTS = (
+    "pct_msda_abi_version", "pct_msda_error_string", "pct_msda_launch_count",
+    "pct_msda_kernel_family", "pct_msda_forward", "pct_msda_forward_ex",
+    "pct_msda_backward_workspace_bytes", "pct_msda_backward", "pct_msda_backward_ex",
+)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class MSDAError(RuntimeError):
+    """A pct_msda_* entry point returned a non-zero code."""
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises ImportError if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m pctrans_b200.build` "
+                "(nvcc, sm_100a).  pctrans_b200 has no CPU or PyTorch fallback for MSDeformAttn.")
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i32, u32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t
+        lib.pct_msda_abi_version.restype = i32
+        lib.pct_msda_abi_version.argtypes = []
+        lib.pct_msda_error_string.restype = ctypes.c_char_p
+        lib.pct_msda_error_string.argtypes = [i32]
+        lib.pct_msda_launch_count.restype = ctypes.c_uint64
+        lib.pct_msda_launch_count.argtypes = []
+        lib.pct_msda_kernel_family.restype = i32
+        lib.pct_msda_kernel_family.argtypes = [i32] * 5
+        fwd_args = [vp] * 6 + [i32] * 8 + [vp]
+        lib.pct_msda_forward.restype = i32
+        lib.pct_msda_forward.argtypes = fwd_args
+        lib.pct_msda_forward_ex.restype = i32
+        lib.pct_msda_forward_ex.argtypes = fwd_args + [u32]
+        lib.pct_msda_backward_workspace_bytes.restype = sz
+        lib.pct_msda_backward_workspace_bytes.argtypes = [i32] * 5
+        bwd_args = [vp] * 9 + [i32] * 8 + [vp, sz, vp]
+        lib.pct_msda_backward.restype = i32
+        lib.pct_msda_backward.argtypes = bwd_args
+        lib.pct_msda_backward_ex.restype = i32
+        lib.pct_msda_backward_ex.argtypes = bwd_args + [u32]
+        got = lib.pct_msda_abi_version()
+        if got != ABI_VERSION:
+            raise ImportError(f"{LIB_PATH}: ABI version {got}, expected {ABI_VERSION}; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().pct_msda_error_string(code).decode()
+        raise MSDAError(f"{what} failed with code {code}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().pct_msda_launch_count())
+
+
+def kernel_family(channels: int, num_levels: int, num_point: int, dtype: torch.dtype,
+                  backward: bool = False) -> int:
+    return int(load().pct_msda_kernel_family(channels, num_levels, num_point, DTYPE_CODES[dtype],
+                                             int(backward)))
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, flags: int = 0,
+            out=None):
+    """Raw forward on validated, contiguous CUDA tensors.  Returns output (N, Lq, M*D)
+    (written into ``out`` when given)."""
+    lib = load()
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    if out is None:
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device_of(value):
+        rc = lib.pct_msda_forward_ex(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
+            N, S, M, D, L, Lq, P, DTYPE_CODES[value.dtype], _stream_ptr(value.device), flags)
+    check(rc, "pct_msda_forward")
+    return out
+
+
+def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+             flags: int = 0, out=None, workspace=None):
+    """Raw backward.  Returns (grad_value, grad_sampling_loc, grad_attn_weight); ``out`` may
+    supply the three tensors and ``workspace`` a uint8 scratch tensor to avoid allocations."""
+    lib = load()
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    code = DTYPE_CODES[value.dtype]
+    if out is None:
+        grad_value = torch.empty_like(value)
+        grad_loc = torch.empty_like(sampling_loc)
+        grad_attn = torch.empty_like(attn_weight)
+    else:
+        grad_value, grad_loc, grad_attn = out
+    ws_bytes = int(lib.pct_msda_backward_workspace_bytes(N, S, M, D, code))
+    ws = workspace
+    if ws_bytes and (ws is None or ws.numel() < ws_bytes):
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device)
+    with torch.cuda.device_of(value):
+        rc = lib.pct_msda_backward_ex(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
+            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+            N, S, M, D, L, Lq, P, code, ws.data_ptr() if ws is not None else None, ws_bytes,
+            _stream_ptr(value.device), flags)
+    check(rc, "pct_msda_backward")
+    return grad_value, grad_loc, grad_attn

@@ -1,0 +1,404 @@
+// msda_capi.cu -- C ABI (include/pct_msda.h) and launch logic for the MSDeformAttn kernels.
+//
+// Host side of the drop-in boundary: argument validation (the reference's AT_ASSERTM block,
+// OPS/src/cuda/ms_deform_attn_cuda.cu:33-57,98-124, becomes error codes), kernel selection and
+// asynchronous launches on the caller's stream.  Links against the CUDA runtime only.
+#include "../../include/pct_msda.h"
+
+#include <atomic>
+#include <cstdio>
+
+#include "msda_kernels.cuh"
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+struct DeviceInfo {
+  int sm_count = 0;
+};
+
+int device_sm_count(int* out) {
+  // Cached per device ordinal; racing initialisers write the same value.
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev >= 0 && dev < 64) {
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v > 0) { *out = v; return 0; }
+  }
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+  *out = n;
+  return 0;
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+inline size_t elem_size(int dtype) {
+  return dtype == PCT_MSDA_F32 ? 4 : dtype == PCT_MSDA_BF16 ? 2 : 8;
+}
+
+// lanes per (query, head) pair on the vector path, or 0 if the shape does not fit it
+inline int vec_lanes(int channels, int num_levels, int dtype) {
+  if (dtype != PCT_MSDA_F32 && dtype != PCT_MSDA_BF16) return 0;
+  if (num_levels > pct::kMaxFastLevels) return 0;
+  const size_t bytes = (size_t)channels * elem_size(dtype);
+  if (bytes % 16 != 0) return 0;
+  const size_t lanes = bytes / 16;
+  if (lanes < 1 || lanes > 32 || (lanes & (lanes - 1)) != 0) return 0;
+  return (int)lanes;
+}
+
+struct Dims {
+  int N, S, M, D, L, Lq, P;
+};
+
+int check_dims(const Dims& d, int dtype) {
+  if (dtype != PCT_MSDA_F32 && dtype != PCT_MSDA_BF16 && dtype != PCT_MSDA_F64) return PCT_MSDA_E_BAD_DTYPE;
+  if (d.N < 0 || d.S < 0 || d.Lq < 0 || d.M <= 0 || d.D <= 0 || d.L <= 0 || d.P <= 0) return PCT_MSDA_E_BAD_SHAPE;
+  // per-image element counts are indexed with 64-bit offsets, but keep every count representable
+  const long double lim = 9.0e18L;
+  if ((long double)d.N * d.S * d.M * d.D > lim || (long double)d.N * d.Lq * d.M * d.L * d.P * 2 > lim)
+    return PCT_MSDA_E_TOO_LARGE;
+  return 0;
+}
+
+struct LaunchShape {
+  int grid, block;
+};
+
+// Persistent launch: one CTA per SM (or fewer when there is little work).
+LaunchShape vec_launch_shape(long long n_tasks, int sm_count, unsigned flags, int default_block) {
+  int block = default_block;
+  int ctas_per_sm = 1;
+  const int fb = (int)((flags >> 8) & 0xffu);   // threads / 32
+  const int fc = (int)((flags >> 16) & 0xfu);
+  if (fb > 0 && fb * 32 <= default_block) block = fb * 32;
+  if (fc > 0) ctas_per_sm = fc;
+  const int warps = block / 32;
+  long long want = (n_tasks + warps - 1) / warps;
+  long long cap = (long long)sm_count * ctas_per_sm;
+  LaunchShape s;
+  s.grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+  s.block = block;
+  return s;
+}
+
+template <typename T, int LPP>
+int launch_fwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                   const void* attn, void* out, const Dims& d, int sm_count, cudaStream_t st,
+                   unsigned flags) {
+  constexpr int PPW = 32 / LPP;
+  const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
+  const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kVecThreads);
+  pct::msda_fwd_vec_kernel<T, LPP><<<ls.grid, ls.block, 0, st>>>(
+      (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (T*)out, d.N, d.S, d.M,
+      d.L, d.Lq, d.P);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <typename T, int LPP>
+int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                   const void* attn, const void* grad_out, float* gacc, void* grad_loc,
+                   void* grad_attn, const Dims& d, int sm_count, cudaStream_t st, unsigned flags) {
+  constexpr int PPW = 32 / LPP;
+  const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
+  const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kBwdVecThreads);
+  pct::msda_bwd_vec_kernel<T, LPP><<<ls.grid, ls.block, 0, st>>>(
+      (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
+      gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+int dispatch_fwd_vec(int lanes, const void* value, const int64_t* shapes, const int64_t* lsi,
+                     const void* loc, const void* attn, void* out, const Dims& d, int sm_count,
+                     cudaStream_t st, unsigned flags) {
+  switch (lanes) {
+#define PCT_CASE(n) \
+  case n: return launch_fwd_vec<T, n>(value, shapes, lsi, loc, attn, out, d, sm_count, st, flags);
+    PCT_CASE(1) PCT_CASE(2) PCT_CASE(4) PCT_CASE(8) PCT_CASE(16) PCT_CASE(32)
+#undef PCT_CASE
+  }
+  return PCT_MSDA_E_BAD_SHAPE;
+}
+
+template <typename T>
+int dispatch_bwd_vec(int lanes, const void* value, const int64_t* shapes, const int64_t* lsi,
+                     const void* loc, const void* attn, const void* grad_out, float* gacc,
+                     void* grad_loc, void* grad_attn, const Dims& d, int sm_count, cudaStream_t st,
+                     unsigned flags) {
+  switch (lanes) {
+#define PCT_CASE(n)                                                                            \
+  case n: return launch_bwd_vec<T, n>(value, shapes, lsi, loc, attn, grad_out, gacc, grad_loc, \
+                                      grad_attn, d, sm_count, st, flags);
+    PCT_CASE(1) PCT_CASE(2) PCT_CASE(4) PCT_CASE(8) PCT_CASE(16) PCT_CASE(32)
+#undef PCT_CASE
+  }
+  return PCT_MSDA_E_BAD_SHAPE;
+}
+
+int generic_grid(long long n_tasks, int sm_count) {
+  const int warps = pct::kGenericThreads / 32;
+  long long want = (n_tasks + warps - 1) / warps;
+  long long cap = (long long)sm_count * 8;
+  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+template <typename T, typename CT>
+int launch_fwd_generic(const void* value, const int64_t* shapes, const int64_t* lsi,
+                       const void* loc, const void* attn, void* out, const Dims& d, int sm_count,
+                       cudaStream_t st) {
+  const long long n_tasks = (long long)d.N * d.M * d.Lq;
+  pct::msda_fwd_generic_kernel<T, CT><<<generic_grid(n_tasks, sm_count), pct::kGenericThreads, 0, st>>>(
+      (const T*)value, shapes, lsi, (const CT*)loc, (const CT*)attn, (T*)out, d.N, d.S, d.M, d.D,
+      d.L, d.Lq, d.P);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <typename T, typename CT, typename AT>
+int launch_bwd_generic(const void* value, const int64_t* shapes, const int64_t* lsi,
+                       const void* loc, const void* attn, const void* grad_out, AT* gacc,
+                       void* grad_loc, void* grad_attn, const Dims& d, int sm_count,
+                       cudaStream_t st) {
+  const long long n_tasks = (long long)d.N * d.M * d.Lq;
+  pct::msda_bwd_generic_kernel<T, CT, AT><<<generic_grid(n_tasks, sm_count), pct::kGenericThreads, 0, st>>>(
+      (const T*)value, shapes, lsi, (const CT*)loc, (const CT*)attn, (const T*)grad_out, gacc,
+      (CT*)grad_loc, (CT*)grad_attn, d.N, d.S, d.M, d.D, d.L, d.Lq, d.P);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+int round_workspace_to_bf16(const float* ws, void* grad_value, long long n, int sm_count,
+                            cudaStream_t st) {
+  const long long n8 = n / 8;
+  if (n8 > 0) {
+    long long want = (n8 + 255) / 256;
+    long long cap = (long long)sm_count * 16;
+    pct::msda_round_to_bf16_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(
+        ws, (__nv_bfloat16*)grad_value, n8);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (n8 * 8 < n) {
+    pct::msda_round_to_bf16_tail_kernel<<<1, 32, 0, st>>>(ws, (__nv_bfloat16*)grad_value, n8 * 8, n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+bool vec_eligible(const Dims& d, int dtype, unsigned flags, const void* value, const void* io,
+                  const void* loc, const void* attn, int* lanes) {
+  if (flags & PCT_MSDA_FLAG_FORCE_GENERIC) return false;
+  *lanes = vec_lanes(d.D, d.L, dtype);
+  if (*lanes == 0) return false;
+  if ((long long)d.S * d.M * d.D >= (1ll << 31)) return false;  // 32-bit in-image offsets
+  return aligned(value, 16) && aligned(io, 16) && aligned(loc, 8) && aligned(attn, 4);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pct_msda_abi_version(void) { return PCT_MSDA_ABI_VERSION; }
+
+uint64_t pct_msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* pct_msda_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case PCT_MSDA_E_NULL_POINTER: return "pct_msda: null pointer argument";
+    case PCT_MSDA_E_BAD_SHAPE: return "pct_msda: invalid dimension";
+    case PCT_MSDA_E_BAD_DTYPE: return "pct_msda: unsupported value_dtype";
+    case PCT_MSDA_E_MISALIGNED: return "pct_msda: buffer is not aligned to its element size";
+    case PCT_MSDA_E_WORKSPACE: return "pct_msda: workspace missing or too small";
+    case PCT_MSDA_E_TOO_LARGE: return "pct_msda: tensor too large";
+    default:
+      if (code > 0 && code < 1000) return cudaGetErrorString((cudaError_t)code);
+      return "pct_msda: unknown error code";
+  }
+}
+
+int pct_msda_kernel_family(int channels, int num_levels, int num_point, int value_dtype,
+                           int backward) {
+  (void)num_point;
+  (void)backward;
+  return vec_lanes(channels, num_levels, value_dtype) > 0 ? 1 : 0;
+}
+
+int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
+                        const int64_t* level_start_index, const void* sampling_loc,
+                        const void* attn_weight, void* output, int batch, int spatial_size,
+                        int num_heads, int channels, int num_levels, int num_query,
+                        int num_point, int value_dtype, void* cuda_stream, unsigned flags) {
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  int rc = check_dims(d, value_dtype);
+  if (rc) return rc;
+  if ((long long)d.N * d.Lq == 0) return 0;  // empty output, nothing to write
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output)
+    return PCT_MSDA_E_NULL_POINTER;
+  const size_t es = elem_size(value_dtype);
+  const size_t ls = value_dtype == PCT_MSDA_F64 ? 8 : 4;
+  if (!aligned(value, es) || !aligned(output, es) || !aligned(sampling_loc, ls) ||
+      !aligned(attn_weight, ls) || !aligned(spatial_shapes, 8) || !aligned(level_start_index, 8))
+    return PCT_MSDA_E_MISALIGNED;
+  int sm_count = 0;
+  rc = device_sm_count(&sm_count);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+
+  int lanes = 0;
+  if (vec_eligible(d, value_dtype, flags, value, output, sampling_loc, attn_weight, &lanes)) {
+    if (value_dtype == PCT_MSDA_F32)
+      return dispatch_fwd_vec<float>(lanes, value, spatial_shapes, level_start_index, sampling_loc,
+                                     attn_weight, output, d, sm_count, st, flags);
+    return dispatch_fwd_vec<__nv_bfloat16>(lanes, value, spatial_shapes, level_start_index,
+                                           sampling_loc, attn_weight, output, d, sm_count, st, flags);
+  }
+  switch (value_dtype) {
+    case PCT_MSDA_F32:
+      return launch_fwd_generic<float, float>(value, spatial_shapes, level_start_index, sampling_loc,
+                                              attn_weight, output, d, sm_count, st);
+    case PCT_MSDA_BF16:
+      return launch_fwd_generic<__nv_bfloat16, float>(value, spatial_shapes, level_start_index,
+                                                      sampling_loc, attn_weight, output, d, sm_count, st);
+    default:
+      return launch_fwd_generic<double, double>(value, spatial_shapes, level_start_index,
+                                                sampling_loc, attn_weight, output, d, sm_count, st);
+  }
+}
+
+int pct_msda_forward(const void* value, const int64_t* spatial_shapes,
+                     const int64_t* level_start_index, const void* sampling_loc,
+                     const void* attn_weight, void* output, int batch, int spatial_size,
+                     int num_heads, int channels, int num_levels, int num_query, int num_point,
+                     int value_dtype, void* cuda_stream) {
+  return pct_msda_forward_ex(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                             output, batch, spatial_size, num_heads, channels, num_levels,
+                             num_query, num_point, value_dtype, cuda_stream, 0u);
+}
+
+size_t pct_msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
+                                         int value_dtype) {
+  if (value_dtype != PCT_MSDA_BF16) return 0;
+  if (batch <= 0 || spatial_size <= 0 || num_heads <= 0 || channels <= 0) return 0;
+  return (size_t)batch * spatial_size * num_heads * channels * sizeof(float);
+}
+
+int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
+                         const int64_t* level_start_index, const void* sampling_loc,
+                         const void* attn_weight, const void* grad_output, void* grad_value,
+                         void* grad_sampling_loc, void* grad_attn_weight, int batch,
+                         int spatial_size, int num_heads, int channels, int num_levels,
+                         int num_query, int num_point, int value_dtype, void* workspace,
+                         size_t workspace_bytes, void* cuda_stream, unsigned flags) {
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  int rc = check_dims(d, value_dtype);
+  if (rc) return rc;
+  const long long n_value = (long long)d.N * d.S * d.M * d.D;
+  const long long n_pairs = (long long)d.N * d.Lq * d.M;
+  if (n_value == 0 && n_pairs == 0) return 0;
+  if (!spatial_shapes || !level_start_index) return PCT_MSDA_E_NULL_POINTER;
+  if (n_value > 0 && (!value || !grad_value)) return PCT_MSDA_E_NULL_POINTER;
+  if (n_pairs > 0 && (!sampling_loc || !attn_weight || !grad_output || !grad_sampling_loc || !grad_attn_weight))
+    return PCT_MSDA_E_NULL_POINTER;
+  const size_t es = elem_size(value_dtype);
+  const size_t ls = value_dtype == PCT_MSDA_F64 ? 8 : 4;
+  if (!aligned(value, es) || !aligned(grad_value, es) || !aligned(grad_output, es) ||
+      !aligned(sampling_loc, ls) || !aligned(attn_weight, ls) || !aligned(grad_sampling_loc, ls) ||
+      !aligned(grad_attn_weight, ls) || !aligned(spatial_shapes, 8) || !aligned(level_start_index, 8))
+    return PCT_MSDA_E_MISALIGNED;
+  const size_t need = pct_msda_backward_workspace_bytes(batch, spatial_size, num_heads, channels, value_dtype);
+  if (need > 0 && (!workspace || workspace_bytes < need || !aligned(workspace, 16)))
+    return PCT_MSDA_E_WORKSPACE;
+  int sm_count = 0;
+  rc = device_sm_count(&sm_count);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+
+  // grad_value accumulates through reductions: clear the accumulator image first.
+  void* acc_image = value_dtype == PCT_MSDA_BF16 ? workspace : grad_value;
+  const size_t acc_bytes = value_dtype == PCT_MSDA_BF16 ? need : (size_t)n_value * es;
+  if (acc_bytes > 0) {
+    cudaError_t e = cudaMemsetAsync(acc_image, 0, acc_bytes, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (n_pairs == 0 || n_value == 0) {
+    // no samples can touch a value: grads w.r.t. loc/attn are all zero
+    if (n_pairs > 0) {
+      cudaError_t e = cudaMemsetAsync(grad_sampling_loc, 0, (size_t)n_pairs * d.L * d.P * 2 * ls, st);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaMemsetAsync(grad_attn_weight, 0, (size_t)n_pairs * d.L * d.P * ls, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    if (value_dtype == PCT_MSDA_BF16 && n_value > 0) {
+      cudaError_t e = cudaMemsetAsync(grad_value, 0, (size_t)n_value * es, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+  }
+
+  int lanes = 0;
+  const bool vec = vec_eligible(d, value_dtype, flags, value, grad_output, sampling_loc, attn_weight, &lanes) &&
+                   aligned(acc_image, 16) && aligned(grad_sampling_loc, 8);
+  if (vec) {
+    if (value_dtype == PCT_MSDA_F32)
+      rc = dispatch_bwd_vec<float>(lanes, value, spatial_shapes, level_start_index, sampling_loc,
+                                   attn_weight, grad_output, (float*)acc_image, grad_sampling_loc,
+                                   grad_attn_weight, d, sm_count, st, flags);
+    else
+      rc = dispatch_bwd_vec<__nv_bfloat16>(lanes, value, spatial_shapes, level_start_index,
+                                           sampling_loc, attn_weight, grad_output, (float*)acc_image,
+                                           grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags);
+  } else {
+    switch (value_dtype) {
+      case PCT_MSDA_F32:
+        rc = launch_bwd_generic<float, float, float>(value, spatial_shapes, level_start_index,
+                                                     sampling_loc, attn_weight, grad_output,
+                                                     (float*)acc_image, grad_sampling_loc,
+                                                     grad_attn_weight, d, sm_count, st);
+        break;
+      case PCT_MSDA_BF16:
+        rc = launch_bwd_generic<__nv_bfloat16, float, float>(value, spatial_shapes, level_start_index,
+                                                             sampling_loc, attn_weight, grad_output,
+                                                             (float*)acc_image, grad_sampling_loc,
+                                                             grad_attn_weight, d, sm_count, st);
+        break;
+      default:
+        rc = launch_bwd_generic<double, double, double>(value, spatial_shapes, level_start_index,
+                                                        sampling_loc, attn_weight, grad_output,
+                                                        (double*)acc_image, grad_sampling_loc,
+                                                        grad_attn_weight, d, sm_count, st);
+        break;
+    }
+  }
+  if (rc) return rc;
+  if (value_dtype == PCT_MSDA_BF16)
+    return round_workspace_to_bf16((const float*)workspace, grad_value, n_value, sm_count, st);
+  return 0;
+}
+
+int pct_msda_backward(const void* value, const int64_t* spatial_shapes,
+                      const int64_t* level_start_index, const void* sampling_loc,
+                      const void* attn_weight, const void* grad_output, void* grad_value,
+                      void* grad_sampling_loc, void* grad_attn_weight, int batch,
+                      int spatial_size, int num_heads, int channels, int num_levels,
+                      int num_query, int num_point, int value_dtype, void* workspace,
+                      size_t workspace_bytes, void* cuda_stream) {
+  return pct_msda_backward_ex(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                              grad_output, grad_value, grad_sampling_loc, grad_attn_weight, batch,
+                              spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                              value_dtype, workspace, workspace_bytes, cuda_stream, 0u);
+}
+
+}  // extern "C"

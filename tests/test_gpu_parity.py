@@ -1,0 +1,287 @@
+"""GPU parity: the sm_100a kernels (through the C ABI / MSDeformAttnFunction) vs the CPU oracle.
+
+Tolerances (BASELINE.json north_star): forward <= 1e-5 relative in fp32 (2e-2 for bf16 values),
+backward grads <= 1e-4 in fp32 (atomic ordering).  "Relative" is max-abs error over the max-abs
+of the oracle tensor (SURVEY.md hard part 4: element-wise relative error is meaningless on
+near-zero gradients).  The oracle runs in fp64 on the same (fp32 / bf16-rounded) input bits.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import msda_oracle as oracle
+from pctrans_b200 import _cabi, synth
+from pctrans_b200.functions import MSDeformAttnFunction, ms_deform_attn_core_pytorch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+FWD_TOL = {torch.float32: 1e-5, torch.float64: 1e-12, torch.bfloat16: 2e-2}
+BWD_TOL = {torch.float32: 1e-4, torch.float64: 1e-11, torch.bfloat16: 2e-2}
+
+
+def rel(a, b):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a.reshape(b.shape) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def run_gpu(value, shapes, lsi, loc, attn, grad_out, dtype):
+    """fwd + bwd through MSDeformAttnFunction on the GPU; inputs are CPU tensors."""
+    ldt = torch.float64 if dtype == torch.float64 else torch.float32
+    v = value.to(DEV, dtype).requires_grad_(True)
+    lo = loc.to(DEV, ldt).requires_grad_(True)
+    at = attn.to(DEV, ldt).requires_grad_(True)
+    out = MSDeformAttnFunction.apply(v, shapes.to(DEV), lsi.to(DEV), lo, at, 128)
+    out.backward(grad_out.to(DEV, dtype))
+    torch.cuda.synchronize()
+    return out, v.grad, lo.grad, at.grad
+
+
+def check_case(value, shapes, lsi, loc, attn, grad_out, dtype, expect_family=None, scale=1.0):
+    if dtype == torch.bfloat16:       # oracle sees the bf16-rounded bits (SURVEY hard part 7)
+        value = value.bfloat16().float()
+        grad_out = grad_out.bfloat16().float()
+    if dtype != torch.float64:
+        loc, attn = loc.float(), attn.float()
+    N, S, M, D = value.shape
+    L, P = loc.shape[3], loc.shape[4]
+    if expect_family is not None:
+        assert _cabi.kernel_family(D, L, P, dtype) == expect_family
+    out, gv, gl, ga = run_gpu(value, shapes, lsi, loc, attn, grad_out, dtype)
+    assert out.dtype == dtype and gv.dtype == dtype
+    assert out.shape == (N, loc.shape[1], M * D)
+    ref_out = oracle.forward_c(value, shapes, lsi, loc, attn)
+    ref_gv, ref_gl, ref_ga = oracle.backward_c(value, shapes, lsi, loc, attn, grad_out)
+    ft, bt = FWD_TOL[dtype] * scale, BWD_TOL[dtype] * scale
+    errs = dict(out=rel(out, ref_out), gv=rel(gv, ref_gv), gl=rel(gl, ref_gl), ga=rel(ga, ref_ga))
+    assert errs["out"] <= ft, errs
+    assert errs["gv"] <= bt, errs
+    assert errs["gl"] <= bt, errs
+    assert errs["ga"] <= bt, errs
+    return errs
+
+
+def _golden(golden_dir):
+    return sorted(p for p in glob.glob(os.path.join(golden_dir, "*.npz")) if "cfg1" not in p)
+
+
+def test_library_loaded_and_fast_path_selected():
+    assert _cabi.load().pct_msda_abi_version() == 1
+    assert _cabi.kernel_family(32, 3, 4, torch.float32) == 1
+    assert _cabi.kernel_family(16, 3, 4, torch.float32) == 1
+    assert _cabi.kernel_family(32, 3, 4, torch.bfloat16) == 1
+    assert _cabi.kernel_family(30, 3, 4, torch.float32) == 0
+    assert _cabi.kernel_family(32, 3, 4, torch.float64) == 0
+
+
+def test_reference_golden_vectors(golden_dir):
+    """The reference's own outputs (tests/golden/, made by make_golden.py) -- OPS/test.py recipe
+    in fp64 for D in {2,30,32,64,71} plus the ragged out-of-range case."""
+    for path in _golden(golden_dir):
+        z = np.load(path)
+        g = {k: torch.from_numpy(z[k]) for k in z.files}
+        dtype = g["value"].dtype
+        out, gv, gl, ga = run_gpu(g["value"], g["shapes"], g["lsi"], g["loc"], g["attn"],
+                                  g["grad_out"], dtype)
+        assert rel(out, z["out"]) <= FWD_TOL[dtype], path
+        assert rel(gv, z["grad_value"]) <= BWD_TOL[dtype], path
+        assert rel(gl, z["grad_loc"]) <= BWD_TOL[dtype], path
+        assert rel(ga, z["grad_attn"]) <= BWD_TOL[dtype], path
+
+
+def test_golden_recipe_in_fp32_hits_vector_and_generic_kernels(golden_dir):
+    """Same fixtures cast to fp32: D=32/64 run the 128-bit path, D=2/30/71 the generic one;
+    the reference's own fp32 tolerance is rtol=1e-2, atol=1e-3 (OPS/test.py:59) -- ours is tighter."""
+    for d, fam in ((2, 0), (30, 0), (32, 1), (64, 1), (71, 0)):
+        z = np.load(os.path.join(golden_dir, f"kat_opstest_D{d}.npz"))
+        g = {k: torch.from_numpy(z[k]) for k in z.files}
+        check_case(g["value"].float(), g["shapes"], g["lsi"], g["loc"], g["attn"],
+                   g["grad_out"].float(), torch.float32, expect_family=fam)
+
+
+@pytest.mark.parametrize("D", [4, 8, 16, 32, 64, 128])
+@pytest.mark.parametrize("regime", ["U", "O"])
+def test_vector_path_fp32_small(D, regime):
+    shapes = ((7, 9), (4, 5), (2, 3))
+    value, sh, lsi, loc, attn = synth.make_inputs(3, shapes, M=4, D=D, P=4, regime=regime,
+                                                  seed=D + 1, Lq=37)
+    g = torch.randn(3, 37, 4 * D, generator=torch.Generator().manual_seed(D))
+    check_case(value, sh, lsi, loc, attn, g, torch.float32, expect_family=1)
+
+
+@pytest.mark.parametrize("D", [8, 16, 32, 64, 256])
+def test_vector_path_bf16_small(D):
+    shapes = ((6, 11), (3, 6))
+    value, sh, lsi, loc, attn = synth.make_inputs(2, shapes, M=8, D=D, P=4, regime="O",
+                                                  seed=D + 3, Lq=29)
+    g = torch.randn(2, 29, 8 * D, generator=torch.Generator().manual_seed(D))
+    check_case(value, sh, lsi, loc, attn, g, torch.bfloat16, expect_family=1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+@pytest.mark.parametrize("D", [1, 3, 30, 71, 1025])
+def test_generic_path(D, dtype):
+    shapes = ((6, 4), (3, 2))
+    value, sh, lsi, loc, attn = synth.make_inputs(2, shapes, M=2, D=D, P=2, regime="O",
+                                                  seed=D, Lq=5)
+    g = torch.randn(2, 5, 2 * D, generator=torch.Generator().manual_seed(D + 7))
+    if dtype == torch.float64:
+        value, loc, attn, g = value.double(), loc.double(), attn.double(), g.double()
+    fam = 1 if (dtype == torch.bfloat16 and (D * 2) % 16 == 0) else 0
+    check_case(value, sh, lsi, loc, attn, g, dtype, expect_family=fam)
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71])
+def test_gradcheck_fp64_like_reference_selftest(channels):
+    """OPS/test.py:66-89 check_gradient_numerical, asserting instead of printing."""
+    torch.manual_seed(3)
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=DEV)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = 30
+    value = (torch.rand(N, S, M, channels) * 0.01).double().to(DEV).requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2).double().to(DEV).requires_grad_(True)
+    attn = torch.rand(N, Lq, M, L, P) + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().to(DEV).requires_grad_(True)
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, attn, 2))
+
+
+@pytest.mark.parametrize("channels", [1025, 2048, 3096])
+def test_large_channel_counts_fp64(channels):
+    """The remaining channel counts of OPS/test.py:88: analytic grads vs the oracle (a numerical
+    gradcheck over 30*2*3096 value elements would only re-test the oracle's own closed form)."""
+    value, sh, lsi, loc, attn = synth.make_inputs(1, ((6, 4), (3, 2)), M=2, D=channels, P=2,
+                                                  regime="U", seed=3, Lq=2, value_scale=0.01)
+    g = torch.rand(1, 2, 2 * channels, generator=torch.Generator().manual_seed(4))
+    check_case(value.double(), sh, lsi, loc.double(), attn.double(), g.double(), torch.float64,
+               expect_family=0)
+
+
+@pytest.mark.parametrize("shapes,N,regime", [
+    (synth.CVPPP_512, 2, "R"),          # BASELINE config 1
+    (synth.CVPPP_512, 2, "U"),
+    (synth.BBBC_520x696, 2, "R"),       # config 4 pyramid (non-square, non-power-of-two)
+    (synth.CVPPP_448, 2, "R"),
+])
+@pytest.mark.parametrize("D,dtype", [(32, torch.float32), (16, torch.float32), (32, torch.bfloat16)])
+def test_baseline_shapes_vs_oracle(shapes, N, regime, D, dtype):
+    value, sh, lsi, loc, attn = synth.make_inputs(N, shapes, M=8, D=D, P=4, regime=regime, seed=0)
+    g = torch.randn(N, value.shape[1], 8 * D, generator=torch.Generator().manual_seed(1))
+    check_case(value, sh, lsi, loc, attn, g, dtype, expect_family=1)
+
+
+def test_cfg1_against_reference_golden_subsample(golden_dir):
+    """BASELINE config 1 against the sub-sampled outputs of the reference's own function."""
+    z = np.load(os.path.join(golden_dir, "cfg1_R_f32.npz"))
+    value, sh, lsi, loc, attn = synth.make_inputs(2, synth.CVPPP_512, M=8, D=32, P=4,
+                                                  regime="R", seed=0)
+    g = torch.randn(2, value.shape[1], 256, generator=torch.Generator().manual_seed(1))
+    out, gv, gl, ga = run_gpu(value, sh, lsi, loc, attn, g, torch.float32)
+    stride = int(z["stride"])
+    for name, mine, tol in (("out", out, 1e-5), ("grad_value", gv, 1e-4), ("grad_loc", gl, 1e-4),
+                            ("grad_attn", ga, 1e-4)):
+        got = mine.detach().cpu().reshape(-1)[::stride].numpy()
+        if got.shape != z[name].shape:
+            pytest.skip("fixture made from a different RNG stream")
+        err = np.abs(got - z[name]).max() / float(z[name + "_absmax"])
+        # the fixture itself is the reference's fp32 result (error ~1e-6 of its own)
+        assert err <= 2 * tol, (name, err)
+
+
+def test_cfg3_full_size_batch16():
+    """BASELINE config 3 size (N=16, 512 pyramid): full oracle comparison, fp32 and bf16."""
+    value, sh, lsi, loc, attn = synth.make_inputs(16, synth.CVPPP_512, M=8, D=32, P=4,
+                                                  regime="R", seed=0)
+    g = torch.randn(16, value.shape[1], 256, generator=torch.Generator().manual_seed(1))
+    check_case(value, sh, lsi, loc, attn, g, torch.float32, expect_family=1)
+    check_case(value, sh, lsi, loc, attn, g, torch.bfloat16, expect_family=1)
+
+
+def test_size_independent_properties_full_size():
+    """Linearity in value and attention, zero output for out-of-range points, batch independence
+    (the property the multi-GPU sharding relies on) at the benchmark size."""
+    value, sh, lsi, loc, attn = synth.make_inputs(8, synth.CVPPP_512, M=8, D=32, P=4,
+                                                  regime="R", seed=2)
+    sh_d, lsi_d = sh.to(DEV), lsi.to(DEV)
+    v, lo, at = value.to(DEV), loc.to(DEV), attn.to(DEV)
+    f = lambda v_, lo_, at_: MSDeformAttnFunction.apply(v_, sh_d, lsi_d, lo_, at_, 128)
+    base = f(v, lo, at)
+    assert torch.allclose(f(2 * v, lo, at), 2 * base, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(f(v, lo, 0.5 * at), 0.5 * base, rtol=1e-6, atol=1e-6)
+    v2 = torch.randn_like(v)
+    assert torch.allclose(f(v + v2, lo, at), base + f(v2, lo, at), rtol=1e-4, atol=1e-5)
+    assert not f(v, lo + 7.0, at).any()
+    # per-image independence: running images 2..5 alone gives the same bits
+    part = f(v[2:6].contiguous(), lo[2:6].contiguous(), at[2:6].contiguous())
+    assert torch.equal(part, base[2:6])
+    # constant value map + weights summing to 1 + all taps inside => output == constant
+    inner = (lo.clamp(0.3, 0.7)).contiguous()
+    ones = torch.full_like(v, 3.0)
+    assert torch.allclose(f(ones, inner, at), torch.full_like(base, 3.0), rtol=1e-5, atol=1e-5)
+
+
+def test_product_debug_helper_agrees_on_gpu():
+    value, sh, lsi, loc, attn = synth.make_inputs(2, ((9, 7), (5, 4)), M=4, D=32, P=4,
+                                                  regime="O", seed=4, Lq=50)
+    v, lo, at = value.to(DEV), loc.to(DEV), attn.to(DEV)
+    a = MSDeformAttnFunction.apply(v, sh.to(DEV), lsi.to(DEV), lo, at, 64)
+    b = ms_deform_attn_core_pytorch(v, sh, lo, at)
+    assert rel(a, b.cpu().numpy()) <= 1e-5
+
+
+def test_edge_cases_empty_and_ragged():
+    sh = torch.as_tensor([(3, 5)], dtype=torch.long, device=DEV)
+    lsi = torch.zeros(1, dtype=torch.long, device=DEV)
+    v = torch.randn(2, 15, 2, 8, device=DEV)
+    # no queries
+    out = MSDeformAttnFunction.apply(v, sh, lsi, torch.empty(2, 0, 2, 1, 3, 2, device=DEV),
+                                     torch.empty(2, 0, 2, 1, 3, device=DEV), 128)
+    assert out.shape == (2, 0, 16)
+    # empty batch
+    out = MSDeformAttnFunction.apply(v[:0], sh, lsi, torch.empty(0, 4, 2, 1, 3, 2, device=DEV),
+                                     torch.empty(0, 4, 2, 1, 3, device=DEV), 128)
+    assert out.shape == (0, 4, 16)
+    # batch not divisible by im2col_step (the reference asserts, cu:57) and a query count that
+    # is not a multiple of the pairs-per-warp
+    value, shp, l, loc, attn = synth.make_inputs(3, ((3, 5),), M=2, D=8, P=3, regime="O", seed=8, Lq=13)
+    g = torch.randn(3, 13, 16, generator=torch.Generator().manual_seed(2))
+    check_case(value, shp, l, loc, attn, g, torch.float32, expect_family=1)
+
+
+def test_preconditions_raise():
+    value, sh, lsi, loc, attn = synth.make_inputs(1, ((4, 4),), M=2, D=8, P=2, regime="U", seed=1, Lq=4)
+    with pytest.raises(RuntimeError):
+        MSDeformAttnFunction.apply(value, sh, lsi, loc, attn, 128)            # CPU tensors (cu:39)
+    v, s, l, lo, at = (t.to(DEV) for t in (value, sh, lsi, loc, attn))
+    with pytest.raises(RuntimeError):
+        MSDeformAttnFunction.apply(v.transpose(1, 2).contiguous().transpose(1, 2), s, l, lo, at, 128)
+    with pytest.raises(TypeError):
+        MSDeformAttnFunction.apply(v.half(), s, l, lo, at, 128)
+    with pytest.raises(TypeError):
+        MSDeformAttnFunction.apply(v, s.int(), l.int(), lo, at, 128)
+    with pytest.raises(ValueError):
+        MSDeformAttnFunction.apply(v, s, l, lo[..., :1].contiguous(), at, 128)
+    # raw ABI: null pointer and bad dtype come back as codes, not crashes
+    lib = _cabi.load()
+    assert lib.pct_msda_forward(None, s.data_ptr(), l.data_ptr(), lo.data_ptr(), at.data_ptr(),
+                                v.data_ptr(), 1, 16, 2, 8, 1, 4, 2, 0, None) == 1001
+    assert lib.pct_msda_forward(v.data_ptr(), s.data_ptr(), l.data_ptr(), lo.data_ptr(),
+                                at.data_ptr(), v.data_ptr(), 1, 16, 2, 8, 1, 4, 2, 9, None) == 1003
+
+
+def test_non_default_stream_and_launch_counter():
+    value, sh, lsi, loc, attn = synth.make_inputs(2, ((8, 8), (4, 4)), M=4, D=32, P=4, regime="U", seed=6)
+    v, s, l, lo, at = (t.to(DEV) for t in (value, sh, lsi, loc, attn))
+    ref = MSDeformAttnFunction.apply(v, s, l, lo, at, 128)
+    before = _cabi.launch_count()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        out = MSDeformAttnFunction.apply(v, s, l, lo, at, 128)
+    st.synchronize()
+    assert _cabi.launch_count() == before + 1
+    assert torch.equal(out, ref)
