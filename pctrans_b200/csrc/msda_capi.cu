@@ -14,10 +14,6 @@ namespace {
 
 std::atomic<uint64_t> g_launches{0};
 
-struct DeviceInfo {
-  int sm_count = 0;
-};
-
 int device_sm_count(int* out) {
   // Cached per device ordinal; racing initialisers write the same value.
   static std::atomic<int> cache[64];
@@ -42,15 +38,35 @@ inline size_t elem_size(int dtype) {
   return dtype == PCT_MSDA_F32 ? 4 : dtype == PCT_MSDA_BF16 ? 2 : 8;
 }
 
-// lanes per (query, head) pair on the vector path, or 0 if the shape does not fit it
-inline int vec_lanes(int channels, int num_levels, int dtype) {
-  if (dtype != PCT_MSDA_F32 && dtype != PCT_MSDA_BF16) return 0;
-  if (num_levels > pct::kMaxFastLevels) return 0;
+// How a (query, head) pair is spread over lanes on the vector path.
+struct VecPlan {
+  int lanes = 0;  // lanes per pair (0 = shape does not fit the vector path)
+  int vb = 0;     // bytes of channels per lane
+};
+
+inline bool pow2_le32(size_t x) { return x >= 1 && x <= 32 && (x & (x - 1)) == 0; }
+
+// Forward prefers 16-byte lanes (LDG.128); backward wants 4 channels per lane so that every
+// red.v4.f32 covers whole sectors together with its neighbours (16 B fp32, 8 B bf16).  Wider lanes
+// are the fall-back for head dims that would need more than 32 lanes.
+inline VecPlan vec_plan(int channels, int num_levels, int num_point, int dtype, bool backward) {
+  VecPlan p;
+  if (dtype != PCT_MSDA_F32 && dtype != PCT_MSDA_BF16) return p;
+  if ((long long)num_levels * num_point > pct::kMaxFastSamples) return p;
   const size_t bytes = (size_t)channels * elem_size(dtype);
-  if (bytes % 16 != 0) return 0;
-  const size_t lanes = bytes / 16;
-  if (lanes < 1 || lanes > 32 || (lanes & (lanes - 1)) != 0) return 0;
-  return (int)lanes;
+  const int first = (dtype == PCT_MSDA_BF16 && backward) ? 8 : 16;
+  const int second = first * 2;
+  if (bytes % first == 0 && pow2_le32(bytes / first)) {
+    p.lanes = (int)(bytes / first);
+    p.vb = first;
+  } else if (bytes % second == 0 && bytes / second == 32) {
+    p.lanes = 32;
+    p.vb = second;
+  } else if (dtype == PCT_MSDA_BF16 && !backward && bytes == 8) {
+    p.lanes = 1;
+    p.vb = 8;
+  }
+  return p;
 }
 
 struct Dims {
@@ -88,61 +104,73 @@ LaunchShape vec_launch_shape(long long n_tasks, int sm_count, unsigned flags, in
   return s;
 }
 
-template <typename T, int LPP>
+template <typename T, int LPP, int VB>
 int launch_fwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                    const void* attn, void* out, const Dims& d, int sm_count, cudaStream_t st,
                    unsigned flags) {
   constexpr int PPW = 32 / LPP;
   const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kVecThreads);
-  pct::msda_fwd_vec_kernel<T, LPP><<<ls.grid, ls.block, 0, st>>>(
+  pct::msda_fwd_vec_kernel<T, LPP, VB><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (T*)out, d.N, d.S, d.M,
       d.L, d.Lq, d.P);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
 
-template <typename T, int LPP>
+template <typename T, int LPP, int VB>
 int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                    const void* attn, const void* grad_out, float* gacc, void* grad_loc,
                    void* grad_attn, const Dims& d, int sm_count, cudaStream_t st, unsigned flags) {
   constexpr int PPW = 32 / LPP;
   const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kBwdVecThreads);
-  pct::msda_bwd_vec_kernel<T, LPP><<<ls.grid, ls.block, 0, st>>>(
+  pct::msda_bwd_vec_kernel<T, LPP, VB><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
       gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
 
-template <typename T>
-int dispatch_fwd_vec(int lanes, const void* value, const int64_t* shapes, const int64_t* lsi,
-                     const void* loc, const void* attn, void* out, const Dims& d, int sm_count,
-                     cudaStream_t st, unsigned flags) {
-  switch (lanes) {
-#define PCT_CASE(n) \
-  case n: return launch_fwd_vec<T, n>(value, shapes, lsi, loc, attn, out, d, sm_count, st, flags);
-    PCT_CASE(1) PCT_CASE(2) PCT_CASE(4) PCT_CASE(8) PCT_CASE(16) PCT_CASE(32)
-#undef PCT_CASE
+#define PCT_LANE_CASES(LAUNCH, T, VB)                                                    \
+  switch (plan.lanes) {                                                                 \
+    case 1: return LAUNCH<T, 1, VB>;                                                    \
+    case 2: return LAUNCH<T, 2, VB>;                                                    \
+    case 4: return LAUNCH<T, 4, VB>;                                                    \
+    case 8: return LAUNCH<T, 8, VB>;                                                    \
+    case 16: return LAUNCH<T, 16, VB>;                                                  \
+    case 32: return LAUNCH<T, 32, VB>;                                                  \
+  }                                                                                     \
+  return nullptr;
+
+using FwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
+                            void*, const Dims&, int, cudaStream_t, unsigned);
+using BwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
+                            const void*, float*, void*, void*, const Dims&, int, cudaStream_t,
+                            unsigned);
+
+FwdLauncher pick_fwd(const VecPlan& plan, int dtype) {
+  if (dtype == PCT_MSDA_F32) {
+    if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, float, 16) }
+    if (plan.vb == 32 && plan.lanes == 32) return launch_fwd_vec<float, 32, 32>;
+  } else {
+    if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, __nv_bfloat16, 16) }
+    if (plan.vb == 8 && plan.lanes == 1) return launch_fwd_vec<__nv_bfloat16, 1, 8>;
   }
-  return PCT_MSDA_E_BAD_SHAPE;
+  return nullptr;
 }
 
-template <typename T>
-int dispatch_bwd_vec(int lanes, const void* value, const int64_t* shapes, const int64_t* lsi,
-                     const void* loc, const void* attn, const void* grad_out, float* gacc,
-                     void* grad_loc, void* grad_attn, const Dims& d, int sm_count, cudaStream_t st,
-                     unsigned flags) {
-  switch (lanes) {
-#define PCT_CASE(n)                                                                            \
-  case n: return launch_bwd_vec<T, n>(value, shapes, lsi, loc, attn, grad_out, gacc, grad_loc, \
-                                      grad_attn, d, sm_count, st, flags);
-    PCT_CASE(1) PCT_CASE(2) PCT_CASE(4) PCT_CASE(8) PCT_CASE(16) PCT_CASE(32)
-#undef PCT_CASE
+BwdLauncher pick_bwd(const VecPlan& plan, int dtype) {
+  if (dtype == PCT_MSDA_F32) {
+    if (plan.vb == 16) { PCT_LANE_CASES(launch_bwd_vec, float, 16) }
+    if (plan.vb == 32 && plan.lanes == 32) return launch_bwd_vec<float, 32, 32>;
+  } else {
+    if (plan.vb == 8) { PCT_LANE_CASES(launch_bwd_vec, __nv_bfloat16, 8) }
+    if (plan.vb == 16 && plan.lanes == 32) return launch_bwd_vec<__nv_bfloat16, 32, 16>;
   }
-  return PCT_MSDA_E_BAD_SHAPE;
+  return nullptr;
 }
+#undef PCT_LANE_CASES
 
 int generic_grid(long long n_tasks, int sm_count) {
   const int warps = pct::kGenericThreads / 32;
@@ -197,13 +225,18 @@ int round_workspace_to_bf16(const float* ws, void* grad_value, long long n, int 
   return 0;
 }
 
-bool vec_eligible(const Dims& d, int dtype, unsigned flags, const void* value, const void* io,
-                  const void* loc, const void* attn, int* lanes) {
-  if (flags & PCT_MSDA_FLAG_FORCE_GENERIC) return false;
-  *lanes = vec_lanes(d.D, d.L, dtype);
-  if (*lanes == 0) return false;
-  if ((long long)d.S * d.M * d.D >= (1ll << 31)) return false;  // 32-bit in-image offsets
-  return aligned(value, 16) && aligned(io, 16) && aligned(loc, 8) && aligned(attn, 4);
+// `io` is output (forward) or grad_output (backward); `acc` the fp32 grad_value accumulator
+// (backward only).
+VecPlan vec_eligible(const Dims& d, int dtype, unsigned flags, const void* value, const void* io,
+                     const void* acc, const void* loc, const void* attn) {
+  VecPlan none;
+  if (flags & PCT_MSDA_FLAG_FORCE_GENERIC) return none;
+  if ((long long)d.S * d.M * d.D >= (1ll << 31) || d.S == 0) return none;  // 32-bit in-image offsets
+  if (!aligned(loc, 8) || !aligned(attn, 4)) return none;
+  VecPlan p = vec_plan(d.D, d.L, d.P, dtype, acc != nullptr);
+  if (p.lanes == 0) return none;
+  if (!aligned(value, p.vb) || !aligned(io, p.vb) || (acc && !aligned(acc, 16))) return none;
+  return p;
 }
 
 }  // namespace
@@ -231,9 +264,7 @@ const char* pct_msda_error_string(int code) {
 
 int pct_msda_kernel_family(int channels, int num_levels, int num_point, int value_dtype,
                            int backward) {
-  (void)num_point;
-  (void)backward;
-  return vec_lanes(channels, num_levels, value_dtype) > 0 ? 1 : 0;
+  return vec_plan(channels, num_levels, num_point, value_dtype, backward != 0).lanes > 0 ? 1 : 0;
 }
 
 int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
@@ -257,14 +288,14 @@ int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)cuda_stream;
 
-  int lanes = 0;
-  if (vec_eligible(d, value_dtype, flags, value, output, sampling_loc, attn_weight, &lanes)) {
-    if (value_dtype == PCT_MSDA_F32)
-      return dispatch_fwd_vec<float>(lanes, value, spatial_shapes, level_start_index, sampling_loc,
-                                     attn_weight, output, d, sm_count, st, flags);
-    return dispatch_fwd_vec<__nv_bfloat16>(lanes, value, spatial_shapes, level_start_index,
-                                           sampling_loc, attn_weight, output, d, sm_count, st, flags);
+  if ((long long)d.S * d.M * d.D == 0) {
+    // no value to sample: every point is out of range, the output is all zeros
+    return (int)cudaMemsetAsync(output, 0, (size_t)d.N * d.Lq * d.M * d.D * es, st);
   }
+  const VecPlan vp = vec_eligible(d, value_dtype, flags, value, output, nullptr, sampling_loc, attn_weight);
+  if (FwdLauncher fn = vp.lanes > 0 ? pick_fwd(vp, value_dtype) : nullptr)
+    return fn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, sm_count,
+              st, flags);
   switch (value_dtype) {
     case PCT_MSDA_F32:
       return launch_fwd_generic<float, float>(value, spatial_shapes, level_start_index, sampling_loc,
@@ -348,18 +379,13 @@ int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
     return 0;
   }
 
-  int lanes = 0;
-  const bool vec = vec_eligible(d, value_dtype, flags, value, grad_output, sampling_loc, attn_weight, &lanes) &&
-                   aligned(acc_image, 16) && aligned(grad_sampling_loc, 8);
-  if (vec) {
-    if (value_dtype == PCT_MSDA_F32)
-      rc = dispatch_bwd_vec<float>(lanes, value, spatial_shapes, level_start_index, sampling_loc,
-                                   attn_weight, grad_output, (float*)acc_image, grad_sampling_loc,
-                                   grad_attn_weight, d, sm_count, st, flags);
-    else
-      rc = dispatch_bwd_vec<__nv_bfloat16>(lanes, value, spatial_shapes, level_start_index,
-                                           sampling_loc, attn_weight, grad_output, (float*)acc_image,
-                                           grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags);
+  const VecPlan vp = aligned(grad_sampling_loc, 8)
+                         ? vec_eligible(d, value_dtype, flags, value, grad_output, acc_image,
+                                        sampling_loc, attn_weight)
+                         : VecPlan{};
+  if (BwdLauncher fn = vp.lanes > 0 ? pick_bwd(vp, value_dtype) : nullptr) {
+    rc = fn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+            (float*)acc_image, grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags);
   } else {
     switch (value_dtype) {
       case PCT_MSDA_F32:

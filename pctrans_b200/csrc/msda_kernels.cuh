@@ -9,14 +9,18 @@
 //    queries of ONE head of ONE image: the bilinear footprints of neighbouring queries overlap,
 //    and the SM's L1 acts as a sliding window over each level's value map (the gather moves 15x
 //    the HBM bytes through L1, so L1 locality -- not HBM -- decides the speed of this op).
-//  * A (query, head) pair is handled by LPP = D*sizeof(T)/16 lanes, each owning one 128-bit
-//    channel vector, so every tap is one LDG.128 per lane and a warp covers 32/LPP pairs.
-//  * grad_value leaves the SM as 128-bit vector reductions (red.global.add.v4.f32, one per tap per
-//    lane) instead of per-channel scalar atomics; grad_sampling_loc / grad_attn_weight are reduced
-//    over the LPP channel lanes with xor-shuffles and written once (no shared memory, no
-//    __syncthreads in either kernel's main loop).
-//  * The generic kernels (any D, fp64, L > kMaxFastLevels) keep the same stream ordering with one
-//    warp per pair.
+//  * A (query, head) pair is handled by LPP lanes, each owning 16 or 32 contiguous bytes of the
+//    head's channels, so every bilinear tap is one 128-bit or 256-bit load per lane (LDG.E.128 /
+//    LDG.E.ENL2.256) and a warp covers 32/LPP pairs.
+//  * The per-sample scalar work (pixel coordinates, in-range predicate, bilinear weights, corner
+//    addresses) is done by ONE lane per sample and broadcast with warp shuffles, not recomputed
+//    by every channel lane.
+//  * grad_value leaves the SM as 128-bit vector reductions (red.global.add.v4.f32) instead of
+//    per-channel scalar atomics; grad_sampling_loc / grad_attn_weight come from four per-corner
+//    dot products reduced over the LPP channel lanes with xor-shuffles and are written coalesced
+//    by the lane that owns the sample (no __syncthreads in either kernel's main loop).
+//  * The generic kernels (any D, fp64, L*P > kMaxFastSamples) keep the same stream ordering with
+//    one warp per pair.
 #pragma once
 
 #include <cuda_bf16.h>
@@ -25,36 +29,57 @@
 
 namespace pct {
 
-constexpr int kMaxFastLevels = 16;
 constexpr int kVecThreads = 1024;  // forward: one persistent 32-warp CTA per SM
 constexpr int kBwdVecThreads = 768; // backward needs ~80 registers per thread
 constexpr int kGenericThreads = 256;
 
 // ---------------------------------------------------------------------------------------------
-// 128-bit channel vectors
+// Channel vectors: one lane owns VB contiguous bytes of a (pixel, head) row, moved with one
+// 64-bit, 128-bit or 256-bit (LDG.E.ENL2.256 on sm_100a) instruction.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-struct Vec16;
+template <typename T, int VB>
+struct ChanVec;
 
 template <>
-struct Vec16<float> {
+struct ChanVec<float, 16> {
   static constexpr int kElems = 4;
-  static __device__ __forceinline__ void load(const float* p, bool pred, float (&v)[4]) {
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pred) r = __ldg(reinterpret_cast<const float4*>(p));
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
   }
   static __device__ __forceinline__ void load_stream(const float* p, float (&v)[4]) {
-    float4 r = __ldcs(reinterpret_cast<const float4*>(p));
+    const float4 r = __ldcs(reinterpret_cast<const float4*>(p));
     v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
   }
-  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+  static __device__ __forceinline__ void store_stream(float* p, const float (&v)[4]) {
     __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
   }
 };
 
 template <>
-struct Vec16<__nv_bfloat16> {
+struct ChanVec<float, 32> {
+  static constexpr int kElems = 8;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]),
+                   "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+  }
+  static __device__ __forceinline__ void load_stream(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]),
+                   "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+  }
+  static __device__ __forceinline__ void store_stream(float* p, const float (&v)[8]) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]),
+                 "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+  }
+};
+
+template <>
+struct ChanVec<__nv_bfloat16, 16> {
   static constexpr int kElems = 8;
   static __device__ __forceinline__ void unpack(const uint4& r, float (&v)[8]) {
     const unsigned w[4] = {r.x, r.y, r.z, r.w};
@@ -64,16 +89,13 @@ struct Vec16<__nv_bfloat16> {
       v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
   }
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, bool pred, float (&v)[8]) {
-    uint4 r = make_uint4(0u, 0u, 0u, 0u);
-    if (pred) r = __ldg(reinterpret_cast<const uint4*>(p));
-    unpack(r, v);
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    unpack(__ldg(reinterpret_cast<const uint4*>(p)), v);
   }
   static __device__ __forceinline__ void load_stream(const __nv_bfloat16* p, float (&v)[8]) {
-    uint4 r = __ldcs(reinterpret_cast<const uint4*>(p));
-    unpack(r, v);
+    unpack(__ldcs(reinterpret_cast<const uint4*>(p)), v);
   }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+  static __device__ __forceinline__ void store_stream(__nv_bfloat16* p, const float (&v)[8]) {
     uint4 r;
     unsigned* w = reinterpret_cast<unsigned*>(&r);
 #pragma unroll
@@ -85,6 +107,31 @@ struct Vec16<__nv_bfloat16> {
   }
 };
 
+template <>
+struct ChanVec<__nv_bfloat16, 8> {
+  static constexpr int kElems = 4;
+  static __device__ __forceinline__ void unpack(const uint2& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x << 16);
+    v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16);
+    v[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+    unpack(__ldg(reinterpret_cast<const uint2*>(p)), v);
+  }
+  static __device__ __forceinline__ void load_stream(const __nv_bfloat16* p, float (&v)[4]) {
+    unpack(__ldcs(reinterpret_cast<const uint2*>(p)), v);
+  }
+  static __device__ __forceinline__ void store_stream(__nv_bfloat16* p, const float (&v)[4]) {
+    uint2 r;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(v[2], v[3]);
+    r.x = *reinterpret_cast<unsigned*>(&lo);
+    r.y = *reinterpret_cast<unsigned*>(&hi);
+    __stcs(reinterpret_cast<uint2*>(p), r);
+  }
+};
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
                "f"(d)
@@ -92,61 +139,76 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bilinear taps (cuh:45-58 geometry, cuh:61-83 per-corner bounds, cuh:293 in-range predicate)
+// Bilinear taps (cuh:45-58 geometry, cuh:61-83 per-corner bounds, cuh:293 in-range predicate).
+//
+// One lane computes the taps of ONE sample and broadcasts them to the lanes that share its
+// (query, head) pair, instead of every channel lane recomputing them.  Taps are made branch-free
+// for the consumers: the four corner addresses are clamped into the map (always loadable) and a
+// corner that the reference would skip gets weight 0, so it contributes exactly nothing (for
+// finite values) and its grad_value update is skipped.
 // ---------------------------------------------------------------------------------------------
-struct Taps {
-  int off00;           // element offset of pixel (y0, x0) inside the level map, head 0 channel 0
-  bool m00, m01, m10, m11;  // corner is inside the map (and the point passed the predicate)
-  float ly, lx, hy, hx;
+struct SampleTaps {
+  int off;   // element offset (inside one image, head 0, channel 0) of the clamped (y0, x0) corner
+  int dx;    // element step to the x+1 corner (0 when clamped onto the same pixel)
+  int dy;    // element step to the y+1 corner
+  float ly, lx;          // fractional parts
+  bool v00, v01, v10, v11;  // corner is sampled by the reference
 };
 
-__device__ __forceinline__ Taps make_taps(float loc_x, float loc_y, int H, int W, int MD) {
-  Taps t;
+// tab = {H, W, level_start, unused}
+__device__ __forceinline__ SampleTaps make_sample_taps(float loc_x, float loc_y, int H, int W,
+                                                       int start, int MD) {
+  SampleTaps t;
   // The reference evaluates loc*size - 0.5 in double and rounds once (the literal 0.5 promotes,
   // cuh:290-291): that is exactly one fused multiply-add in fp32.
   const float y = fmaf(loc_y, (float)H, -0.5f);
   const float x = fmaf(loc_x, (float)W, -0.5f);
   const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
   const float fy = floorf(y), fx = floorf(x);
-  const int y0 = (int)fy, x0 = (int)fx;
   t.ly = y - fy;
   t.lx = x - fx;
-  t.hy = 1.f - t.ly;
-  t.hx = 1.f - t.lx;
+  const int y0 = inside ? (int)fy : 0, x0 = inside ? (int)fx : 0;
   const bool top = inside && (y0 >= 0), bot = inside && (y0 + 1 <= H - 1);
   const bool lef = (x0 >= 0), rig = (x0 + 1 <= W - 1);
-  t.m00 = top && lef;
-  t.m01 = top && rig;
-  t.m10 = bot && lef;
-  t.m11 = bot && rig;
-  t.off00 = (y0 * W + x0) * MD;
+  t.v00 = top && lef;
+  t.v01 = top && rig;
+  t.v10 = bot && lef;
+  t.v11 = bot && rig;
+  // inside => H >= 1 and W >= 1, so the clamps below stay inside the map
+  const int y0c = max(y0, 0), x0c = max(x0, 0);
+  const int y1c = min(y0 + 1, H - 1), x1c = min(x0 + 1, W - 1);
+  t.off = inside ? (start + y0c * W + x0c) * MD : 0;
+  t.dx = inside ? (x1c - x0c) * MD : 0;
+  t.dy = inside ? (y1c - y0c) * W * MD : 0;
   return t;
 }
 
-struct StreamTask {
-  int b, m, q;      // q = first query of the warp's group
-  long long pair;   // ((b*Lq + q) * M + m) for the lane's own pair (clamped to a valid query)
-  bool valid;
-};
+constexpr int kMaxFastSamples = 128;  // L*P limit of the vector path (level table in smem)
+
+__device__ __forceinline__ void fill_level_table(int4* tab, const int64_t* shapes,
+                                                 const int64_t* lsi, int L, int P) {
+  for (int s = threadIdx.x; s < L * P; s += blockDim.x) {
+    const int l = s / P;
+    tab[s] = make_int4((int)shapes[2 * l], (int)shapes[2 * l + 1], (int)lsi[l], 0);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
-// Forward, vector path.  T = float | bf16; LPP lanes per (query, head) pair; D = LPP * 16/sizeof(T)
+// Forward, vector path.  T = float | bf16; LPP lanes per (query, head) pair, each owning VB
+// bytes of the head's channels: D = LPP * VB/sizeof(T); a warp covers 32/LPP pairs.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LPP>
+template <typename T, int LPP, int VB>
 __global__ void __launch_bounds__(kVecThreads, 1)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, T* __restrict__ out, int N, int S, int M,
                     int L, int Lq, int P) {
-  constexpr int VE = Vec16<T>::kElems;
+  using CV = ChanVec<T, VB>;
+  constexpr int VE = CV::kElems;
   constexpr int D = LPP * VE;
   constexpr int PPW = 32 / LPP;  // pairs per warp
-  __shared__ int sH[kMaxFastLevels], sW[kMaxFastLevels], sStart[kMaxFastLevels];
-  if (threadIdx.x < L) {
-    sH[threadIdx.x] = (int)shapes[2 * threadIdx.x];
-    sW[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
-    sStart[threadIdx.x] = (int)lsi[threadIdx.x];
-  }
+  __shared__ int4 s_tab[kMaxFastSamples];
+  fill_level_table(s_tab, shapes, lsi, L, P);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -173,52 +235,82 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 #pragma unroll
     for (int i = 0; i < VE; ++i) acc[i] = 0.f;
 
-    for (int l = 0; l < L; ++l) {
-      const int H = sH[l], W = sW[l];
-      const T* vl = vimg + (long long)sStart[l] * MD;
-      const int rowstep = W * MD;
-#pragma unroll 2
-      for (int p = 0; p < P; ++p) {
-        const float2 xy = __ldg(lp + l * P + p);
-        const float a = __ldg(ap + l * P + p);
-        const Taps tp = make_taps(xy.x, xy.y, H, W, MD);
-        const T* p00 = vl + tp.off00;
-        float v00[VE], v01[VE], v10[VE], v11[VE];
-        Vec16<T>::load(p00, tp.m00, v00);
-        Vec16<T>::load(p00 + MD, tp.m01, v01);
-        Vec16<T>::load(p00 + rowstep, tp.m10, v10);
-        Vec16<T>::load(p00 + rowstep + MD, tp.m11, v11);
-        const float w00 = tp.hy * tp.hx * a, w01 = tp.hy * tp.lx * a;
-        const float w10 = tp.ly * tp.hx * a, w11 = tp.ly * tp.lx * a;
+    // software pipeline: the location / weight of this lane's sample of the NEXT round
+    float2 xy_n = make_float2(0.f, 0.f);
+    float a_n = 0.f;
+    if (sub < LP) {
+      xy_n = __ldg(lp + sub);
+      a_n = __ldg(ap + sub);
+    }
+    for (int s0 = 0; s0 < LP; s0 += LPP) {
+      const int s = s0 + sub;
+      const float2 xy = xy_n;
+      const float a = a_n;
+      if (s + LPP < LP) {
+        xy_n = __ldg(lp + s + LPP);
+        a_n = __ldg(ap + s + LPP);
+      }
+      int off = 0, dx = 0, dy = 0;
+      float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+      if (s < LP) {
+        const int4 tb = s_tab[s];
+        const SampleTaps tp = make_sample_taps(xy.x, xy.y, tb.x, tb.y, tb.z, MD);
+        const float hy = 1.f - tp.ly, hx = 1.f - tp.lx;
+        off = tp.off; dx = tp.dx; dy = tp.dy;
+        w00 = tp.v00 ? hy * hx * a : 0.f;
+        w01 = tp.v01 ? hy * tp.lx * a : 0.f;
+        w10 = tp.v10 ? tp.ly * hx * a : 0.f;
+        w11 = tp.v11 ? tp.ly * tp.lx * a : 0.f;
+      }
 #pragma unroll
-        for (int i = 0; i < VE; ++i)
-          acc[i] = fmaf(w00, v00[i], fmaf(w01, v01[i], fmaf(w10, v10[i], fmaf(w11, v11[i], acc[i]))));
+      for (int j = 0; j < LPP; ++j) {
+        if (s0 + j < LP) {  // warp-uniform
+          const int o = __shfl_sync(0xffffffffu, off, j, LPP);
+          const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
+          const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
+          const float b00 = __shfl_sync(0xffffffffu, w00, j, LPP);
+          const float b01 = __shfl_sync(0xffffffffu, w01, j, LPP);
+          const float b10 = __shfl_sync(0xffffffffu, w10, j, LPP);
+          const float b11 = __shfl_sync(0xffffffffu, w11, j, LPP);
+          const T* p00 = vimg + o;
+          const T* p10 = p00 + oy;
+          float v00[VE], v01[VE], v10[VE], v11[VE];
+          CV::load(p00, v00);
+          CV::load(p00 + ox, v01);
+          CV::load(p10, v10);
+          CV::load(p10 + ox, v11);
+#pragma unroll
+          for (int i = 0; i < VE; ++i)
+            acc[i] = fmaf(b00, v00[i], fmaf(b01, v01[i], fmaf(b10, v10[i], fmaf(b11, v11[i], acc[i]))));
+        }
       }
     }
-    if (qvalid) Vec16<T>::store(out + pair * D + sub * VE, acc);
+    if (qvalid) CV::store_stream(out + pair * D + sub * VE, acc);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Backward, vector path.  grad_value is accumulated in fp32 (`gacc`: grad_value itself for fp32
-// values, the caller's workspace for bf16 values) with 128-bit vector reductions.
+// values, the caller's workspace for bf16 values) with 128-bit vector reductions.  The launcher
+// picks VB so that a lane owns 4 channels whenever it can: the LPP lanes of a pair then cover
+// whole 32-byte sectors with ONE red.v4 each, and the L2 -- which retires reductions per sector,
+// ~199 sectors/ns measured on B200 -- sees 4 sector operations per 128-byte tap instead of 8.  Per sample the
+// channel lanes only form the four dot products <grad_out, corner value>; the lane that owns the
+// sample combines them into grad_attn and grad_loc (cuh:128-163) and writes them coalesced.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LPP>
+template <typename T, int LPP, int VB>
 __global__ void __launch_bounds__(kBwdVecThreads, 1)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, const T* __restrict__ grad_out,
                     float* __restrict__ gacc, float* __restrict__ grad_loc,
                     float* __restrict__ grad_attn, int N, int S, int M, int L, int Lq, int P) {
-  constexpr int VE = Vec16<T>::kElems;
+  using CV = ChanVec<T, VB>;
+  constexpr int VE = CV::kElems;
   constexpr int D = LPP * VE;
   constexpr int PPW = 32 / LPP;
-  __shared__ int sH[kMaxFastLevels], sW[kMaxFastLevels], sStart[kMaxFastLevels];
-  if (threadIdx.x < L) {
-    sH[threadIdx.x] = (int)shapes[2 * threadIdx.x];
-    sW[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
-    sStart[threadIdx.x] = (int)lsi[threadIdx.x];
-  }
+  __shared__ int4 s_tab[kMaxFastSamples];
+  fill_level_table(s_tab, shapes, lsi, L, P);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -244,67 +336,95 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     float* gimg = gacc + img_off;
 
     float go[VE];
-    Vec16<T>::load_stream(grad_out + pair * D + sub * VE, go);
+    CV::load_stream(grad_out + pair * D + sub * VE, go);
 
-    for (int l = 0; l < L; ++l) {
-      const int H = sH[l], W = sW[l];
-      const long long lvl_off = (long long)sStart[l] * MD;
-      const T* vl = vimg + lvl_off;
-      float* gl = gimg + lvl_off;
-      const int rowstep = W * MD;
-#pragma unroll 2
-      for (int p = 0; p < P; ++p) {
-        const float2 xy = __ldg(lp + l * P + p);
-        const float a = __ldg(ap + l * P + p);
-        Taps tp = make_taps(xy.x, xy.y, H, W, MD);
-        tp.m00 = tp.m00 && qvalid;
-        tp.m01 = tp.m01 && qvalid;
-        tp.m10 = tp.m10 && qvalid;
-        tp.m11 = tp.m11 && qvalid;
-        const T* p00 = vl + tp.off00;
-        float v00[VE], v01[VE], v10[VE], v11[VE];
-        Vec16<T>::load(p00, tp.m00, v00);
-        Vec16<T>::load(p00 + MD, tp.m01, v01);
-        Vec16<T>::load(p00 + rowstep, tp.m10, v10);
-        Vec16<T>::load(p00 + rowstep + MD, tp.m11, v11);
-
-        const float w00 = tp.hy * tp.hx, w01 = tp.hy * tp.lx;
-        const float w10 = tp.ly * tp.hx, w11 = tp.ly * tp.lx;
-        float s_val = 0.f, s_gh = 0.f, s_gw = 0.f;
+    float2 xy_n = make_float2(0.f, 0.f);
+    float a_n = 0.f;
+    if (sub < LP) {
+      xy_n = __ldg(lp + sub);
+      a_n = __ldg(ap + sub);
+    }
+    for (int s0 = 0; s0 < LP; s0 += LPP) {
+      const int s = s0 + sub;
+      const float2 xy = xy_n;
+      const float a = a_n;
+      if (s + LPP < LP) {
+        xy_n = __ldg(lp + s + LPP);
+        a_n = __ldg(ap + s + LPP);
+      }
+      // this lane's sample
+      int off = 0, dx = 0, dy = 0;
+      float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;   // bilinear weights, 0 for skipped corners
+      float ch00 = 0.f, ch01 = 0.f, ch10 = 0.f, ch11 = 0.f;  // d(val)/d(y) coefficients
+      float cw00 = 0.f, cw01 = 0.f, cw10 = 0.f, cw11 = 0.f;  // d(val)/d(x) coefficients
+      float Hf = 0.f, Wf = 0.f;
+      if (s < LP) {
+        const int4 tb = s_tab[s];
+        const SampleTaps tp = make_sample_taps(xy.x, xy.y, tb.x, tb.y, tb.z, MD);
+        const float hy = 1.f - tp.ly, hx = 1.f - tp.lx;
+        off = tp.off; dx = tp.dx; dy = tp.dy;
+        Hf = (float)tb.x; Wf = (float)tb.y;
+        // grad_h_weight = -hw*v1 - lw*v2 + hw*v3 + lw*v4 ; grad_w_weight = -hh*v1 + hh*v2 - lh*v3 + lh*v4
+        if (tp.v00) { w00 = hy * hx;       ch00 = -hx;    cw00 = -hy; }
+        if (tp.v01) { w01 = hy * tp.lx;    ch01 = -tp.lx; cw01 = hy; }
+        if (tp.v10) { w10 = tp.ly * hx;    ch10 = hx;     cw10 = -tp.ly; }
+        if (tp.v11) { w11 = tp.ly * tp.lx; ch11 = tp.lx;  cw11 = tp.ly; }
+      }
+      const float ae = qvalid ? a : 0.f;   // padded tail pairs scatter nothing
+      const float aw00 = w00 * ae, aw01 = w01 * ae, aw10 = w10 * ae, aw11 = w11 * ae;
+      float D00 = 0.f, D01 = 0.f, D10 = 0.f, D11 = 0.f;   // full dot products of MY sample
 #pragma unroll
-        for (int i = 0; i < VE; ++i) {
-          const float g = go[i];
-          const float val = fmaf(w00, v00[i], fmaf(w01, v01[i], fmaf(w10, v10[i], w11 * v11[i])));
-          // grad_h_weight = -hw*v1 - lw*v2 + hw*v3 + lw*v4 ; grad_w_weight = -hh*v1 + hh*v2 - lh*v3 + lh*v4
-          const float gh = fmaf(tp.hx, v10[i] - v00[i], tp.lx * (v11[i] - v01[i]));
-          const float gw = fmaf(tp.hy, v01[i] - v00[i], tp.ly * (v11[i] - v10[i]));
-          s_val = fmaf(g, val, s_val);
-          s_gh = fmaf(g, gh, s_gh);
-          s_gw = fmaf(g, gw, s_gw);
-        }
-        // grad_value taps: w_k * attn * grad_out  (cuh:118,130,139,148,157)
-        float* g00 = gl + tp.off00;
-        const float a00 = w00 * a, a01 = w01 * a, a10 = w10 * a, a11 = w11 * a;
+      for (int j = 0; j < LPP; ++j) {
+        if (s0 + j < LP) {  // warp-uniform
+          const int o = __shfl_sync(0xffffffffu, off, j, LPP);
+          const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
+          const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
+          const float b00 = __shfl_sync(0xffffffffu, aw00, j, LPP);
+          const float b01 = __shfl_sync(0xffffffffu, aw01, j, LPP);
+          const float b10 = __shfl_sync(0xffffffffu, aw10, j, LPP);
+          const float b11 = __shfl_sync(0xffffffffu, aw11, j, LPP);
+          const T* p00 = vimg + o;
+          const T* p10 = p00 + oy;
+          float v00[VE], v01[VE], v10[VE], v11[VE];
+          CV::load(p00, v00);
+          CV::load(p00 + ox, v01);
+          CV::load(p10, v10);
+          CV::load(p10 + ox, v11);
+          // grad_value taps: w_k * attn * grad_out  (cuh:118,130,139,148,157)
+          float* g00 = gimg + o;
+          float* g10 = g00 + oy;
 #pragma unroll
-        for (int i = 0; i < VE; i += 4) {
-          if (tp.m00) red_add_v4(g00 + i, a00 * go[i], a00 * go[i + 1], a00 * go[i + 2], a00 * go[i + 3]);
-          if (tp.m01) red_add_v4(g00 + MD + i, a01 * go[i], a01 * go[i + 1], a01 * go[i + 2], a01 * go[i + 3]);
-          if (tp.m10) red_add_v4(g00 + rowstep + i, a10 * go[i], a10 * go[i + 1], a10 * go[i + 2], a10 * go[i + 3]);
-          if (tp.m11) red_add_v4(g00 + rowstep + MD + i, a11 * go[i], a11 * go[i + 1], a11 * go[i + 2], a11 * go[i + 3]);
-        }
-        // reduce the three partial sums over the pair's LPP channel lanes
+          for (int i = 0; i < VE; i += 4) {
+            if (b00 != 0.f) red_add_v4(g00 + i, b00 * go[i], b00 * go[i + 1], b00 * go[i + 2], b00 * go[i + 3]);
+            if (b01 != 0.f) red_add_v4(g00 + ox + i, b01 * go[i], b01 * go[i + 1], b01 * go[i + 2], b01 * go[i + 3]);
+            if (b10 != 0.f) red_add_v4(g10 + i, b10 * go[i], b10 * go[i + 1], b10 * go[i + 2], b10 * go[i + 3]);
+            if (b11 != 0.f) red_add_v4(g10 + ox + i, b11 * go[i], b11 * go[i + 1], b11 * go[i + 2], b11 * go[i + 3]);
+          }
+          float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
 #pragma unroll
-        for (int o = LPP / 2; o > 0; o >>= 1) {
-          s_val += __shfl_xor_sync(0xffffffffu, s_val, o);
-          s_gh += __shfl_xor_sync(0xffffffffu, s_gh, o);
-          s_gw += __shfl_xor_sync(0xffffffffu, s_gw, o);
+          for (int i = 0; i < VE; ++i) {
+            d00 = fmaf(go[i], v00[i], d00);
+            d01 = fmaf(go[i], v01[i], d01);
+            d10 = fmaf(go[i], v10[i], d10);
+            d11 = fmaf(go[i], v11[i], d11);
+          }
+#pragma unroll
+          for (int w = LPP / 2; w > 0; w >>= 1) {
+            d00 += __shfl_xor_sync(0xffffffffu, d00, w);
+            d01 += __shfl_xor_sync(0xffffffffu, d01, w);
+            d10 += __shfl_xor_sync(0xffffffffu, d10, w);
+            d11 += __shfl_xor_sync(0xffffffffu, d11, w);
+          }
+          if (sub == j) { D00 = d00; D01 = d01; D10 = d10; D11 = d11; }
         }
-        if (sub == 0 && qvalid) {
-          const long long s = pair * LP + l * P + p;
-          grad_attn[s] = s_val;                                                     // cuh:161
-          reinterpret_cast<float2*>(grad_loc)[s] =
-              make_float2((float)W * s_gw * a, (float)H * s_gh * a);               // cuh:162-163
-        }
+      }
+      if (s < LP && qvalid) {
+        const float s_val = w00 * D00 + w01 * D01 + w10 * D10 + w11 * D11;
+        const float s_gh = ch00 * D00 + ch01 * D01 + ch10 * D10 + ch11 * D11;
+        const float s_gw = cw00 * D00 + cw01 * D01 + cw10 * D10 + cw11 * D11;
+        const long long si = pair * LP + s;
+        grad_attn[si] = s_val;                                                       // cuh:161
+        reinterpret_cast<float2*>(grad_loc)[si] = make_float2(Wf * s_gw * a, Hf * s_gh * a);  // cuh:162-163
       }
     }
   }
@@ -321,7 +441,7 @@ __global__ void msda_round_to_bf16_kernel(const float* __restrict__ src,
     const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    Vec16<__nv_bfloat16>::store(dst + 8 * i, v);
+    ChanVec<__nv_bfloat16, 16>::store_stream(dst + 8 * i, v);
   }
 }
 

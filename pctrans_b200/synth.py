@@ -79,3 +79,18 @@ def make_inputs(N: int, shapes: Sequence[Tuple[int, int]], M: int = 8, D: int = 
     else:
         raise ValueError(f"unknown regime {regime!r}")
     return value, spatial_shapes, lsi, loc.contiguous(), attn.contiguous()
+
+
+def nudge_off_grid(loc: torch.Tensor, shapes: Sequence[Tuple[int, int]], eps: float = 1e-3):
+    """Move sampling locations whose pixel coordinate ``loc*size - 0.5`` lies within ``eps`` of
+    an integer away from it.  The op is not differentiable w.r.t. the location on the pixel
+    grid (the bilinear cell changes there), so an fp32 and an fp64 evaluation of the same bits
+    may legitimately pick different cells; gradient parity tests use inputs off the grid."""
+    loc = loc.clone()
+    for lvl, (H, W) in enumerate(shapes):
+        for axis, size in ((0, W), (1, H)):
+            c = loc[:, :, :, lvl, :, axis].double() * size - 0.5
+            near = (c - c.round()).abs() < eps
+            loc[:, :, :, lvl, :, axis] = torch.where(
+                near, loc[:, :, :, lvl, :, axis] + 3.0 * eps / size, loc[:, :, :, lvl, :, axis])
+    return loc

@@ -44,7 +44,7 @@ def test_abi_scalar_entry_points_without_gpu():
     assert _cabi.kernel_family(32, 3, 4, torch.float32) == 1
     assert _cabi.kernel_family(16, 3, 4, torch.float32, backward=True) == 1
     assert _cabi.kernel_family(71, 3, 4, torch.float32) == 0
-    assert _cabi.kernel_family(32, 17, 4, torch.float32) == 0
+    assert _cabi.kernel_family(32, 33, 4, torch.float32) == 0   # L*P > 128 sample table
     # argument validation happens before any CUDA call
     assert lib.pct_msda_forward(None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 7, None) == 1003
     assert lib.pct_msda_forward(None, None, None, None, None, None, 1, 1, 0, 1, 1, 1, 1, 0, None) == 1002

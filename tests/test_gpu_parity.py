@@ -47,6 +47,8 @@ def check_case(value, shapes, lsi, loc, attn, grad_out, dtype, expect_family=Non
         grad_out = grad_out.bfloat16().float()
     if dtype != torch.float64:
         loc, attn = loc.float(), attn.float()
+    # gradients w.r.t. the location are undefined on the pixel grid: keep the test off it
+    loc = synth.nudge_off_grid(loc, [tuple(r) for r in shapes.tolist()])
     N, S, M, D = value.shape
     L, P = loc.shape[3], loc.shape[4]
     if expect_family is not None:
@@ -103,7 +105,7 @@ def test_golden_recipe_in_fp32_hits_vector_and_generic_kernels(golden_dir):
                    g["grad_out"].float(), torch.float32, expect_family=fam)
 
 
-@pytest.mark.parametrize("D", [4, 8, 16, 32, 64, 128])
+@pytest.mark.parametrize("D", [4, 8, 16, 32, 64, 128, 256])
 @pytest.mark.parametrize("regime", ["U", "O"])
 def test_vector_path_fp32_small(D, regime):
     shapes = ((7, 9), (4, 5), (2, 3))
@@ -113,7 +115,7 @@ def test_vector_path_fp32_small(D, regime):
     check_case(value, sh, lsi, loc, attn, g, torch.float32, expect_family=1)
 
 
-@pytest.mark.parametrize("D", [8, 16, 32, 64, 256])
+@pytest.mark.parametrize("D", [4, 8, 16, 32, 64, 128, 256])
 def test_vector_path_bf16_small(D):
     shapes = ((6, 11), (3, 6))
     value, sh, lsi, loc, attn = synth.make_inputs(2, shapes, M=8, D=D, P=4, regime="O",
@@ -190,6 +192,20 @@ def test_cfg1_against_reference_golden_subsample(golden_dir):
         err = np.abs(got - z[name]).max() / float(z[name + "_absmax"])
         # the fixture itself is the reference's fp32 result (error ~1e-6 of its own)
         assert err <= 2 * tol, (name, err)
+
+
+def test_fp32_oracle_same_cells_without_nudging():
+    """Against the oracle's literal-fp32 instantiation (coordinate rounded once, as cuh:290-291)
+    the kernels pick the same bilinear cell for every point, so no nudging is needed even on the
+    non-power-of-two BBBC pyramid."""
+    value, sh, lsi, loc, attn = synth.make_inputs(2, synth.BBBC_520x696, M=8, D=32, P=4,
+                                                  regime="R", seed=0)
+    g = torch.randn(2, value.shape[1], 256, generator=torch.Generator().manual_seed(1))
+    out, gv, gl, ga = run_gpu(value, sh, lsi, loc, attn, g, torch.float32)
+    ref_out = oracle.forward_c(value, sh, lsi, loc, attn, dtype=np.float32)
+    ref_gv, ref_gl, ref_ga = oracle.backward_c(value, sh, lsi, loc, attn, g, dtype=np.float32)
+    assert rel(out, ref_out) <= 1e-5
+    assert rel(gv, ref_gv) <= 1e-4 and rel(gl, ref_gl) <= 1e-4 and rel(ga, ref_ga) <= 1e-4
 
 
 def test_cfg3_full_size_batch16():
