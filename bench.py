@@ -70,6 +70,27 @@ def bytes_per_query(D: int, L: int, P: int, val_bytes: int):
     return fwd, bwd
 
 
+def make_config(args, pyramid, pyr_name, world):
+    """`config` shared by both arms (the driver compares the lines of the two arms)."""
+    L = len(pyramid)
+    D = args.d_model // M_HEADS
+    S = sum(h * w for h, w in pyramid)
+    val_bytes = 4 if args.dtype == "f32" else 2
+    b_fwd, b_bwd = bytes_per_query(D, L, N_POINTS, val_bytes)
+    return {
+        "workload": f"MSDeformAttnFunction fwd+bwd (BASELINE config 3 shape), {pyr_name} "
+                    f"pyramid, batch {args.batch}/GPU, d_model {args.d_model}, {M_HEADS} heads, "
+                    f"{L} levels, {N_POINTS} points, {args.regime} locations",
+        "pyramid": [list(p) for p in pyramid], "batch_per_gpu": args.batch,
+        "global_batch": args.batch * world, "queries_per_step_per_gpu": args.batch * S,
+        "head_dim": D, "regime": args.regime,
+        "parallelism": f"batch-sharded x{world}" + (
+            f", NCCL all-reduce of {PARAM_GRAD_FLOATS} fp32 param grads per step" if world > 1 else ""),
+        "l2": "no flush: one step touches "
+              f"{(b_fwd + b_bwd) * args.batch * S / 1e6:.0f} MB of distinct tensors (> 126 MB L2)",
+    }
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -77,6 +98,21 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(pyr_name: str, batch: int, dtype: str, which: str):
+    """DRAM bytes per launch of the forward / backward kernel from the committed ncu --set full
+    capture of the same shape (profiles/*_ncu_dram_traffic.json), or None."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_dram_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                entry = json.load(f).get(f"{pyr_name}/{batch}/{dtype}")
+            if entry:
+                return float(entry[which]["dram_bytes"])
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -208,10 +244,8 @@ def run_reference_arm(args, pyramid, pyr_name, D):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"MSDeformAttn fwd+bwd, {pyr_name} pyramid, d_model {D * M_HEADS}, "
-                               f"{M_HEADS} heads, 3 levels, {N_POINTS} points, host CPU",
-                   "pyramid": [list(p) for p in pyramid], "regime": args.regime,
-                   "images_per_step": n_images},
+        "config": dict(make_config(args, pyramid, pyr_name, max(1, args.gpus)),
+                       cpu_sample_images_per_step=n_images),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -356,7 +390,8 @@ def main():
     dom_gbs = bwd_gbs if dominant == "backward" else fwd_gbs
     roofline = {"bound": "hbm", "kernel": f"msda_{'bwd' if dominant == 'backward' else 'fwd'}_vec_kernel",
                 "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": ncu_traffic(pyr_name, N, args.dtype, dominant) if args.regime == "R" else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_query": b_bwd if dominant == "backward" else b_fwd,
                 "kernel_ms": bwd_ms if dominant == "backward" else fwd_ms,
                 "note": "CUDA events around the C-ABI call on the launching stream (backward "
@@ -373,17 +408,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {
-                "workload": f"MSDeformAttnFunction fwd+bwd (BASELINE config 3 shape), {pyr_name} "
-                            f"pyramid, batch {N}/GPU, d_model {args.d_model}, {M_HEADS} heads, "
-                            f"{L} levels, {N_POINTS} points, {args.regime} locations",
-                "pyramid": [list(p) for p in pyramid], "batch_per_gpu": N, "global_batch": N * world,
-                "queries_per_step_per_gpu": queries_per_step, "head_dim": D, "regime": args.regime,
-                "parallelism": f"batch-sharded x{world}" + (
-                    f", NCCL all-reduce of {PARAM_GRAD_FLOATS} fp32 param grads per step" if world > 1 else ""),
-                "l2": "no flush: one step touches "
-                      f"{(b_fwd + b_bwd) * queries_per_step / 1e6:.0f} MB of distinct tensors (> 126 MB L2)",
-            },
+            "config": make_config(args, pyramid, pyr_name, world),
             "roofline": roofline,
             "forward": {"ms": fwd_ms, "queries_per_s": queries_per_step / (fwd_ms * 1e-3),
                         "algorithmic_gbs": fwd_gbs, "frac": fwd_gbs / peak},

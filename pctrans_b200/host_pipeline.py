@@ -29,7 +29,7 @@ class HostPipeline:
             return
         N, S, M, D = value.shape
         Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
-        c = self.chunk_images or max(1, min(N, -(-N // 4)))
+        c = self.chunk_images or max(1, N // 8)
         self._c = c
         dev, dt = self.device, self.dtype
         f32 = torch.float32
