@@ -1,0 +1,129 @@
+"""The callers of the op (pixel-decoder encoder, pctrans_b200/encoder.py) -- BASELINE configs 2
+and 4.  The same module weights are run twice: once through the CUDA op and once with the op
+replaced by the oracle's grid_sample port (monkeypatched in the TEST only; the product has no
+such switch)."""
+import pytest
+import torch
+
+from oracle import msda_oracle as oracle
+from pctrans_b200 import encoder as enc
+from pctrans_b200.modules import ms_deform_attn as mod_file
+
+
+class _OracleFunction:
+    """Stands in for MSDeformAttnFunction inside tests: same call signature, oracle arithmetic."""
+
+    @staticmethod
+    def apply(value, shapes, lsi, loc, attn, im2col_step):
+        return oracle.core_grid_sample(value, shapes, loc, attn)
+
+
+def _features(n, sizes, chans=(256, 512, 1024, 2048), seed=0, device="cpu"):
+    g = torch.Generator().manual_seed(seed)
+    return {f"res{i + 2}": torch.randn(n, c, h, w, generator=g).to(device)
+            for i, (c, (h, w)) in enumerate(zip(chans, sizes))}
+
+
+def _decoder(conv_dim, seed=0, layers=6):
+    torch.manual_seed(seed)
+    return enc.MSDeformAttnPixelDecoder(
+        {"res2": (256, 4), "res3": (512, 8), "res4": (1024, 16), "res5": (2048, 32)},
+        conv_dim=conv_dim, mask_dim=conv_dim, transformer_enc_layers=layers, transformer_dropout=0.0)
+
+
+def test_state_dict_keys_match_reference_layout():
+    dec = _decoder(128, layers=2)
+    keys = set(dec.state_dict())
+    for k in ("transformer.level_embed",
+              "transformer.encoder.layers.1.self_attn.sampling_offsets.bias",
+              "transformer.encoder.layers.0.self_attn.value_proj.weight",
+              "transformer.encoder.layers.0.norm1.weight", "transformer.encoder.layers.0.linear1.weight",
+              "transformer.encoder.layers.0.linear2.bias", "transformer.encoder.layers.0.norm2.bias",
+              "input_proj.0.0.weight", "input_proj.2.1.bias", "adapter_1.weight",
+              "adapter_1.norm.weight", "layer_1.weight", "layer_1.norm.bias"):
+        assert k in keys, k
+    # d256 encoder parameter count quoted in SURVEY.md 2a (4 393 920 incl. level_embed)
+    assert sum(p.numel() for p in _decoder(256).transformer.parameters()) == 4_393_920
+
+
+def test_decoder_runs_on_cpu_through_oracle(monkeypatch):
+    """Host logic only (no GPU): shapes, level order low->high resolution, FPN output grid."""
+    monkeypatch.setattr(mod_file, "MSDeformAttnFunction", _OracleFunction)
+    dec = _decoder(64, layers=1).eval()
+    feats = _features(1, ((32, 32), (16, 16), (8, 8), (4, 4)))
+    with torch.no_grad():
+        mask_feat, lowest, multi = dec.forward_features(feats)
+        srcs = [dec.input_proj[i](feats[f]) for i, f in enumerate(("res5", "res4", "res3"))]
+        pos = [dec.pe_layer(feats[f]) for f in ("res5", "res4", "res3")]
+        memory, shapes, lsi = dec.transformer(srcs, pos)
+    assert shapes.tolist() == [[4, 4], [8, 8], [16, 16]] and lsi.tolist() == [0, 16, 80]
+    assert memory.shape == (1, 336, 64)
+    assert lowest.shape == (1, 64, 4, 4) and mask_feat.shape == (1, 64, 16, 16)
+    assert [m.shape[-1] for m in multi] == [4, 8, 16]
+    ref = enc.MSDeformAttnTransformerEncoder.get_reference_points(
+        [(2, 3)], torch.ones(1, 1, 2), "cpu")
+    assert torch.allclose(ref[0, 0, 0], torch.tensor([0.5 / 3, 0.25]))
+
+
+def test_module_without_cuda_fails_loudly():
+    dec = _decoder(64, layers=1).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dec.forward_features(_features(1, ((16, 16), (8, 8), (4, 4), (2, 2))))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("conv_dim", [256, 128])
+def test_config2_decoder_forward_matches_oracle(monkeypatch, conv_dim):
+    """BASELINE config 2: pixel-decoder forward (inference), batch 8, 512x512 pyramid; the d128
+    variant is PCTrans's real CONVS_DIM (head dim 16)."""
+    dev = "cuda:0"
+    dec = _decoder(conv_dim).to(dev).eval()
+    feats = _features(8, ((128, 128), (64, 64), (32, 32), (16, 16)), device=dev)
+    with torch.no_grad():
+        got = dec.forward_features(feats)
+        srcs = [dec.input_proj[i](feats[f]) for i, f in enumerate(("res5", "res4", "res3"))]
+        pos = [dec.pe_layer(feats[f]) for f in ("res5", "res4", "res3")]
+        mem = dec.transformer(srcs, pos)[0]
+        monkeypatch.setattr(mod_file, "MSDeformAttnFunction", _OracleFunction)
+        want = dec.forward_features(feats)
+        mem_ref = dec.transformer(srcs, pos)[0]
+    assert mem.shape == (8, 5376, conv_dim)
+    err = float((mem - mem_ref).abs().max() / mem_ref.abs().max())
+    assert err <= 1e-5, err            # accumulates over 6 layers
+    for a, b in zip((got[0], got[1], *got[2]), (want[0], want[1], *want[2])):
+        assert float((a - b).abs().max() / b.abs().max()) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_config4_bbbc_encoder_forward_backward(monkeypatch):
+    """BASELINE config 4 shape (520x696 pyramid, 6 encoder layers, fwd+bwd), small batch for the
+    oracle leg; parameter gradients of the two legs must agree."""
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    model = enc.MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder_layers=6,
+                                                   dim_feedforward=1024, dropout=0.0,
+                                                   num_feature_levels=3).to(dev)
+    g = torch.Generator().manual_seed(3)
+    sizes = ((17, 22), (33, 44), (65, 87))
+    srcs = [torch.randn(2, 256, h, w, generator=g).to(dev) for h, w in sizes]
+    pe = enc.PositionEmbeddingSine(128, normalize=True)
+    pos = [pe(s) for s in srcs]
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        mem, shapes, _ = model(srcs, pos)
+        mem.square().mean().backward()
+        return mem.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+    mem, grads = run()
+    monkeypatch.setattr(mod_file, "MSDeformAttnFunction", _OracleFunction)
+    mem_ref, grads_ref = run()
+    assert mem.shape == (2, 7481, 256)
+    assert float((mem - mem_ref).abs().max() / mem_ref.abs().max()) <= 1e-5
+    for k in grads:
+        scale = float(grads_ref[k].abs().max())
+        if scale == 0.0:
+            assert float(grads[k].abs().max()) == 0.0
+            continue
+        err = float((grads[k] - grads_ref[k]).abs().max()) / scale
+        assert err <= 1e-3, (k, err)
