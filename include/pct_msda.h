@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define PCT_MSDA_ABI_VERSION 1
+#define PCT_MSDA_ABI_VERSION 2
 
 /* value_dtype */
 #define PCT_MSDA_F32 0
@@ -61,6 +61,7 @@ extern "C" {
 #define PCT_MSDA_E_MISALIGNED 1004
 #define PCT_MSDA_E_WORKSPACE 1005
 #define PCT_MSDA_E_TOO_LARGE 1006
+#define PCT_MSDA_E_UNSUPPORTED 1007
 
 /* flags for the *_ex entry points (0 = library default; used by the tuning harness) */
 #define PCT_MSDA_FLAG_FORCE_GENERIC 0x1u /* use the any-D scalar kernels even when a vector path fits */
@@ -118,6 +119,36 @@ int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
                          int spatial_size, int num_heads, int channels, int num_levels,
                          int num_query, int num_point, int value_dtype, void* workspace,
                          size_t workspace_bytes, void* cuda_stream, unsigned flags);
+
+/*
+ * Fused prologue: the same op, fed with what the module's Linears
+ * produce instead of materialised locations / weights.  Replaces, together with the kernels,
+ * OPS/modules/ms_deform_attn.py:104 (softmax over L*P) and :106-112 (location arithmetic):
+ *   reference_points (N, Lq, L, ref_dim) fp32, ref_dim = 2 (points) or 4 (boxes cx,cy,w,h)
+ *   sampling_offsets (N, Lq, M, L, P, 2) fp32 raw     attn_logits (N, Lq, M, L*P) fp32 raw
+ *   loc = ref + off / (W_l, H_l)              (ref_dim 2)
+ *   loc = ref.xy + off / P * ref.wh * 0.5     (ref_dim 4)        attn = softmax(logits)
+ * value_dtype F32 or BF16.  Only shapes served by the vector kernels are accepted
+ * (pct_msda_kernel_family == 1, S > 0); otherwise PCT_MSDA_E_UNSUPPORTED is returned and the
+ * caller composes softmax / locations itself and calls pct_msda_forward.
+ * The backward writes d/d(sampling_offsets) and d/d(attn_logits); reference points get no
+ * gradient from these entry points.
+ */
+int pct_msda_fused_forward(const void* value, const int64_t* spatial_shapes,
+                           const int64_t* level_start_index, const void* reference_points,
+                           int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                           void* output, int batch, int spatial_size, int num_heads, int channels,
+                           int num_levels, int num_query, int num_point, int value_dtype,
+                           void* cuda_stream);
+
+int pct_msda_fused_backward(const void* value, const int64_t* spatial_shapes,
+                            const int64_t* level_start_index, const void* reference_points,
+                            int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                            const void* grad_output, void* grad_value, void* grad_offsets,
+                            void* grad_logits, int batch, int spatial_size, int num_heads,
+                            int channels, int num_levels, int num_query, int num_point,
+                            int value_dtype, void* workspace, size_t workspace_bytes,
+                            void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -14,8 +14,10 @@ import threading
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "_build", "libpctrans_msda.so")
-ABI_VERSION = 1
+# PCTRANS_MSDA_LIB selects another build of the SAME C ABI (the bounds-checking debug library in
+# tests); it is not a fallback: a missing file is still an ImportError.
+LIB_PATH = os.environ.get("PCTRANS_MSDA_LIB") or os.path.join(_PKG_DIR, "_build", "libpctrans_msda.so")
+ABI_VERSION = 2
 
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}
 
@@ -23,7 +25,9 @@ EXPORTS = (
     "pct_msda_abi_version", "pct_msda_error_string", "pct_msda_launch_count",
     "pct_msda_kernel_family", "pct_msda_forward", "pct_msda_forward_ex",
     "pct_msda_backward_workspace_bytes", "pct_msda_backward", "pct_msda_backward_ex",
+    "pct_msda_fused_forward", "pct_msda_fused_backward",
 )
+E_UNSUPPORTED = 1007
 
 _lib = None
 _lock = threading.Lock()
@@ -67,6 +71,10 @@ def load():
         lib.pct_msda_backward.argtypes = bwd_args
         lib.pct_msda_backward_ex.restype = i32
         lib.pct_msda_backward_ex.argtypes = bwd_args + [u32]
+        lib.pct_msda_fused_forward.restype = i32
+        lib.pct_msda_fused_forward.argtypes = [vp] * 4 + [i32] + [vp] * 3 + [i32] * 8 + [vp]
+        lib.pct_msda_fused_backward.restype = i32
+        lib.pct_msda_fused_backward.argtypes = [vp] * 4 + [i32] + [vp] * 6 + [i32] * 8 + [vp, sz, vp]
         got = lib.pct_msda_abi_version()
         if got != ABI_VERSION:
             raise ImportError(f"{LIB_PATH}: ABI version {got}, expected {ABI_VERSION}; rebuild")
@@ -141,3 +149,51 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
             _stream_ptr(value.device), flags)
     check(rc, "pct_msda_backward")
     return grad_value, grad_loc, grad_attn
+
+
+def fused_forward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                  attn_logits, out=None):
+    """Fused-prologue forward (softmax + location arithmetic inside the kernel).  Returns the
+    output, or None when the shape is not served by the fused kernels (caller uses ``forward``)."""
+    lib = load()
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_offsets.shape[1], sampling_offsets.shape[4]
+    if out is None:
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device_of(value):
+        rc = lib.pct_msda_fused_forward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            reference_points.data_ptr(), reference_points.shape[-1], sampling_offsets.data_ptr(),
+            attn_logits.data_ptr(), out.data_ptr(), N, S, M, D, L, Lq, P,
+            DTYPE_CODES[value.dtype], _stream_ptr(value.device))
+    if rc == E_UNSUPPORTED:
+        return None
+    check(rc, "pct_msda_fused_forward")
+    return out
+
+
+def fused_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                   attn_logits, grad_output, workspace=None):
+    """Returns (grad_value, grad_sampling_offsets, grad_attn_logits)."""
+    lib = load()
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_offsets.shape[1], sampling_offsets.shape[4]
+    code = DTYPE_CODES[value.dtype]
+    grad_value = torch.empty_like(value)
+    grad_off = torch.empty_like(sampling_offsets)
+    grad_logits = torch.empty_like(attn_logits)
+    ws_bytes = int(lib.pct_msda_backward_workspace_bytes(N, S, M, D, code))
+    ws = workspace
+    if ws_bytes and (ws is None or ws.numel() < ws_bytes):
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device)
+    with torch.cuda.device_of(value):
+        rc = lib.pct_msda_fused_backward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            reference_points.data_ptr(), reference_points.shape[-1], sampling_offsets.data_ptr(),
+            attn_logits.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
+            grad_off.data_ptr(), grad_logits.data_ptr(), N, S, M, D, L, Lq, P, code,
+            ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(value.device))
+    check(rc, "pct_msda_fused_backward")
+    return grad_value, grad_off, grad_logits

@@ -40,8 +40,25 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA sources for sm_100a.  Returns the path of the shared library."""
+DEBUG_LIB_PATH = os.path.join(OUT_DIR, "libpctrans_msda_dbg.so")
+
+
+def build_library(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a.  Returns the path of the shared library.
+    ``debug=True`` builds libpctrans_msda_dbg.so with -DPCT_MSDA_BOUNDS_CHECK (tap addresses
+    checked in-kernel; used by tests/test_gpu_bounds.py through PCTRANS_MSDA_LIB)."""
+    if debug:
+        os.makedirs(OUT_DIR, exist_ok=True)
+        if not force and os.path.exists(DEBUG_LIB_PATH) and all(
+                os.path.getmtime(os.path.join(CSRC, d)) <= os.path.getmtime(DEBUG_LIB_PATH) for d in DEPS):
+            return DEBUG_LIB_PATH
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-DPCT_MSDA_BOUNDS_CHECK", "-o", DEBUG_LIB_PATH] + \
+            [os.path.join(CSRC, s) for s in SOURCES] + ["-ccbin", "/usr/bin/g++"]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stdout)
+            raise RuntimeError("nvcc failed building the bounds-check library")
+        return DEBUG_LIB_PATH
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)

@@ -104,69 +104,72 @@ LaunchShape vec_launch_shape(long long n_tasks, int sm_count, unsigned flags, in
   return s;
 }
 
-template <typename T, int LPP, int VB>
+template <typename T, int LPP, int VB, bool FUSED>
 int launch_fwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                    const void* attn, void* out, const Dims& d, int sm_count, cudaStream_t st,
-                   unsigned flags) {
+                   unsigned flags, pct::FusedRef fr) {
   constexpr int PPW = 32 / LPP;
   const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kVecThreads);
-  pct::msda_fwd_vec_kernel<T, LPP, VB><<<ls.grid, ls.block, 0, st>>>(
+  pct::msda_fwd_vec_kernel<T, LPP, VB, FUSED><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (T*)out, d.N, d.S, d.M,
-      d.L, d.Lq, d.P);
+      d.L, d.Lq, d.P, fr);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
 
-template <typename T, int LPP, int VB>
+template <typename T, int LPP, int VB, bool FUSED>
 int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                    const void* attn, const void* grad_out, float* gacc, void* grad_loc,
-                   void* grad_attn, const Dims& d, int sm_count, cudaStream_t st, unsigned flags) {
+                   void* grad_attn, const Dims& d, int sm_count, cudaStream_t st, unsigned flags,
+                   pct::FusedRef fr) {
   constexpr int PPW = 32 / LPP;
   const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kBwdVecThreads);
-  pct::msda_bwd_vec_kernel<T, LPP, VB><<<ls.grid, ls.block, 0, st>>>(
+  pct::msda_bwd_vec_kernel<T, LPP, VB, FUSED><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
-      gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P);
+      gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, fr);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
 
-#define PCT_LANE_CASES(LAUNCH, T, VB)                                                    \
+#define PCT_LANE_CASES(LAUNCH, T, VB, FUSED)                                             \
   switch (plan.lanes) {                                                                 \
-    case 1: return LAUNCH<T, 1, VB>;                                                    \
-    case 2: return LAUNCH<T, 2, VB>;                                                    \
-    case 4: return LAUNCH<T, 4, VB>;                                                    \
-    case 8: return LAUNCH<T, 8, VB>;                                                    \
-    case 16: return LAUNCH<T, 16, VB>;                                                  \
-    case 32: return LAUNCH<T, 32, VB>;                                                  \
+    case 1: return LAUNCH<T, 1, VB, FUSED>;                                             \
+    case 2: return LAUNCH<T, 2, VB, FUSED>;                                             \
+    case 4: return LAUNCH<T, 4, VB, FUSED>;                                             \
+    case 8: return LAUNCH<T, 8, VB, FUSED>;                                             \
+    case 16: return LAUNCH<T, 16, VB, FUSED>;                                           \
+    case 32: return LAUNCH<T, 32, VB, FUSED>;                                           \
   }                                                                                     \
   return nullptr;
 
 using FwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
-                            void*, const Dims&, int, cudaStream_t, unsigned);
+                            void*, const Dims&, int, cudaStream_t, unsigned, pct::FusedRef);
 using BwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
                             const void*, float*, void*, void*, const Dims&, int, cudaStream_t,
-                            unsigned);
+                            unsigned, pct::FusedRef);
 
+template <bool FUSED>
 FwdLauncher pick_fwd(const VecPlan& plan, int dtype) {
   if (dtype == PCT_MSDA_F32) {
-    if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, float, 16) }
-    if (plan.vb == 32 && plan.lanes == 32) return launch_fwd_vec<float, 32, 32>;
+    if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, float, 16, FUSED) }
+    if (plan.vb == 32 && plan.lanes == 32) return launch_fwd_vec<float, 32, 32, FUSED>;
   } else {
-    if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, __nv_bfloat16, 16) }
-    if (plan.vb == 8 && plan.lanes == 1) return launch_fwd_vec<__nv_bfloat16, 1, 8>;
+    if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, __nv_bfloat16, 16, FUSED) }
+    if (plan.vb == 8 && plan.lanes == 1) return launch_fwd_vec<__nv_bfloat16, 1, 8, FUSED>;
   }
   return nullptr;
 }
 
+template <bool FUSED>
 BwdLauncher pick_bwd(const VecPlan& plan, int dtype) {
   if (dtype == PCT_MSDA_F32) {
-    if (plan.vb == 16) { PCT_LANE_CASES(launch_bwd_vec, float, 16) }
-    if (plan.vb == 32 && plan.lanes == 32) return launch_bwd_vec<float, 32, 32>;
+    if (plan.vb == 16) { PCT_LANE_CASES(launch_bwd_vec, float, 16, FUSED) }
+    if (plan.vb == 32 && plan.lanes == 32) return launch_bwd_vec<float, 32, 32, FUSED>;
   } else {
-    if (plan.vb == 8) { PCT_LANE_CASES(launch_bwd_vec, __nv_bfloat16, 8) }
-    if (plan.vb == 16 && plan.lanes == 32) return launch_bwd_vec<__nv_bfloat16, 32, 16>;
+    if (plan.vb == 8) { PCT_LANE_CASES(launch_bwd_vec, __nv_bfloat16, 8, FUSED) }
+    if (plan.vb == 16 && plan.lanes == 32) return launch_bwd_vec<__nv_bfloat16, 32, 16, FUSED>;
   }
   return nullptr;
 }
@@ -256,6 +259,7 @@ const char* pct_msda_error_string(int code) {
     case PCT_MSDA_E_MISALIGNED: return "pct_msda: buffer is not aligned to its element size";
     case PCT_MSDA_E_WORKSPACE: return "pct_msda: workspace missing or too small";
     case PCT_MSDA_E_TOO_LARGE: return "pct_msda: tensor too large";
+    case PCT_MSDA_E_UNSUPPORTED: return "pct_msda: shape / dtype not supported by the fused entry points";
     default:
       if (code > 0 && code < 1000) return cudaGetErrorString((cudaError_t)code);
       return "pct_msda: unknown error code";
@@ -267,11 +271,18 @@ int pct_msda_kernel_family(int channels, int num_levels, int num_point, int valu
   return vec_plan(channels, num_levels, num_point, value_dtype, backward != 0).lanes > 0 ? 1 : 0;
 }
 
-int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
-                        const int64_t* level_start_index, const void* sampling_loc,
-                        const void* attn_weight, void* output, int batch, int spatial_size,
-                        int num_heads, int channels, int num_levels, int num_query,
-                        int num_point, int value_dtype, void* cuda_stream, unsigned flags) {
+}  // extern "C"
+
+namespace {
+
+// Shared by the plain and the fused entry points.  fused: `sampling_loc` holds raw offsets,
+// `attn_weight` raw logits, fr the reference points.
+int forward_impl(const void* value, const int64_t* spatial_shapes,
+                 const int64_t* level_start_index, const void* sampling_loc,
+                 const void* attn_weight, void* output, int batch, int spatial_size,
+                 int num_heads, int channels, int num_levels, int num_query, int num_point,
+                 int value_dtype, void* cuda_stream, unsigned flags, pct::FusedRef fr) {
+  const bool fused = fr.ref != nullptr;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   int rc = check_dims(d, value_dtype);
   if (rc) return rc;
@@ -293,9 +304,12 @@ int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
     return (int)cudaMemsetAsync(output, 0, (size_t)d.N * d.Lq * d.M * d.D * es, st);
   }
   const VecPlan vp = vec_eligible(d, value_dtype, flags, value, output, nullptr, sampling_loc, attn_weight);
-  if (FwdLauncher fn = vp.lanes > 0 ? pick_fwd(vp, value_dtype) : nullptr)
+  if (FwdLauncher fn = vp.lanes == 0 ? nullptr
+                       : fused       ? pick_fwd<true>(vp, value_dtype)
+                                     : pick_fwd<false>(vp, value_dtype))
     return fn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, sm_count,
-              st, flags);
+              st, flags, fr);
+  if (fused) return PCT_MSDA_E_UNSUPPORTED;  // the fused prologue exists on the vector path only
   switch (value_dtype) {
     case PCT_MSDA_F32:
       return launch_fwd_generic<float, float>(value, spatial_shapes, level_start_index, sampling_loc,
@@ -307,6 +321,36 @@ int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
       return launch_fwd_generic<double, double>(value, spatial_shapes, level_start_index,
                                                 sampling_loc, attn_weight, output, d, sm_count, st);
   }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
+                        const int64_t* level_start_index, const void* sampling_loc,
+                        const void* attn_weight, void* output, int batch, int spatial_size,
+                        int num_heads, int channels, int num_levels, int num_query,
+                        int num_point, int value_dtype, void* cuda_stream, unsigned flags) {
+  return forward_impl(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output,
+                      batch, spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                      value_dtype, cuda_stream, flags, pct::FusedRef{nullptr, 0});
+}
+
+int pct_msda_fused_forward(const void* value, const int64_t* spatial_shapes,
+                           const int64_t* level_start_index, const void* reference_points,
+                           int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                           void* output, int batch, int spatial_size, int num_heads, int channels,
+                           int num_levels, int num_query, int num_point, int value_dtype,
+                           void* cuda_stream) {
+  if (ref_dim != 2 && ref_dim != 4) return PCT_MSDA_E_BAD_SHAPE;
+  if ((long long)batch * num_query > 0 && !reference_points) return PCT_MSDA_E_NULL_POINTER;
+  if (!aligned(reference_points, ref_dim == 2 ? 8 : 16)) return PCT_MSDA_E_MISALIGNED;
+  if (value_dtype == PCT_MSDA_F64) return PCT_MSDA_E_UNSUPPORTED;
+  return forward_impl(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                      output, batch, spatial_size, num_heads, channels, num_levels, num_query,
+                      num_point, value_dtype, cuda_stream, 0u,
+                      pct::FusedRef{(const float*)reference_points, ref_dim});
 }
 
 int pct_msda_forward(const void* value, const int64_t* spatial_shapes,
@@ -326,13 +370,18 @@ size_t pct_msda_backward_workspace_bytes(int batch, int spatial_size, int num_he
   return (size_t)batch * spatial_size * num_heads * channels * sizeof(float);
 }
 
-int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
-                         const int64_t* level_start_index, const void* sampling_loc,
-                         const void* attn_weight, const void* grad_output, void* grad_value,
-                         void* grad_sampling_loc, void* grad_attn_weight, int batch,
-                         int spatial_size, int num_heads, int channels, int num_levels,
-                         int num_query, int num_point, int value_dtype, void* workspace,
-                         size_t workspace_bytes, void* cuda_stream, unsigned flags) {
+}  // extern "C"
+
+namespace {
+
+int backward_impl(const void* value, const int64_t* spatial_shapes,
+                  const int64_t* level_start_index, const void* sampling_loc,
+                  const void* attn_weight, const void* grad_output, void* grad_value,
+                  void* grad_sampling_loc, void* grad_attn_weight, int batch, int spatial_size,
+                  int num_heads, int channels, int num_levels, int num_query, int num_point,
+                  int value_dtype, void* workspace, size_t workspace_bytes, void* cuda_stream,
+                  unsigned flags, pct::FusedRef fr) {
+  const bool fused = fr.ref != nullptr;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   int rc = check_dims(d, value_dtype);
   if (rc) return rc;
@@ -383,9 +432,13 @@ int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
                          ? vec_eligible(d, value_dtype, flags, value, grad_output, acc_image,
                                         sampling_loc, attn_weight)
                          : VecPlan{};
-  if (BwdLauncher fn = vp.lanes > 0 ? pick_bwd(vp, value_dtype) : nullptr) {
+  if (BwdLauncher fn = vp.lanes == 0 ? nullptr
+                       : fused       ? pick_bwd<true>(vp, value_dtype)
+                                     : pick_bwd<false>(vp, value_dtype)) {
     rc = fn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-            (float*)acc_image, grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags);
+            (float*)acc_image, grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags, fr);
+  } else if (fused) {
+    return PCT_MSDA_E_UNSUPPORTED;
   } else {
     switch (value_dtype) {
       case PCT_MSDA_F32:
@@ -412,6 +465,44 @@ int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
   if (value_dtype == PCT_MSDA_BF16)
     return round_workspace_to_bf16((const float*)workspace, grad_value, n_value, sm_count, st);
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
+                         const int64_t* level_start_index, const void* sampling_loc,
+                         const void* attn_weight, const void* grad_output, void* grad_value,
+                         void* grad_sampling_loc, void* grad_attn_weight, int batch,
+                         int spatial_size, int num_heads, int channels, int num_levels,
+                         int num_query, int num_point, int value_dtype, void* workspace,
+                         size_t workspace_bytes, void* cuda_stream, unsigned flags) {
+  return backward_impl(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                       grad_output, grad_value, grad_sampling_loc, grad_attn_weight, batch,
+                       spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                       value_dtype, workspace, workspace_bytes, cuda_stream, flags,
+                       pct::FusedRef{nullptr, 0});
+}
+
+int pct_msda_fused_backward(const void* value, const int64_t* spatial_shapes,
+                            const int64_t* level_start_index, const void* reference_points,
+                            int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                            const void* grad_output, void* grad_value, void* grad_offsets,
+                            void* grad_logits, int batch, int spatial_size, int num_heads,
+                            int channels, int num_levels, int num_query, int num_point,
+                            int value_dtype, void* workspace, size_t workspace_bytes,
+                            void* cuda_stream) {
+  if (ref_dim != 2 && ref_dim != 4) return PCT_MSDA_E_BAD_SHAPE;
+  if ((long long)batch * num_query > 0 && !reference_points) return PCT_MSDA_E_NULL_POINTER;
+  if (!aligned(reference_points, ref_dim == 2 ? 8 : 16)) return PCT_MSDA_E_MISALIGNED;
+  if (value_dtype == PCT_MSDA_F64) return PCT_MSDA_E_UNSUPPORTED;
+  if ((long long)batch * spatial_size == 0) return PCT_MSDA_E_UNSUPPORTED;
+  return backward_impl(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                       grad_output, grad_value, grad_offsets, grad_logits, batch, spatial_size,
+                       num_heads, channels, num_levels, num_query, num_point, value_dtype,
+                       workspace, workspace_bytes, cuda_stream, 0u,
+                       pct::FusedRef{(const float*)reference_points, ref_dim});
 }
 
 int pct_msda_backward(const void* value, const int64_t* spatial_shapes,

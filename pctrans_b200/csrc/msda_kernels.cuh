@@ -27,6 +27,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Debug build (-DPCT_MSDA_BOUNDS_CHECK, libpctrans_msda_dbg.so): every tap address of the vector
+// kernels is checked against the image extent and the kernel traps on a violation.  This stands
+// in for compute-sanitizer, which is closed on the B200 pool; tests/test_gpu_bounds.py runs it.
+#ifdef PCT_MSDA_BOUNDS_CHECK
+#define PCT_CHECK_TAP(o, ox, oy, lane_off, ve, img_elems)                                        \
+  do {                                                                                           \
+    const long long lo_ = (long long)(o) + (lane_off);                                           \
+    const long long hi_ = lo_ + (ox) + (oy) + (ve);                                              \
+    if ((o) < 0 || (ox) < 0 || (oy) < 0 || hi_ > (long long)(img_elems)) __trap();               \
+  } while (0)
+#else
+#define PCT_CHECK_TAP(o, ox, oy, lane_off, ve, img_elems) do { } while (0)
+#endif
+
 namespace pct {
 
 constexpr int kVecThreads = 1024;  // forward: one persistent 32-warp CTA per SM
@@ -155,7 +169,7 @@ struct SampleTaps {
   bool v00, v01, v10, v11;  // corner is sampled by the reference
 };
 
-// tab = {H, W, level_start, unused}
+// level table entry = {H, W, level_start, level index}
 __device__ __forceinline__ SampleTaps make_sample_taps(float loc_x, float loc_y, int H, int W,
                                                        int start, int MD) {
   SampleTaps t;
@@ -189,20 +203,59 @@ __device__ __forceinline__ void fill_level_table(int4* tab, const int64_t* shape
                                                  const int64_t* lsi, int L, int P) {
   for (int s = threadIdx.x; s < L * P; s += blockDim.x) {
     const int l = s / P;
-    tab[s] = make_int4((int)shapes[2 * l], (int)shapes[2 * l + 1], (int)lsi[l], 0);
+    tab[s] = make_int4((int)shapes[2 * l], (int)shapes[2 * l + 1], (int)lsi[l], l);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused prologue.  With FUSED = true the kernels consume what the module's
+// Linears produce instead of materialised locations / weights:
+//   `loc`  = raw sampling offsets (N,Lq,M,L,P,2),  `attn` = raw attention logits (N,Lq,M,L*P),
+//   `ref`  = reference points (N,Lq,L,ref_dim) with ref_dim 2 (points) or 4 (boxes cx,cy,w,h),
+// and evaluate  loc = ref + off/(W_l,H_l)            (mod.py:106-109)
+//          or   loc = ref.xy + off/P * ref.wh * 0.5  (mod.py:110-112)
+// and the softmax over the L*P logits of a (query, head) pair (mod.py:104) in registers.
+// ---------------------------------------------------------------------------------------------
+struct FusedRef {
+  const float* ref;  // nullptr when not fused
+  int ref_dim;       // 2 or 4
+};
+
+template <int LPP>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int w = LPP / 2; w > 0; w >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, w));
+  return v;
+}
+template <int LPP>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int w = LPP / 2; w > 0; w >>= 1) v += __shfl_xor_sync(0xffffffffu, v, w);
+  return v;
+}
+
+// sampling location of sample s from the raw offset (fused) -- same operation order as the module
+__device__ __forceinline__ float2 fused_location(const float* __restrict__ rp, int ref_dim, int l,
+                                                 float2 off, int H, int W, int P) {
+  if (ref_dim == 2) {
+    const float2 r = __ldg(reinterpret_cast<const float2*>(rp) + l);
+    return make_float2(r.x + __fdiv_rn(off.x, (float)W), r.y + __fdiv_rn(off.y, (float)H));
+  }
+  const float4 r = __ldg(reinterpret_cast<const float4*>(rp) + l);
+  return make_float2(r.x + __fdiv_rn(off.x, (float)P) * r.z * 0.5f,
+                     r.y + __fdiv_rn(off.y, (float)P) * r.w * 0.5f);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Forward, vector path.  T = float | bf16; LPP lanes per (query, head) pair, each owning VB
 // bytes of the head's channels: D = LPP * VB/sizeof(T); a warp covers 32/LPP pairs.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LPP, int VB>
+template <typename T, int LPP, int VB, bool FUSED>
 __global__ void __launch_bounds__(kVecThreads, 1)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, T* __restrict__ out, int N, int S, int M,
-                    int L, int Lq, int P) {
+                    int L, int Lq, int P, FusedRef fr) {
   using CV = ChanVec<T, VB>;
   constexpr int VE = CV::kElems;
   constexpr int D = LPP * VE;
@@ -235,6 +288,17 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 #pragma unroll
     for (int i = 0; i < VE; ++i) acc[i] = 0.f;
 
+    // fused softmax: stabilise with the pair's max logit, accumulate with un-normalised weights
+    // exp(logit - max) and divide the output once by their sum
+    float lmax = 0.f, esum = 0.f;
+    const float* rp = nullptr;
+    if (FUSED) {
+      rp = fr.ref + ((long long)b * Lq + (qvalid ? q : Lq - 1)) * L * fr.ref_dim;
+      float mx = -INFINITY;
+      for (int s = sub; s < LP; s += LPP) mx = fmaxf(mx, __ldg(ap + s));
+      lmax = group_max<LPP>(mx);
+    }
+
     // software pipeline: the location / weight of this lane's sample of the NEXT round
     float2 xy_n = make_float2(0.f, 0.f);
     float a_n = 0.f;
@@ -244,8 +308,8 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     }
     for (int s0 = 0; s0 < LP; s0 += LPP) {
       const int s = s0 + sub;
-      const float2 xy = xy_n;
-      const float a = a_n;
+      float2 xy = xy_n;
+      float a = a_n;
       if (s + LPP < LP) {
         xy_n = __ldg(lp + s + LPP);
         a_n = __ldg(ap + s + LPP);
@@ -254,6 +318,11 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
       if (s < LP) {
         const int4 tb = s_tab[s];
+        if (FUSED) {
+          xy = fused_location(rp, fr.ref_dim, tb.w, xy, tb.x, tb.y, P);
+          a = expf(a - lmax);
+          esum += a;
+        }
         const SampleTaps tp = make_sample_taps(xy.x, xy.y, tb.x, tb.y, tb.z, MD);
         const float hy = 1.f - tp.ly, hx = 1.f - tp.lx;
         off = tp.off; dx = tp.dx; dy = tp.dy;
@@ -272,6 +341,7 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           const float b01 = __shfl_sync(0xffffffffu, w01, j, LPP);
           const float b10 = __shfl_sync(0xffffffffu, w10, j, LPP);
           const float b11 = __shfl_sync(0xffffffffu, w11, j, LPP);
+          PCT_CHECK_TAP(o, ox, oy, (m * D + sub * VE), VE, (long long)S * MD);
           const T* p00 = vimg + o;
           const T* p10 = p00 + oy;
           float v00[VE], v01[VE], v10[VE], v11[VE];
@@ -284,6 +354,11 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
             acc[i] = fmaf(b00, v00[i], fmaf(b01, v01[i], fmaf(b10, v10[i], fmaf(b11, v11[i], acc[i]))));
         }
       }
+    }
+    if (FUSED) {
+      const float inv = 1.f / group_sum<LPP>(esum);
+#pragma unroll
+      for (int i = 0; i < VE; ++i) acc[i] *= inv;
     }
     if (qvalid) CV::store_stream(out + pair * D + sub * VE, acc);
   }
@@ -298,13 +373,16 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 // channel lanes only form the four dot products <grad_out, corner value>; the lane that owns the
 // sample combines them into grad_attn and grad_loc (cuh:128-163) and writes them coalesced.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LPP, int VB>
+// With FUSED the kernel writes grad w.r.t. the raw offsets into `grad_loc` and grad w.r.t. the raw
+// logits into `grad_attn` (softmax backward: a_s * (g_s - sum_t a_t g_t)).
+template <typename T, int LPP, int VB, bool FUSED>
 __global__ void __launch_bounds__(kBwdVecThreads, 1)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, const T* __restrict__ grad_out,
                     float* __restrict__ gacc, float* __restrict__ grad_loc,
-                    float* __restrict__ grad_attn, int N, int S, int M, int L, int Lq, int P) {
+                    float* __restrict__ grad_attn, int N, int S, int M, int L, int Lq, int P,
+                    FusedRef fr) {
   using CV = ChanVec<T, VB>;
   constexpr int VE = CV::kElems;
   constexpr int D = LPP * VE;
@@ -338,6 +416,19 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     float go[VE];
     CV::load_stream(grad_out + pair * D + sub * VE, go);
 
+    // fused softmax: max and normaliser of the pair's logits before the first tap
+    float lmax = 0.f, inv_sum = 1.f, ag_dot = 0.f;
+    const float* rp = nullptr;
+    if (FUSED) {
+      rp = fr.ref + ((long long)b * Lq + (qvalid ? q : Lq - 1)) * L * fr.ref_dim;
+      float mx = -INFINITY;
+      for (int s = sub; s < LP; s += LPP) mx = fmaxf(mx, __ldg(ap + s));
+      lmax = group_max<LPP>(mx);
+      float es = 0.f;
+      for (int s = sub; s < LP; s += LPP) es += expf(__ldg(ap + s) - lmax);
+      inv_sum = 1.f / group_sum<LPP>(es);
+    }
+
     float2 xy_n = make_float2(0.f, 0.f);
     float a_n = 0.f;
     if (sub < LP) {
@@ -346,8 +437,9 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     }
     for (int s0 = 0; s0 < LP; s0 += LPP) {
       const int s = s0 + sub;
-      const float2 xy = xy_n;
-      const float a = a_n;
+      float2 xy = xy_n;
+      float a = a_n;
+      const float2 raw_off = xy_n;
       if (s + LPP < LP) {
         xy_n = __ldg(lp + s + LPP);
         a_n = __ldg(ap + s + LPP);
@@ -358,8 +450,19 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       float ch00 = 0.f, ch01 = 0.f, ch10 = 0.f, ch11 = 0.f;  // d(val)/d(y) coefficients
       float cw00 = 0.f, cw01 = 0.f, cw10 = 0.f, cw11 = 0.f;  // d(val)/d(x) coefficients
       float Hf = 0.f, Wf = 0.f;
+      float2 dloc = make_float2(1.f, 1.f);   // d(location)/d(raw offset), fused only
       if (s < LP) {
         const int4 tb = s_tab[s];
+        if (FUSED) {
+          xy = fused_location(rp, fr.ref_dim, tb.w, raw_off, tb.x, tb.y, P);
+          a = expf(a - lmax) * inv_sum;
+          if (fr.ref_dim == 2) {
+            dloc = make_float2(__fdiv_rn(1.f, (float)tb.y), __fdiv_rn(1.f, (float)tb.x));
+          } else {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(rp) + tb.w);
+            dloc = make_float2(__fdiv_rn(r.z * 0.5f, (float)P), __fdiv_rn(r.w * 0.5f, (float)P));
+          }
+        }
         const SampleTaps tp = make_sample_taps(xy.x, xy.y, tb.x, tb.y, tb.z, MD);
         const float hy = 1.f - tp.ly, hx = 1.f - tp.lx;
         off = tp.off; dx = tp.dx; dy = tp.dy;
@@ -383,6 +486,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           const float b01 = __shfl_sync(0xffffffffu, aw01, j, LPP);
           const float b10 = __shfl_sync(0xffffffffu, aw10, j, LPP);
           const float b11 = __shfl_sync(0xffffffffu, aw11, j, LPP);
+          PCT_CHECK_TAP(o, ox, oy, (m * D + sub * VE), VE, (long long)S * MD);
           const T* p00 = vimg + o;
           const T* p10 = p00 + oy;
           float v00[VE], v01[VE], v10[VE], v11[VE];
@@ -424,7 +528,24 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         const float s_gw = cw00 * D00 + cw01 * D01 + cw10 * D10 + cw11 * D11;
         const long long si = pair * LP + s;
         grad_attn[si] = s_val;                                                       // cuh:161
-        reinterpret_cast<float2*>(grad_loc)[si] = make_float2(Wf * s_gw * a, Hf * s_gh * a);  // cuh:162-163
+        float2 gl = make_float2(Wf * s_gw * a, Hf * s_gh * a);                      // cuh:162-163
+        if (FUSED) {
+          gl.x *= dloc.x;
+          gl.y *= dloc.y;
+          ag_dot = fmaf(a, s_val, ag_dot);
+        }
+        reinterpret_cast<float2*>(grad_loc)[si] = gl;
+      }
+    }
+    if (FUSED) {
+      // softmax backward over the pair's L*P logits: each lane re-reads the g_s it just wrote
+      const float dot = group_sum<LPP>(ag_dot);
+      if (qvalid) {
+        for (int s = sub; s < LP; s += LPP) {
+          const long long si = pair * LP + s;
+          const float a = expf(__ldg(ap + s) - lmax) * inv_sum;
+          grad_attn[si] = a * (grad_attn[si] - dot);
+        }
       }
     }
   }

@@ -1,3 +1,4 @@
-from .ms_deform_attn_func import MSDeformAttnFunction, ms_deform_attn_core_pytorch
+from .ms_deform_attn_func import (MSDeformAttnFunction, MSDeformAttnFusedFunction,
+                                  ms_deform_attn_core_pytorch)
 
-__all__ = ["MSDeformAttnFunction", "ms_deform_attn_core_pytorch"]
+__all__ = ["MSDeformAttnFunction", "MSDeformAttnFusedFunction", "ms_deform_attn_core_pytorch"]

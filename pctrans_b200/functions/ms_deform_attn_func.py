@@ -90,6 +90,60 @@ class MSDeformAttnFunction(Function):
         return grad_value, None, None, grad_loc, grad_attn, None
 
 
+class MSDeformAttnFusedFunction(Function):
+    """Fused-prologue variant: takes what the module's Linears produce and
+    evaluates the softmax over L*P (mod.py:104) and the location arithmetic (mod.py:106-112)
+    inside the kernels, so neither ``sampling_locations`` nor ``attention_weights`` (nor their
+    gradients) ever exist in HBM.
+
+        MSDeformAttnFusedFunction.apply(value, value_spatial_shapes, value_level_start_index,
+                                        reference_points, sampling_offsets, attention_logits)
+
+    reference_points (N, Lq, L, 2|4) fp32, no gradient; sampling_offsets (N, Lq, M, L, P, 2) and
+    attention_logits (N, Lq, M, L*P) fp32, raw.  ``supported(...)`` tells whether a call can take
+    this route; otherwise the caller composes the prologue in PyTorch and uses
+    ``MSDeformAttnFunction`` (still the CUDA kernels -- there is no CPU route either way)."""
+
+    @staticmethod
+    def supported(value, reference_points, n_levels, n_points):
+        return (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16)
+                and not reference_points.requires_grad and value.shape[1] > 0
+                and reference_points.shape[-1] in (2, 4)
+                and _cabi.kernel_family(value.shape[3], n_levels, n_points, value.dtype) == 1
+                and _cabi.kernel_family(value.shape[3], n_levels, n_points, value.dtype, True) == 1)
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points,
+                sampling_offsets, attention_logits):
+        N, S, M, D = value.shape
+        L = value_spatial_shapes.shape[0]
+        _check_inputs(value, value_spatial_shapes, value_level_start_index, sampling_offsets,
+                      attention_logits.view(tuple(sampling_offsets.shape[:5])))
+        _require(reference_points.is_cuda and reference_points.is_contiguous()
+                 and reference_points.dtype == torch.float32,
+                 "reference_points must be a contiguous float32 CUDA tensor")
+        _require(tuple(reference_points.shape[:3]) == (N, sampling_offsets.shape[1], L)
+                 and reference_points.shape[-1] in (2, 4),
+                 "reference_points must be (N, Lq, L, 2) or (N, Lq, L, 4)", ValueError)
+        out = _cabi.fused_forward(value, value_spatial_shapes, value_level_start_index,
+                                  reference_points, sampling_offsets, attention_logits)
+        _require(out is not None, "shape not supported by the fused MSDeformAttn kernels; "
+                                  "check MSDeformAttnFusedFunction.supported() first")
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
+                              reference_points, sampling_offsets, attention_logits)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, ref, offsets, logits = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        if grad_output.dtype != value.dtype:
+            grad_output = grad_output.to(value.dtype)
+        gv, goff, glog = _cabi.fused_backward(value, shapes, lsi, ref, offsets, logits, grad_output)
+        return gv, None, None, None, goff, glog
+
+
 def ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations, attention_weights):
     """Debug / test helper kept because callers import this name from this module
     (OPS/modules/ms_deform_attn.py:25, OPS/test.py:21; func.py:53-54 says "for debug and test

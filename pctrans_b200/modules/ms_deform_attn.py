@@ -21,7 +21,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 
 def _is_power_of_2(n):
@@ -45,6 +45,9 @@ class MSDeformAttn(nn.Module):
                           "implementation.")
 
         self.im2col_step = 128
+        # Use the fused-prologue kernels (softmax + location arithmetic inside the op, SURVEY.md
+        # 8f rank 1) when the call qualifies; results agree with the unfused route to rounding.
+        self.fused_prologue = True
         self.d_model = d_model
         self.n_levels = n_levels
         self.n_heads = n_heads
@@ -99,6 +102,16 @@ class MSDeformAttn(nn.Module):
             N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         weights = self.attention_weights(query).view(
             N, Len_q, self.n_heads, self.n_levels * self.n_points)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead."
+                             .format(reference_points.shape[-1]))
+        if self.fused_prologue and MSDeformAttnFusedFunction.supported(
+                value, reference_points, self.n_levels, self.n_points):
+            output = MSDeformAttnFusedFunction.apply(
+                value.contiguous(), input_spatial_shapes, input_level_start_index,
+                reference_points.float().contiguous(), offsets.float().contiguous(),
+                weights.float().contiguous())
+            return self.output_proj(output.to(query.dtype))
         weights = F.softmax(weights, -1).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points)
         if reference_points.shape[-1] == 2:

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Where does one encoder layer spend its time?  torch.profiler kernel table (GPU box)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from torch.profiler import profile, ProfilerActivity
+from pctrans_b200 import encoder as enc, synth
+
+dev = "cuda:0"
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+train = (sys.argv[2] if len(sys.argv) > 2 else "train") == "train"
+torch.manual_seed(0)
+model = enc.MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder_layers=1,
+                                               dim_feedforward=1024, dropout=0.0, num_feature_levels=3).to(dev)
+srcs = [torch.randn(n, 256, h, w, device=dev) for h, w in synth.CVPPP_512]
+pe = enc.PositionEmbeddingSine(128, normalize=True)
+pos = [pe(s) for s in srcs]
+def step():
+    if train:
+        model.zero_grad(set_to_none=True)
+        model(srcs, pos)[0].square().mean().backward()
+    else:
+        with torch.no_grad():
+            model(srcs, pos)
+for _ in range(5): step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
