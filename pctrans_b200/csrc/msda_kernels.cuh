@@ -43,8 +43,15 @@
 
 namespace pct {
 
-constexpr int kVecThreads = 1024;  // forward: one persistent 32-warp CTA per SM
-constexpr int kBwdVecThreads = 768; // backward needs ~80 registers per thread
+// Tuning overrides (scripts/build_variants.sh): -DPCT_FWD_THREADS=..., -DPCT_BWD_THREADS=...
+#ifndef PCT_FWD_THREADS
+#define PCT_FWD_THREADS 1024
+#endif
+#ifndef PCT_BWD_THREADS
+#define PCT_BWD_THREADS 768
+#endif
+constexpr int kVecThreads = PCT_FWD_THREADS;     // forward: one persistent 32-warp CTA per SM
+constexpr int kBwdVecThreads = PCT_BWD_THREADS;  // backward needs ~80 registers per thread
 constexpr int kGenericThreads = 256;
 
 // ---------------------------------------------------------------------------------------------

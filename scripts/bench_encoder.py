@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--core", default="cuda", choices=["cuda", "gridsample"])
+    ap.add_argument("--fused", type=int, default=1, help="use the fused-prologue kernels (default)")
+    ap.add_argument("--tf32", type=int, default=0, help="allow TF32 tensor cores for the Linears")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -61,10 +63,14 @@ def main():
                 return msda_oracle.core_grid_sample(value, shapes, loc, attn)
         mod_file.MSDeformAttnFunction = _Core
 
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     torch.manual_seed(0)   # identical initial weights on every rank, as DDP broadcasts them
     model = enc.MSDeformAttnTransformerEncoderOnly(
         d_model=args.d_model, nhead=8, num_encoder_layers=args.layers, dim_feedforward=1024,
         dropout=0.0, num_feature_levels=len(pyramid)).to(dev)
+    for mod in model.modules():
+        if isinstance(mod, mod_file.MSDeformAttn):
+            mod.fused_prologue = bool(args.fused) and args.core == "cuda"
     g = torch.Generator().manual_seed(100 + rank)     # per-rank data (utils/system.py:83)
     srcs = [torch.randn(n, args.d_model, h, w, generator=g).to(dev) for h, w in pyramid]
     pe = enc.PositionEmbeddingSine(args.d_model // 2, normalize=True)
@@ -110,7 +116,8 @@ def main():
     ms = float(ms) / args.steps
     if rank == 0:
         print(json.dumps({
-            "bench": "encoder", "mode": args.mode, "core": args.core, "pyramid": args.pyramid,
+            "bench": "encoder", "mode": args.mode, "core": args.core, "fused": bool(args.fused),
+            "tf32": bool(args.tf32), "pyramid": args.pyramid,
             "d_model": args.d_model, "layers": args.layers, "n_gpus": world, "batch_per_gpu": n,
             "global_batch": n * world, "ms_per_step": ms,
             "query_layers_per_s": world * n * lq * args.layers / (ms * 1e-3),
