@@ -235,6 +235,7 @@ VecPlan vec_eligible(const Dims& d, int dtype, unsigned flags, const void* value
   VecPlan none;
   if (flags & PCT_MSDA_FLAG_FORCE_GENERIC) return none;
   if ((long long)d.S * d.M * d.D >= (1ll << 31) || d.S == 0) return none;  // 32-bit in-image offsets
+  if ((long long)d.N * d.M * d.Lq >= (1ll << 31)) return none;             // 32-bit task index
   if (!aligned(loc, 8) || !aligned(attn, 4)) return none;
   VecPlan p = vec_plan(d.D, d.L, d.P, dtype, acc != nullptr);
   if (p.lanes == 0) return none;

@@ -276,13 +276,14 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int MD = M * D;
   const int LP = L * P;
   const int tasks_per_stream = (Lq + PPW - 1) / PPW;
+  // the launcher guarantees n_tasks < 2^31, so the per-task index math stays 32-bit
   const long long n_tasks = (long long)N * M * tasks_per_stream;
-  const long long t_begin = n_tasks * blockIdx.x / gridDim.x;
-  const long long t_end = n_tasks * (blockIdx.x + 1) / gridDim.x;
+  const int t_begin = (int)(n_tasks * blockIdx.x / gridDim.x);
+  const int t_end = (int)(n_tasks * (blockIdx.x + 1) / gridDim.x);
 
-  for (long long t = t_begin + warp; t < t_end; t += nwarps) {
-    const int stream = (int)(t / tasks_per_stream);
-    const int tq = (int)(t - (long long)stream * tasks_per_stream);
+  for (int t = t_begin + warp; t < t_end; t += nwarps) {
+    const int stream = t / tasks_per_stream;
+    const int tq = t - stream * tasks_per_stream;
     const int b = stream / M, m = stream - b * M;
     const int q = tq * PPW + grp;
     const bool qvalid = q < Lq;
@@ -403,13 +404,14 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int MD = M * D;
   const int LP = L * P;
   const int tasks_per_stream = (Lq + PPW - 1) / PPW;
+  // the launcher guarantees n_tasks < 2^31, so the per-task index math stays 32-bit
   const long long n_tasks = (long long)N * M * tasks_per_stream;
-  const long long t_begin = n_tasks * blockIdx.x / gridDim.x;
-  const long long t_end = n_tasks * (blockIdx.x + 1) / gridDim.x;
+  const int t_begin = (int)(n_tasks * blockIdx.x / gridDim.x);
+  const int t_end = (int)(n_tasks * (blockIdx.x + 1) / gridDim.x);
 
-  for (long long t = t_begin + warp; t < t_end; t += nwarps) {
-    const int stream = (int)(t / tasks_per_stream);
-    const int tq = (int)(t - (long long)stream * tasks_per_stream);
+  for (int t = t_begin + warp; t < t_end; t += nwarps) {
+    const int stream = t / tasks_per_stream;
+    const int tq = t - stream * tasks_per_stream;
     const int b = stream / M, m = stream - b * M;
     const int q = tq * PPW + grp;
     const bool qvalid = q < Lq;

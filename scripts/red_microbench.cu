@@ -40,6 +40,36 @@ __global__ void red_kernel(float* buf, unsigned n_lines, int iters, unsigned see
       const unsigned line = hash32(seed + (gwarp * iters + it) * 8u + grp) % n_lines;
       float* p = buf + (size_t)line * 32 + sub * 8;   // 16 B at 32 B stride: half sectors
       asm volatile("red.global.add.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(p), "f"(1.0f) : "memory");
+    } else if (MODE == 5) {   // plain vector stores, same random-line pattern (L2 write path)
+      const unsigned grp = lane >> 3, sub = lane & 7;
+      const unsigned line = hash32(seed + (gwarp * iters + it) * 4u + grp) % n_lines;
+      float* p = buf + (size_t)line * 32 + sub * 4;
+      asm volatile("st.global.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(p), "f"(1.0f) : "memory");
+    } else if (MODE == 6) {   // plain vector loads that bypass L1 (L2 read path)
+      const unsigned grp = lane >> 3, sub = lane & 7;
+      const unsigned line = hash32(seed + (gwarp * iters + it) * 4u + grp) % n_lines;
+      const float* p = buf + (size_t)line * 32 + sub * 4;
+      float a, b, c, d;
+      asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p));
+      if (a == 123456.f) buf[0] = b + c + d;
+    } else if (MODE == 7) {   // TMA bulk reduction: one elected lane adds a 512-B smem row block
+      __shared__ __align__(128) float srow[32][128];   // per warp 512 B
+      const unsigned warp_in_cta = threadIdx.x >> 5;
+      for (int i = lane; i < 128; i += 32) srow[warp_in_cta][i] = 1.0f;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        for (int g = 0; g < 4; ++g) {
+          const unsigned line = hash32(seed + (gwarp * iters + it) * 4u + g) % n_lines;
+          float* p = buf + (size_t)line * 32;
+          unsigned sa = (unsigned)__cvta_generic_to_shared(&srow[warp_in_cta][g * 32]);
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;"
+                       ::"l"(p), "r"(sa) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if ((it & 7) == 7) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      __syncwarp();
     } else {
       const unsigned grp = lane >> 4, sub = lane & 15;
       const unsigned line = hash32(seed + (gwarp * iters + it) * 2u + grp) % n_lines;
@@ -78,13 +108,16 @@ int main() {
   cudaMalloc(&buf, cap);
   cudaMemset(buf, 0, cap);
   int sms = 148;
-  const size_t regions[] = {22ull << 20, 88ull << 20, 352ull << 20, 2ull << 20};
+  const size_t regions[] = {22ull << 20, 88ull << 20};
   for (size_t region : regions) {
     run<0>("v4.f32 full line (8 lanes/line)", buf, region, sms * 2, 512, 2000, 512);
     run<3>("v4.f32 half sectors", buf, region, sms * 2, 512, 2000, 512);
     run<4>("v2.f32 (16 lanes/line)", buf, region, sms * 2, 512, 2000, 256);
     run<1>("scalar f32 atomicAdd (32 lanes/line)", buf, region, sms * 2, 512, 2000, 128);
     run<2>("bf16x8 (4 lanes / 64 B)", buf, region, sms * 2, 512, 2000, 512);
+    run<5>("st.global.v4 full line", buf, region, sms * 2, 512, 2000, 512);
+    run<6>("ld.global.cg.v4 full line", buf, region, sms * 2, 512, 2000, 512);
+    run<7>("TMA cp.reduce.async.bulk 128 B rows", buf, region, sms * 2, 512, 500, 512);
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
