@@ -207,6 +207,20 @@ int launch_bwd_generic(const void* value, const int64_t* shapes, const int64_t* 
   return (int)cudaGetLastError();
 }
 
+// zero `bytes` at a 16-byte aligned address with a kernel (see msda_zero_kernel)
+int zero_fill(void* p, size_t bytes, int sm_count, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (!aligned(p, 16)) return (int)cudaMemsetAsync(p, 0, bytes, st);
+  const long long n16 = (long long)(bytes / 16);
+  const int n_tail = (int)(bytes % 16);
+  long long want = (n16 + 255) / 256;
+  long long cap = (long long)sm_count * 8;
+  const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+  pct::msda_zero_kernel<<<grid, 256, 0, st>>>((uint4*)p, n16, (unsigned char*)p + n16 * 16, n_tail);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
 int round_workspace_to_bf16(const float* ws, void* grad_value, long long n, int sm_count,
                             cudaStream_t st) {
   const long long n8 = n / 8;
@@ -411,8 +425,8 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
   void* acc_image = value_dtype == PCT_MSDA_BF16 ? workspace : grad_value;
   const size_t acc_bytes = value_dtype == PCT_MSDA_BF16 ? need : (size_t)n_value * es;
   if (acc_bytes > 0) {
-    cudaError_t e = cudaMemsetAsync(acc_image, 0, acc_bytes, st);
-    if (e != cudaSuccess) return (int)e;
+    rc = zero_fill(acc_image, acc_bytes, sm_count, st);
+    if (rc) return rc;
   }
   if (n_pairs == 0 || n_value == 0) {
     // no samples can touch a value: grads w.r.t. loc/attn are all zero

@@ -560,6 +560,18 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   }
 }
 
+// Zero-fill of the grad_value accumulator.  A kernel, not cudaMemsetAsync: a memset may be placed on
+// a copy engine, where it queues behind the host<->device copies of the end-to-end pipeline
+// (pctrans_b200/host_pipeline.py) and stalls the backward of every chunk.
+__global__ void msda_zero_kernel(uint4* __restrict__ dst, long long n16, unsigned char* tail,
+                                 int n_tail) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0;
+}
+
 // fp32 scratch image -> bf16 grad_value (bf16 path only)
 __global__ void msda_round_to_bf16_kernel(const float* __restrict__ src,
                                           __nv_bfloat16* __restrict__ dst, long long n8) {

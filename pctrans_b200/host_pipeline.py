@@ -13,7 +13,7 @@ from . import _cabi
 
 
 class HostPipeline:
-    def __init__(self, device, dtype=torch.float32, chunk_images: int | None = None, slots: int = 3):
+    def __init__(self, device, dtype=torch.float32, chunk_images: int | None = None, slots: int = 4):
         self.device = torch.device(device)
         self.dtype = dtype
         self.chunk_images = chunk_images
@@ -29,7 +29,13 @@ class HostPipeline:
             return
         N, S, M, D = value.shape
         Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
-        c = self.chunk_images or max(1, N // 8)
+        # Chunk schedule: uniform chunks of N/8 images.  Measured on B200 (scripts/e2e_timeline.py,
+        # scripts/pcie_probe2.py): the pipeline is bound by the H2D direction of the duplex host
+        # link (~41 GB/s while D2H runs at ~47 GB/s); finer or tapered chunks change nothing.
+        step = self.chunk_images or max(1, N // 8)
+        sizes = [step] * (N // step) + ([N % step] if N % step else [])
+        self._sizes = sizes
+        c = max(sizes) if sizes else 1
         self._c = c
         dev, dt = self.device, self.dtype
         f32 = torch.float32
@@ -62,14 +68,14 @@ class HostPipeline:
             if t.is_cuda or not t.is_contiguous():
                 raise RuntimeError("HostPipeline takes contiguous host tensors")
         self._prepare(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
-        N, c = value.shape[0], self._c
+        N = value.shape[0]
         s_in, s_run, s_out = self._s_in, self._s_run, self._s_out
         cur = torch.cuda.current_stream(self.device)
         for s in (s_in, s_run, s_out):
             s.wait_stream(cur)
-        for i, lo in enumerate(range(0, N, c)):
-            hi = min(N, lo + c)
-            n = hi - lo
+        lo = 0
+        for i, n in enumerate(self._sizes):
+            hi = lo + n
             b = self._bufs[i % self.slots]
             with torch.cuda.stream(s_in):
                 if i >= self.slots:
@@ -95,5 +101,6 @@ class HostPipeline:
                 self._h_gloc[lo:hi].copy_(b["gloc"][:n], non_blocking=True)
                 self._h_gattn[lo:hi].copy_(b["gattn"][:n], non_blocking=True)
                 b["free"].record(s_out)
+            lo = hi
         s_out.synchronize()
         return self._h_out, self._h_gvalue, self._h_gloc, self._h_gattn

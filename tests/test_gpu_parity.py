@@ -301,3 +301,53 @@ def test_non_default_stream_and_launch_counter():
     st.synchronize()
     assert _cabi.launch_count() == before + 1
     assert torch.equal(out, ref)
+
+
+def test_random_shape_sweep():
+    """Seeded sweep over pyramids / heads / head dims / points / dtypes, including shapes that mix
+    the vector and generic kernels, ragged query counts and 1-pixel levels."""
+    import random
+    rng = random.Random(1234)
+    dims = [1, 2, 4, 6, 8, 12, 16, 20, 32, 48, 64, 96, 128]
+    for case in range(48):
+        L = rng.randint(1, 4)
+        shapes = tuple((rng.randint(1, 13), rng.randint(1, 13)) for _ in range(L))
+        M, D, P = rng.choice([1, 2, 3, 8]), rng.choice(dims), rng.randint(1, 5)
+        N, Lq = rng.randint(1, 3), rng.randint(1, 70)
+        dtype = rng.choice([torch.float32, torch.float32, torch.bfloat16, torch.float64])
+        regime = rng.choice(["U", "O"])
+        value, sh, lsi, loc, attn = synth.make_inputs(N, shapes, M=M, D=D, P=P, regime=regime,
+                                                      seed=case, Lq=Lq)
+        g = torch.randn(N, Lq, M * D, generator=torch.Generator().manual_seed(case + 500))
+        if dtype == torch.float64:
+            value, loc, attn, g = value.double(), loc.double(), attn.double(), g.double()
+        try:
+            check_case(value, sh, lsi, loc, attn, g, dtype)
+        except AssertionError as e:
+            raise AssertionError(f"case {case}: shapes={shapes} M={M} D={D} P={P} N={N} Lq={Lq} "
+                                 f"{dtype} {regime}: {e}") from e
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N", [1, 5, 16])
+def test_host_pipeline_matches_direct_call(dtype, N):
+    """The end-to-end entry (pinned host in/out, chunked 3-stream pipeline) returns the same
+    bits as one direct call on the whole batch (images are independent; only the summation
+    order of grad_value atomics may differ)."""
+    from pctrans_b200.host_pipeline import HostPipeline
+    value, sh, lsi, loc, attn = synth.make_inputs(N, ((12, 9), (6, 5), (3, 3)), M=8, D=32, P=4,
+                                                  regime="O", seed=N)
+    g = torch.randn(N, value.shape[1], 256, generator=torch.Generator().manual_seed(3))
+    hv, hl, ha, hg = value.to(dtype).pin_memory(), loc.pin_memory(), attn.pin_memory(), g.to(dtype).pin_memory()
+    pipe = HostPipeline(torch.device(DEV), dtype)
+    for _ in range(2):      # second call reuses the staging buffers
+        out, gv, gl, ga = pipe.forward_backward(hv, sh, lsi, hl, ha, hg)
+    assert not out.is_cuda and out.is_pinned()
+    d = lambda t: t.to(DEV)
+    ref_out = _cabi.forward(d(hv), d(sh), d(lsi), d(hl), d(ha))
+    ref_gv, ref_gl, ref_ga = _cabi.backward(d(hv), d(sh), d(lsi), d(hl), d(ha), d(hg))
+    assert torch.equal(out, ref_out.cpu())
+    assert torch.equal(gl, ref_gl.cpu()) and torch.equal(ga, ref_ga.cpu())
+    assert rel(gv, ref_gv.float().cpu().numpy()) <= (1e-6 if dtype == torch.float32 else 1e-2)
+    with pytest.raises(RuntimeError):
+        pipe.forward_backward(d(hv), sh, lsi, hl, ha, hg)
