@@ -65,7 +65,8 @@ extern "C" {
 
 /* flags for the *_ex entry points (0 = library default; used by the tuning harness) */
 #define PCT_MSDA_FLAG_FORCE_GENERIC 0x1u /* use the any-D scalar kernels even when a vector path fits */
-/* bits 8..15: threads/32 of the persistent CTA; bits 16..19: CTAs per SM (tuning only) */
+/* bits 8..15: threads/32 of the persistent CTA; bits 16..19: CTAs per SM; bits 20..24: 1 + static
+ * share of the task list in sixteenths (tuning only) */
 
 int pct_msda_abi_version(void);
 

@@ -13,6 +13,23 @@
 namespace {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<unsigned> g_sched_seq{0};   // ring position of the next persistent launch
+
+// Static share of the task list (in 1/16) before the dynamic tail; tuning flag bits 20..24 carry
+// (value + 1) to override.
+constexpr int kStaticSixteenths = 14;
+
+pct::SchedArgs make_sched(long long n_tasks, int grid, int warps, unsigned flags) {
+  int sixteenths = kStaticSixteenths;
+  const int f = (int)((flags >> 20) & 0x1fu);
+  if (f > 0) sixteenths = f - 1;
+  long long per_cta = n_tasks * sixteenths / 16 / grid;
+  per_cta -= per_cta % warps;             // whole rounds of the CTA's warps
+  pct::SchedArgs sa;
+  sa.slot = (int)(g_sched_seq.fetch_add(1, std::memory_order_relaxed) % pct::kSchedSlots);
+  sa.static_per_cta = (int)(per_cta < 0 ? 0 : per_cta);
+  return sa;
+}
 
 int device_sm_count(int* out) {
   // Cached per device ordinal; racing initialisers write the same value.
@@ -113,7 +130,7 @@ int launch_fwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi,
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kVecThreads);
   pct::msda_fwd_vec_kernel<T, LPP, VB, FUSED><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (T*)out, d.N, d.S, d.M,
-      d.L, d.Lq, d.P, fr);
+      d.L, d.Lq, d.P, fr, make_sched(n_tasks, ls.grid, ls.block / 32, flags));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
@@ -128,7 +145,8 @@ int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi,
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kBwdVecThreads);
   pct::msda_bwd_vec_kernel<T, LPP, VB, FUSED><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
-      gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, fr);
+      gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, fr,
+      make_sched(n_tasks, ls.grid, ls.block / 32, flags));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }

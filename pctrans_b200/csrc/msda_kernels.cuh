@@ -215,6 +215,71 @@ __device__ __forceinline__ void fill_level_table(int4* tab, const int64_t* shape
 }
 
 // ---------------------------------------------------------------------------------------------
+// Task scheduling of the persistent vector kernels: "static head, dynamic tail".
+// Every CTA first walks a contiguous static slice of the stream-ordered task list (this is what
+// keeps the L1 sliding window hot), covering `static_per_cta` tasks; the remaining tasks are
+// handed out in mini-chunks of kMiniChunk consecutive tasks per warp through a global counter, so
+// SMs that run faster (near-die L2, no co-running NCCL kernel) absorb the tail instead of idling
+// -- static partitioning alone left 8 % (forward) / 11 % (backward) of the SM time idle.
+// The counters live in a ring of module-scope device words; the last CTA to leave resets its slot.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSchedSlots = 512;
+#ifndef PCT_MINI_CHUNK
+#define PCT_MINI_CHUNK 2
+#endif
+constexpr int kMiniChunk = PCT_MINI_CHUNK;
+__device__ unsigned int g_sched[kSchedSlots * 2];
+
+struct SchedArgs {
+  int slot;            // ring slot of this launch
+  int static_per_cta;  // tasks of the static slice of every CTA
+};
+
+struct TaskIter {
+  int t, t_static_end, n_tasks, dyn_begin, nwarps, lane, chunk_left;
+  unsigned int* ctr;
+  __device__ __forceinline__ TaskIter(const SchedArgs& sa, int n_tasks_, int warp, int nwarps_,
+                                      int lane_)
+      : n_tasks(n_tasks_), nwarps(nwarps_), lane(lane_), chunk_left(0) {
+    const int base = blockIdx.x * sa.static_per_cta;
+    t = base + warp - nwarps_;
+    t_static_end = base + sa.static_per_cta;
+    dyn_begin = gridDim.x * sa.static_per_cta;
+    ctr = g_sched + 2 * sa.slot;
+  }
+  // next task index for this warp, or -1 when the work is exhausted (warp-uniform)
+  __device__ __forceinline__ int next() {
+    if (t_static_end >= 0) {                 // static phase
+      t += nwarps;
+      if (t < t_static_end) return t;
+      t_static_end = -1;
+    }
+    if (chunk_left == 0) {                   // dynamic phase: grab kMiniChunk consecutive tasks
+      unsigned int c = 0;
+      if (lane == 0) c = atomicAdd(ctr, 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      const long long first = (long long)dyn_begin + (long long)c * kMiniChunk;
+      if (first >= n_tasks) return -1;
+      t = (int)first - 1;
+      chunk_left = (int)((n_tasks - first) < kMiniChunk ? (n_tasks - first) : kMiniChunk);
+    }
+    --chunk_left;
+    return ++t;
+  }
+  // call once per CTA after all warps are done (after a __syncthreads)
+  __device__ __forceinline__ void finish() {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+        ctr[0] = 0u;
+        ctr[1] = 0u;
+        __threadfence();
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Fused prologue.  With FUSED = true the kernels consume what the module's
 // Linears produce instead of materialised locations / weights:
 //   `loc`  = raw sampling offsets (N,Lq,M,L,P,2),  `attn` = raw attention logits (N,Lq,M,L*P),
@@ -262,7 +327,7 @@ __global__ void __launch_bounds__(kVecThreads, 1)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, T* __restrict__ out, int N, int S, int M,
-                    int L, int Lq, int P, FusedRef fr) {
+                    int L, int Lq, int P, FusedRef fr, SchedArgs sched) {
   using CV = ChanVec<T, VB>;
   constexpr int VE = CV::kElems;
   constexpr int D = LPP * VE;
@@ -277,11 +342,10 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int LP = L * P;
   const int tasks_per_stream = (Lq + PPW - 1) / PPW;
   // the launcher guarantees n_tasks < 2^31, so the per-task index math stays 32-bit
-  const long long n_tasks = (long long)N * M * tasks_per_stream;
-  const int t_begin = (int)(n_tasks * blockIdx.x / gridDim.x);
-  const int t_end = (int)(n_tasks * (blockIdx.x + 1) / gridDim.x);
+  const int n_tasks = N * M * tasks_per_stream;
+  TaskIter iter(sched, n_tasks, warp, nwarps, lane);
 
-  for (int t = t_begin + warp; t < t_end; t += nwarps) {
+  for (int t = iter.next(); t >= 0; t = iter.next()) {
     const int stream = t / tasks_per_stream;
     const int tq = t - stream * tasks_per_stream;
     const int b = stream / M, m = stream - b * M;
@@ -370,6 +434,8 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     }
     if (qvalid) CV::store_stream(out + pair * D + sub * VE, acc);
   }
+  __syncthreads();
+  iter.finish();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -390,7 +456,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
                     const float* __restrict__ attn, const T* __restrict__ grad_out,
                     float* __restrict__ gacc, float* __restrict__ grad_loc,
                     float* __restrict__ grad_attn, int N, int S, int M, int L, int Lq, int P,
-                    FusedRef fr) {
+                    FusedRef fr, SchedArgs sched) {
   using CV = ChanVec<T, VB>;
   constexpr int VE = CV::kElems;
   constexpr int D = LPP * VE;
@@ -405,11 +471,10 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int LP = L * P;
   const int tasks_per_stream = (Lq + PPW - 1) / PPW;
   // the launcher guarantees n_tasks < 2^31, so the per-task index math stays 32-bit
-  const long long n_tasks = (long long)N * M * tasks_per_stream;
-  const int t_begin = (int)(n_tasks * blockIdx.x / gridDim.x);
-  const int t_end = (int)(n_tasks * (blockIdx.x + 1) / gridDim.x);
+  const int n_tasks = N * M * tasks_per_stream;
+  TaskIter iter(sched, n_tasks, warp, nwarps, lane);
 
-  for (int t = t_begin + warp; t < t_end; t += nwarps) {
+  for (int t = iter.next(); t >= 0; t = iter.next()) {
     const int stream = t / tasks_per_stream;
     const int tq = t - stream * tasks_per_stream;
     const int b = stream / M, m = stream - b * M;
@@ -484,6 +549,48 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       }
       const float ae = qvalid ? a : 0.f;   // padded tail pairs scatter nothing
       const float aw00 = w00 * ae, aw01 = w01 * ae, aw10 = w10 * ae, aw11 = w11 * ae;
+      // Scatter weights of MY sample's four rows.  All samples of a pair scatter the SAME
+      // grad_out vector, so two samples that touch the same value row can share one reduction:
+      // the weights add.  Neighbouring points of a level (p, p+1) overlap by one or two rows
+      // when the head walks in pixel steps (mod.py:66-74), which is 14-28 % of all reductions --
+      // and the backward is bound by L2 reduction throughput.  Each lane hands the rows it
+      // shares with the previous lane's sample to that lane and absorbs the rows the next
+      // lane's sample shares with it (both sides evaluate the same match on the original
+      // weights, so nothing is counted twice or lost).
+      float rw0 = aw00, rw1 = aw01, rw2 = aw10, rw3 = aw11;
+      if (LPP > 1) {
+        const int r0 = off, r1 = off + dx, r2 = off + dy, r3 = off + dx + dy;
+        const int n_off = __shfl_down_sync(0xffffffffu, off, 1, LPP);
+        const int n_dx = __shfl_down_sync(0xffffffffu, dx, 1, LPP);
+        const int n_dy = __shfl_down_sync(0xffffffffu, dy, 1, LPP);
+        const float nw0 = __shfl_down_sync(0xffffffffu, aw00, 1, LPP);
+        const float nw1 = __shfl_down_sync(0xffffffffu, aw01, 1, LPP);
+        const float nw2 = __shfl_down_sync(0xffffffffu, aw10, 1, LPP);
+        const float nw3 = __shfl_down_sync(0xffffffffu, aw11, 1, LPP);
+        const int p_off = __shfl_up_sync(0xffffffffu, off, 1, LPP);
+        const int p_dx = __shfl_up_sync(0xffffffffu, dx, 1, LPP);
+        const int p_dy = __shfl_up_sync(0xffffffffu, dy, 1, LPP);
+        if (sub > 0 && s < LP) {   // rows also touched by sample s-1: that lane scatters them
+          const int p0 = p_off, p1 = p_off + p_dx, p2 = p_off + p_dy, p3 = p_off + p_dx + p_dy;
+          if (r0 == p0 || r0 == p1 || r0 == p2 || r0 == p3) rw0 = 0.f;
+          if (r1 == p0 || r1 == p1 || r1 == p2 || r1 == p3) rw1 = 0.f;
+          if (r2 == p0 || r2 == p1 || r2 == p2 || r2 == p3) rw2 = 0.f;
+          if (r3 == p0 || r3 == p1 || r3 == p2 || r3 == p3) rw3 = 0.f;
+        }
+        if (sub + 1 < LPP && s + 1 < LP) {   // rows of sample s+1 that coincide with mine
+          const int n0 = n_off, n1 = n_off + n_dx, n2 = n_off + n_dy, n3 = n_off + n_dx + n_dy;
+#define PCT_ABSORB(nr, nw)              \
+  if ((nr) == r0) rw0 += (nw);          \
+  else if ((nr) == r1) rw1 += (nw);     \
+  else if ((nr) == r2) rw2 += (nw);     \
+  else if ((nr) == r3) rw3 += (nw);
+          PCT_ABSORB(n0, nw0)
+          PCT_ABSORB(n1, nw1)
+          PCT_ABSORB(n2, nw2)
+          PCT_ABSORB(n3, nw3)
+#undef PCT_ABSORB
+        }
+      }
       float D00 = 0.f, D01 = 0.f, D10 = 0.f, D11 = 0.f;   // full dot products of MY sample
 #pragma unroll
       for (int j = 0; j < LPP; ++j) {
@@ -491,10 +598,10 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           const int o = __shfl_sync(0xffffffffu, off, j, LPP);
           const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
           const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
-          const float b00 = __shfl_sync(0xffffffffu, aw00, j, LPP);
-          const float b01 = __shfl_sync(0xffffffffu, aw01, j, LPP);
-          const float b10 = __shfl_sync(0xffffffffu, aw10, j, LPP);
-          const float b11 = __shfl_sync(0xffffffffu, aw11, j, LPP);
+          const float b00 = __shfl_sync(0xffffffffu, rw0, j, LPP);
+          const float b01 = __shfl_sync(0xffffffffu, rw1, j, LPP);
+          const float b10 = __shfl_sync(0xffffffffu, rw2, j, LPP);
+          const float b11 = __shfl_sync(0xffffffffu, rw3, j, LPP);
           PCT_CHECK_TAP(o, ox, oy, (m * D + sub * VE), VE, (long long)S * MD);
           const T* p00 = vimg + o;
           const T* p10 = p00 + oy;
@@ -558,6 +665,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       }
     }
   }
+  __syncthreads();
+  iter.finish();
 }
 
 // Zero-fill of the grad_value accumulator.  A kernel, not cudaMemsetAsync: a memset may be placed on

@@ -1,15 +1,14 @@
 #!/bin/bash
-# Build tuning variants of the library (different CTA sizes => different register budgets) into
-# scripts/_build/; scripts/tune.py picks one through PCTRANS_MSDA_LIB.
+# Build tuning variants of the library into scripts/_build/ (picked through PCTRANS_MSDA_LIB).
+#   scripts/build_variants.sh name1:"-DX=1 -DY=2" name2:"-DZ=3" ...
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p scripts/_build
-for spec in "$@"; do   # spec = FWD:BWD  e.g. 1024:512
-  f=${spec%%:*}; b=${spec##*:}
-  out=scripts/_build/libpctrans_msda_f${f}_b${b}.so
+for spec in "$@"; do
+  name=${spec%%:*}; defs=${spec#*:}
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared \
-       --cudart shared -ccbin /usr/bin/g++ -DPCT_FWD_THREADS=$f -DPCT_BWD_THREADS=$b \
-       -o $out pctrans_b200/csrc/msda_capi.cu &
+       --cudart shared -ccbin /usr/bin/g++ $defs \
+       -o scripts/_build/libpctrans_msda_$name.so pctrans_b200/csrc/msda_capi.cu &
 done
 wait
-ls -la scripts/_build/*.so
+ls scripts/_build/*.so
