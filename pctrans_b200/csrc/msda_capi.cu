@@ -142,7 +142,8 @@ int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi,
                    pct::FusedRef fr) {
   constexpr int PPW = 32 / LPP;
   const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
-  const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kBwdVecThreads);
+  const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags,
+                                          FUSED ? pct::kBwdFusedThreads : pct::kBwdVecThreads);
   pct::msda_bwd_vec_kernel<T, LPP, VB, FUSED><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
       gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, fr,

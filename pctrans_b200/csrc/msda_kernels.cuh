@@ -50,6 +50,10 @@ namespace pct {
 #ifndef PCT_BWD_THREADS
 #define PCT_BWD_THREADS 768
 #endif
+#ifndef PCT_BWD_FUSED_THREADS
+#define PCT_BWD_FUSED_THREADS 640
+#endif
+constexpr int kBwdFusedThreads = PCT_BWD_FUSED_THREADS;  // fused backward carries more state
 constexpr int kVecThreads = PCT_FWD_THREADS;     // forward: one persistent 32-warp CTA per SM
 constexpr int kBwdVecThreads = PCT_BWD_THREADS;  // backward needs ~80 registers per thread
 constexpr int kGenericThreads = 256;
@@ -364,10 +368,21 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     // exp(logit - max) and divide the output once by their sum
     float lmax = 0.f, esum = 0.f;
     const float* rp = nullptr;
+    // up to three rounds of this lane's logits stay in registers (L*P <= 3*LPP: every PCTrans
+    // shape); longer sample lists re-read them through L1
+    float lg0 = -INFINITY, lg1 = -INFINITY, lg2 = -INFINITY;
+    const bool lg_regs = FUSED && (LP <= 3 * LPP);
     if (FUSED) {
       rp = fr.ref + ((long long)b * Lq + (qvalid ? q : Lq - 1)) * L * fr.ref_dim;
       float mx = -INFINITY;
-      for (int s = sub; s < LP; s += LPP) mx = fmaxf(mx, __ldg(ap + s));
+      if (lg_regs) {
+        if (sub < LP) lg0 = __ldg(ap + sub);
+        if (sub + LPP < LP) lg1 = __ldg(ap + sub + LPP);
+        if (sub + 2 * LPP < LP) lg2 = __ldg(ap + sub + 2 * LPP);
+        mx = fmaxf(lg0, fmaxf(lg1, lg2));
+      } else {
+        for (int s = sub; s < LP; s += LPP) mx = fmaxf(mx, __ldg(ap + s));
+      }
       lmax = group_max<LPP>(mx);
     }
 
@@ -376,7 +391,7 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     float a_n = 0.f;
     if (sub < LP) {
       xy_n = __ldg(lp + sub);
-      a_n = __ldg(ap + sub);
+      a_n = lg_regs ? lg0 : __ldg(ap + sub);
     }
     for (int s0 = 0; s0 < LP; s0 += LPP) {
       const int s = s0 + sub;
@@ -384,7 +399,7 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       float a = a_n;
       if (s + LPP < LP) {
         xy_n = __ldg(lp + s + LPP);
-        a_n = __ldg(ap + s + LPP);
+        a_n = lg_regs ? (s0 == 0 ? lg1 : lg2) : __ldg(ap + s + LPP);
       }
       int off = 0, dx = 0, dy = 0;
       float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
@@ -450,7 +465,7 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 // With FUSED the kernel writes grad w.r.t. the raw offsets into `grad_loc` and grad w.r.t. the raw
 // logits into `grad_attn` (softmax backward: a_s * (g_s - sum_t a_t g_t)).
 template <typename T, int LPP, int VB, bool FUSED>
-__global__ void __launch_bounds__(kBwdVecThreads, 1)
+__global__ void __launch_bounds__(FUSED ? kBwdFusedThreads : kBwdVecThreads, 1)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, const T* __restrict__ grad_out,
@@ -493,13 +508,25 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     // fused softmax: max and normaliser of the pair's logits before the first tap
     float lmax = 0.f, inv_sum = 1.f, ag_dot = 0.f;
     const float* rp = nullptr;
+    // this lane's logits of up to three rounds, then its softmax weights (pa) and the raw
+    // d/d(attn) values (pg) of the same samples, kept for the softmax backward at the end
+    float lg0 = -INFINITY, lg1 = -INFINITY, lg2 = -INFINITY;
+    float pa0 = 0.f, pa1 = 0.f, pa2 = 0.f, pg0 = 0.f, pg1 = 0.f, pg2 = 0.f;
+    const bool lg_regs = FUSED && (LP <= 3 * LPP);
     if (FUSED) {
       rp = fr.ref + ((long long)b * Lq + (qvalid ? q : Lq - 1)) * L * fr.ref_dim;
-      float mx = -INFINITY;
-      for (int s = sub; s < LP; s += LPP) mx = fmaxf(mx, __ldg(ap + s));
-      lmax = group_max<LPP>(mx);
-      float es = 0.f;
-      for (int s = sub; s < LP; s += LPP) es += expf(__ldg(ap + s) - lmax);
+      float mx = -INFINITY, es = 0.f;
+      if (lg_regs) {
+        if (sub < LP) lg0 = __ldg(ap + sub);
+        if (sub + LPP < LP) lg1 = __ldg(ap + sub + LPP);
+        if (sub + 2 * LPP < LP) lg2 = __ldg(ap + sub + 2 * LPP);
+        lmax = group_max<LPP>(fmaxf(lg0, fmaxf(lg1, lg2)));
+        es = expf(lg0 - lmax) + expf(lg1 - lmax) + expf(lg2 - lmax);   // exp(-inf) = 0 for unused slots
+      } else {
+        for (int s = sub; s < LP; s += LPP) mx = fmaxf(mx, __ldg(ap + s));
+        lmax = group_max<LPP>(mx);
+        for (int s = sub; s < LP; s += LPP) es += expf(__ldg(ap + s) - lmax);
+      }
       inv_sum = 1.f / group_sum<LPP>(es);
     }
 
@@ -507,7 +534,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     float a_n = 0.f;
     if (sub < LP) {
       xy_n = __ldg(lp + sub);
-      a_n = __ldg(ap + sub);
+      a_n = lg_regs ? lg0 : __ldg(ap + sub);
     }
     for (int s0 = 0; s0 < LP; s0 += LPP) {
       const int s = s0 + sub;
@@ -516,7 +543,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       const float2 raw_off = xy_n;
       if (s + LPP < LP) {
         xy_n = __ldg(lp + s + LPP);
-        a_n = __ldg(ap + s + LPP);
+        a_n = lg_regs ? (s0 == 0 ? lg1 : lg2) : __ldg(ap + s + LPP);
       }
       // this lane's sample
       int off = 0, dx = 0, dy = 0;
@@ -643,24 +670,34 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         const float s_gh = ch00 * D00 + ch01 * D01 + ch10 * D10 + ch11 * D11;
         const float s_gw = cw00 * D00 + cw01 * D01 + cw10 * D10 + cw11 * D11;
         const long long si = pair * LP + s;
-        grad_attn[si] = s_val;                                                       // cuh:161
+        if (!lg_regs) grad_attn[si] = s_val;                                         // cuh:161
         float2 gl = make_float2(Wf * s_gw * a, Hf * s_gh * a);                      // cuh:162-163
         if (FUSED) {
           gl.x *= dloc.x;
           gl.y *= dloc.y;
           ag_dot = fmaf(a, s_val, ag_dot);
+          if (s0 == 0) { pa0 = a; pg0 = s_val; }
+          else if (s0 == LPP) { pa1 = a; pg1 = s_val; }
+          else { pa2 = a; pg2 = s_val; }
         }
         reinterpret_cast<float2*>(grad_loc)[si] = gl;
       }
     }
     if (FUSED) {
-      // softmax backward over the pair's L*P logits: each lane re-reads the g_s it just wrote
+      // softmax backward over the pair's L*P logits: a_s * (g_s - sum_t a_t g_t)
       const float dot = group_sum<LPP>(ag_dot);
       if (qvalid) {
-        for (int s = sub; s < LP; s += LPP) {
-          const long long si = pair * LP + s;
-          const float a = expf(__ldg(ap + s) - lmax) * inv_sum;
-          grad_attn[si] = a * (grad_attn[si] - dot);
+        if (lg_regs) {
+          const long long si = pair * LP + sub;
+          if (sub < LP) grad_attn[si] = pa0 * (pg0 - dot);
+          if (sub + LPP < LP) grad_attn[si + LPP] = pa1 * (pg1 - dot);
+          if (sub + 2 * LPP < LP) grad_attn[si + 2 * LPP] = pa2 * (pg2 - dot);
+        } else {   // each lane re-reads the g_s it wrote above
+          for (int s = sub; s < LP; s += LPP) {
+            const long long si = pair * LP + s;
+            const float a = expf(__ldg(ap + s) - lmax) * inv_sum;
+            grad_attn[si] = a * (grad_attn[si] - dot);
+          }
         }
       }
     }
