@@ -390,16 +390,16 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     float2 xy_n = make_float2(0.f, 0.f);
     float a_n = 0.f;
     if (sub < LP) {
-      xy_n = __ldg(lp + sub);
-      a_n = lg_regs ? lg0 : __ldg(ap + sub);
+      xy_n = __ldcs(lp + sub);
+      a_n = lg_regs ? lg0 : __ldcs(ap + sub);
     }
     for (int s0 = 0; s0 < LP; s0 += LPP) {
       const int s = s0 + sub;
       float2 xy = xy_n;
       float a = a_n;
       if (s + LPP < LP) {
-        xy_n = __ldg(lp + s + LPP);
-        a_n = lg_regs ? (s0 == 0 ? lg1 : lg2) : __ldg(ap + s + LPP);
+        xy_n = __ldcs(lp + s + LPP);
+        a_n = lg_regs ? (s0 == 0 ? lg1 : lg2) : __ldcs(ap + s + LPP);
       }
       int off = 0, dx = 0, dy = 0;
       float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
@@ -533,8 +533,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     float2 xy_n = make_float2(0.f, 0.f);
     float a_n = 0.f;
     if (sub < LP) {
-      xy_n = __ldg(lp + sub);
-      a_n = lg_regs ? lg0 : __ldg(ap + sub);
+      xy_n = __ldcs(lp + sub);
+      a_n = lg_regs ? lg0 : __ldcs(ap + sub);
     }
     for (int s0 = 0; s0 < LP; s0 += LPP) {
       const int s = s0 + sub;
@@ -542,8 +542,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       float a = a_n;
       const float2 raw_off = xy_n;
       if (s + LPP < LP) {
-        xy_n = __ldg(lp + s + LPP);
-        a_n = lg_regs ? (s0 == 0 ? lg1 : lg2) : __ldg(ap + s + LPP);
+        xy_n = __ldcs(lp + s + LPP);
+        a_n = lg_regs ? (s0 == 0 ? lg1 : lg2) : __ldcs(ap + s + LPP);
       }
       // this lane's sample
       int off = 0, dx = 0, dy = 0;
@@ -670,7 +670,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         const float s_gh = ch00 * D00 + ch01 * D01 + ch10 * D10 + ch11 * D11;
         const float s_gw = cw00 * D00 + cw01 * D01 + cw10 * D10 + cw11 * D11;
         const long long si = pair * LP + s;
-        if (!lg_regs) grad_attn[si] = s_val;                                         // cuh:161
+        if (!FUSED) __stcs(grad_attn + si, s_val);                                   // cuh:161
+        else if (!lg_regs) grad_attn[si] = s_val;
         float2 gl = make_float2(Wf * s_gw * a, Hf * s_gh * a);                      // cuh:162-163
         if (FUSED) {
           gl.x *= dloc.x;
@@ -680,7 +681,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           else if (s0 == LPP) { pa1 = a; pg1 = s_val; }
           else { pa2 = a; pg2 = s_val; }
         }
-        reinterpret_cast<float2*>(grad_loc)[si] = gl;
+        __stcs(reinterpret_cast<float2*>(grad_loc) + si, gl);
       }
     }
     if (FUSED) {
