@@ -18,6 +18,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import torch  # noqa: E402
 
@@ -40,6 +41,9 @@ def main():
     ap.add_argument("--core", default="cuda", choices=["cuda", "gridsample"])
     ap.add_argument("--fused", type=int, default=1, help="use the fused-prologue kernels (default)")
     ap.add_argument("--tf32", type=int, default=0, help="allow TF32 tensor cores for the Linears")
+    ap.add_argument("--autocast", default="none", choices=["none", "bf16"],
+                    help="run the encoder under bf16 autocast (the reference disables autocast here "
+                         "because its kernels are fp32-only, PD/msdeformattn.py:314-320)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -55,12 +59,12 @@ def main():
     pyramid = PYR[args.pyramid]
 
     if args.core == "gridsample":
-        from oracle import msda_oracle
+        from _gridsample import grid_sample_core
 
         class _Core:
             @staticmethod
             def apply(value, shapes, lsi, loc, attn, step):
-                return msda_oracle.core_grid_sample(value, shapes, loc, attn)
+                return grid_sample_core(value, shapes, loc, attn)
         mod_file.MSDeformAttnFunction = _Core
 
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
@@ -79,13 +83,18 @@ def main():
     params = [p for p in model.parameters()]
     side = torch.cuda.Stream()
 
+    import contextlib
+    amp = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if args.autocast == "bf16" \
+        else contextlib.nullcontext
+
     def step():
         if args.mode == "infer":
-            with torch.no_grad():
+            with torch.no_grad(), amp():
                 return model(srcs, pos)[0]
         model.zero_grad(set_to_none=True)
-        mem = model(srcs, pos)[0]
-        mem.square().mean().backward()
+        with amp():
+            mem = model(srcs, pos)[0]
+        mem.float().square().mean().backward()
         if dist is not None:
             # DDP-style exchange: one flat bucket on a side stream (model/build.py:89)
             side.wait_stream(torch.cuda.current_stream())
@@ -117,7 +126,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "bench": "encoder", "mode": args.mode, "core": args.core, "fused": bool(args.fused),
-            "tf32": bool(args.tf32), "pyramid": args.pyramid,
+            "tf32": bool(args.tf32), "autocast": args.autocast, "pyramid": args.pyramid,
             "d_model": args.d_model, "layers": args.layers, "n_gpus": world, "batch_per_gpu": n,
             "global_batch": n * world, "ms_per_step": ms,
             "query_layers_per_s": world * n * lq * args.layers / (ms * 1e-3),

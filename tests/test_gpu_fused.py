@@ -139,3 +139,33 @@ def test_fused_unsupported_shapes_are_reported():
     with pytest.raises(RuntimeError):
         MSDeformAttnFusedFunction.apply(v, sh, lsi, ref, torch.zeros(1, 4, 2, 1, 2, 2, device=DEV),
                                         torch.zeros(1, 4, 2, 2, device=DEV))
+
+
+def test_module_under_bf16_autocast_tracks_fp32():
+    """The reference pins this block to fp32 because its kernels have no half path
+    (PD/msdeformattn.py:314-320, cu:69); ours accepts bf16 values: under autocast the module's
+    output stays within bf16 accuracy of the fp32 run, forward and parameter gradients."""
+    torch.manual_seed(1)
+    m = MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4).to(DEV)
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.02)
+        m.sampling_offsets.bias.add_(0.27)
+        m.attention_weights.weight.normal_(0, 0.1)
+    shapes = ((16, 16), (8, 8), (4, 4))
+    sh, lsi, S = synth.level_tensors(shapes, device=DEV)
+    src = torch.randn(2, S, 256, device=DEV)
+    ref = synth.encoder_reference_points(shapes).to(DEV)[None, :, None, :].expand(2, S, 3, 2).contiguous()
+
+    def run(autocast):
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = m(src, ref, src, sh, lsi)
+        out.float().square().mean().backward()
+        return out.detach().float(), m.value_proj.weight.grad.clone(), m.sampling_offsets.weight.grad.clone()
+
+    o32, gv32, go32 = run(False)
+    o16, gv16, go16 = run(True)
+    assert rel(o16, o32) <= 3e-2
+    assert float((gv16 - gv32).norm() / gv32.norm()) <= 5e-2
+    # d/d(location) is a difference of neighbouring bf16-rounded values: the noisiest gradient
+    assert float((go16 - go32).norm() / go32.norm()) <= 0.25
