@@ -377,8 +377,9 @@ def main():
         d2h = sum(r.numel() * r.element_size() for r in res)
         e2e = {"value": world * queries_per_step * e2e_steps / (float(ms_e2e) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "api": "pctrans_b200.host_pipeline.HostPipeline.forward_backward "
-                      "(pinned host tensors -> MSDeformAttnFunction fwd+bwd -> pinned host tensors)"}
+               "api": "pct_msda_host_forward_backward (C ABI, include/pct_msda.h) through "
+                      "pctrans_b200.host_pipeline.HostPipeline: pinned host buffers in, chunked "
+                      "H2D || fwd+bwd kernels || D2H on three streams, pinned host buffers out"}
     sampler.stop()
 
     # ---- roofline of the dominant kernel ------------------------------------------------------

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define PCT_MSDA_ABI_VERSION 2
+#define PCT_MSDA_ABI_VERSION 3
 
 /* value_dtype */
 #define PCT_MSDA_F32 0
@@ -150,6 +150,34 @@ int pct_msda_fused_backward(const void* value, const int64_t* spatial_shapes,
                             int channels, int num_levels, int num_query, int num_point,
                             int value_dtype, void* workspace, size_t workspace_bytes,
                             void* cuda_stream);
+
+/*
+ * Host pipeline: the same op for callers whose tensors live in HOST memory (the end-to-end path
+ * bench.py reports as `e2e`).  A context owns three CUDA streams and device staging buffers that
+ * grow on demand; a call cuts the batch into chunks of images (the op is per-image independent),
+ * overlaps H2D copies, kernels and D2H copies, and returns when the results are in host memory.
+ * Pinned (page-locked) host buffers give full-duplex copies; pageable buffers work but serialise.
+ * spatial_shapes / level_start_index are HOST arrays here.  One call at a time per context;
+ * contexts are independent (one per device / thread).
+ */
+typedef struct pct_msda_host_ctx pct_msda_host_ctx;
+
+int pct_msda_host_ctx_create(pct_msda_host_ctx** ctx, int device, int chunk_images /* 0 = batch/16 */);
+void pct_msda_host_ctx_destroy(pct_msda_host_ctx* ctx);
+
+int pct_msda_host_forward(pct_msda_host_ctx* ctx, const void* value, const int64_t* spatial_shapes,
+                          const int64_t* level_start_index, const void* sampling_loc,
+                          const void* attn_weight, void* output, int batch, int spatial_size,
+                          int num_heads, int channels, int num_levels, int num_query,
+                          int num_point, int value_dtype);
+
+int pct_msda_host_forward_backward(pct_msda_host_ctx* ctx, const void* value,
+                                   const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                   const void* sampling_loc, const void* attn_weight,
+                                   const void* grad_output, void* output, void* grad_value,
+                                   void* grad_sampling_loc, void* grad_attn_weight, int batch,
+                                   int spatial_size, int num_heads, int channels, int num_levels,
+                                   int num_query, int num_point, int value_dtype);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # PCTRANS_MSDA_LIB selects another build of the SAME C ABI (the bounds-checking debug library in
 # tests); it is not a fallback: a missing file is still an ImportError.
 LIB_PATH = os.environ.get("PCTRANS_MSDA_LIB") or os.path.join(_PKG_DIR, "_build", "libpctrans_msda.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}
 
@@ -26,6 +26,8 @@ EXPORTS = (
     "pct_msda_kernel_family", "pct_msda_forward", "pct_msda_forward_ex",
     "pct_msda_backward_workspace_bytes", "pct_msda_backward", "pct_msda_backward_ex",
     "pct_msda_fused_forward", "pct_msda_fused_backward",
+    "pct_msda_host_ctx_create", "pct_msda_host_ctx_destroy", "pct_msda_host_forward",
+    "pct_msda_host_forward_backward",
 )
 E_UNSUPPORTED = 1007
 
