@@ -33,6 +33,10 @@
  * void*; NULL = legacy default stream) of the CURRENT device, never synchronises the host, is
  * re-entrant and may be called from any host thread (cu:70,140 use the current stream too).
  *
+ * The persistent kernels balance their tail through a ring of 512 module-scope counter slots, one
+ * per launch; launches may overlap freely, but a CUDA graph that captured a call must not be
+ * replayed concurrently with itself (both replays would share the captured slot).
+ *
  * Errors: 0 on success; 1..999 = the cudaError_t of the failing runtime call or launch
  * (the reference only printf()s launch errors, cuh:953-957); >= 1000 = PCT_MSDA_E_* below.
  * There is no CPU fallback of any kind.

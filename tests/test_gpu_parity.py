@@ -351,3 +351,70 @@ def test_host_pipeline_matches_direct_call(dtype, N):
     assert rel(gv, ref_gv.float().cpu().numpy()) <= (1e-6 if dtype == torch.float32 else 1e-2)
     with pytest.raises(RuntimeError):
         pipe.forward_backward(d(hv), sh, lsi, hl, ha, hg)
+
+
+def test_reentrant_from_host_threads_on_separate_streams():
+    """include/pct_msda.h promises re-entrancy: four host threads, each with its own stream and its
+    own inputs, run forward+backward concurrently; every result equals the serial one."""
+    import threading
+    cases = []
+    for k in range(4):
+        value, sh, lsi, loc, attn = synth.make_inputs(4, ((20, 17), (10, 9), (5, 5)), M=8, D=32, P=4,
+                                                      regime="O", seed=40 + k)
+        g = torch.randn(4, value.shape[1], 256, generator=torch.Generator().manual_seed(k))
+        cases.append(tuple(t.to(DEV) for t in (value, sh, lsi, loc, attn, g)))
+    serial = [(_cabi.forward(*c[:5]), _cabi.backward(*c)) for c in cases]
+    torch.cuda.synchronize()
+    results, errors = [None] * 4, []
+
+    def work(k):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(10):
+                    out = _cabi.forward(*cases[k][:5])
+                    grads = _cabi.backward(*cases[k])
+            st.synchronize()
+            results[k] = (out, grads)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(4):
+        assert torch.equal(results[k][0], serial[k][0])
+        assert torch.equal(results[k][1][1], serial[k][1][1]) and torch.equal(results[k][1][2], serial[k][1][2])
+        assert rel(results[k][1][0], serial[k][1][0].cpu().numpy()) <= 1e-6      # atomic order only
+
+
+def test_cuda_graph_capture_and_replay():
+    """The C ABI never synchronises or allocates, so a forward+backward can be captured into a CUDA
+    graph and replayed (one replay at a time, see include/pct_msda.h)."""
+    value, sh, lsi, loc, attn = synth.make_inputs(2, synth.CVPPP_448, M=8, D=16, P=4, regime="R", seed=3)
+    g = torch.randn(2, value.shape[1], 128, generator=torch.Generator().manual_seed(9))
+    v, s, l, lo, at, go = (t.to(DEV) for t in (value, sh, lsi, loc, attn, g))
+    out = torch.empty(2, value.shape[1], 128, device=DEV)
+    grads = (torch.empty_like(v), torch.empty_like(lo), torch.empty_like(at))
+    ref_out = _cabi.forward(v, s, l, lo, at)
+    ref_g = _cabi.backward(v, s, l, lo, at, go)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _cabi.forward(v, s, l, lo, at, out=out)
+        _cabi.backward(v, s, l, lo, at, go, out=grads)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        _cabi.forward(v, s, l, lo, at, out=out)
+        _cabi.backward(v, s, l, lo, at, go, out=grads)
+    for _ in range(3):
+        out.zero_()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out)
+    assert torch.equal(grads[1], ref_g[1]) and torch.equal(grads[2], ref_g[2])
+    assert rel(grads[0], ref_g[0].cpu().numpy()) <= 1e-6
