@@ -69,6 +69,8 @@ extern "C" {
 
 /* flags for the *_ex entry points (0 = library default; used by the tuning harness) */
 #define PCT_MSDA_FLAG_FORCE_GENERIC 0x1u /* use the any-D scalar kernels even when a vector path fits */
+#define PCT_MSDA_FLAG_BF16_ACCUM 0x8u    /* backward, bf16 values: accumulate grad_value directly in bf16
+                                            (packed bf16x2 reductions, no workspace; every tap rounds) */
 /* bits 8..15: threads/32 of the persistent CTA; bits 16..19: CTAs per SM; bits 20..24: 1 + static
  * share of the task list in sixteenths (tuning only) */
 

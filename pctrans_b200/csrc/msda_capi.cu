@@ -135,18 +135,18 @@ int launch_fwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi,
   return (int)cudaGetLastError();
 }
 
-template <typename T, int LPP, int VB, bool FUSED>
+template <typename T, int LPP, int VB, bool FUSED, typename ACC = float>
 int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
-                   const void* attn, const void* grad_out, float* gacc, void* grad_loc,
+                   const void* attn, const void* grad_out, void* gacc, void* grad_loc,
                    void* grad_attn, const Dims& d, int sm_count, cudaStream_t st, unsigned flags,
                    pct::FusedRef fr) {
   constexpr int PPW = 32 / LPP;
   const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags,
                                           FUSED ? pct::kBwdFusedThreads : pct::kBwdVecThreads);
-  pct::msda_bwd_vec_kernel<T, LPP, VB, FUSED><<<ls.grid, ls.block, 0, st>>>(
+  pct::msda_bwd_vec_kernel<T, LPP, VB, FUSED, ACC><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
-      gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, fr,
+      (ACC*)gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, fr,
       make_sched(n_tasks, ls.grid, ls.block / 32, flags));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
@@ -166,7 +166,7 @@ int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi,
 using FwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
                             void*, const Dims&, int, cudaStream_t, unsigned, pct::FusedRef);
 using BwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
-                            const void*, float*, void*, void*, const Dims&, int, cudaStream_t,
+                            const void*, void*, void*, void*, const Dims&, int, cudaStream_t,
                             unsigned, pct::FusedRef);
 
 template <bool FUSED>
@@ -177,6 +177,20 @@ FwdLauncher pick_fwd(const VecPlan& plan, int dtype) {
   } else {
     if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, __nv_bfloat16, 16, FUSED) }
     if (plan.vb == 8 && plan.lanes == 1) return launch_fwd_vec<__nv_bfloat16, 1, 8, FUSED>;
+  }
+  return nullptr;
+}
+
+// bf16 values, bf16 accumulator (opt-in): 8-byte lanes only
+BwdLauncher pick_bwd_bf16_accum(const VecPlan& plan) {
+  if (plan.vb != 8) return nullptr;
+  switch (plan.lanes) {
+    case 1: return launch_bwd_vec<__nv_bfloat16, 1, 8, false, __nv_bfloat16>;
+    case 2: return launch_bwd_vec<__nv_bfloat16, 2, 8, false, __nv_bfloat16>;
+    case 4: return launch_bwd_vec<__nv_bfloat16, 4, 8, false, __nv_bfloat16>;
+    case 8: return launch_bwd_vec<__nv_bfloat16, 8, 8, false, __nv_bfloat16>;
+    case 16: return launch_bwd_vec<__nv_bfloat16, 16, 8, false, __nv_bfloat16>;
+    case 32: return launch_bwd_vec<__nv_bfloat16, 32, 8, false, __nv_bfloat16>;
   }
   return nullptr;
 }
@@ -432,7 +446,17 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
       !aligned(sampling_loc, ls) || !aligned(attn_weight, ls) || !aligned(grad_sampling_loc, ls) ||
       !aligned(grad_attn_weight, ls) || !aligned(spatial_shapes, 8) || !aligned(level_start_index, 8))
     return PCT_MSDA_E_MISALIGNED;
-  const size_t need = pct_msda_backward_workspace_bytes(batch, spatial_size, num_heads, channels, value_dtype);
+  // opt-in bf16 accumulator: grad_value itself is the accumulator (packed bf16x2 reductions), no
+  // fp32 workspace; only on the unfused vector path with 8-byte lanes
+  BwdLauncher bf16_accum = nullptr;
+  if ((flags & PCT_MSDA_FLAG_BF16_ACCUM) && value_dtype == PCT_MSDA_BF16 && !fused && n_value > 0 &&
+      n_pairs > 0 && aligned(grad_sampling_loc, 8) && aligned(grad_value, 8)) {
+    const VecPlan p = vec_eligible(d, value_dtype, flags, value, grad_output, grad_value, sampling_loc,
+                                   attn_weight);
+    if (p.lanes > 0) bf16_accum = pick_bwd_bf16_accum(p);
+  }
+  const size_t need = bf16_accum ? 0 : pct_msda_backward_workspace_bytes(batch, spatial_size, num_heads,
+                                                                         channels, value_dtype);
   if (need > 0 && (!workspace || workspace_bytes < need || !aligned(workspace, 16)))
     return PCT_MSDA_E_WORKSPACE;
   int sm_count = 0;
@@ -441,8 +465,9 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
   cudaStream_t st = (cudaStream_t)cuda_stream;
 
   // grad_value accumulates through reductions: clear the accumulator image first.
-  void* acc_image = value_dtype == PCT_MSDA_BF16 ? workspace : grad_value;
-  const size_t acc_bytes = value_dtype == PCT_MSDA_BF16 ? need : (size_t)n_value * es;
+  const bool ws_accum = value_dtype == PCT_MSDA_BF16 && !bf16_accum;
+  void* acc_image = ws_accum ? workspace : grad_value;
+  const size_t acc_bytes = ws_accum ? need : (size_t)n_value * es;
   if (acc_bytes > 0) {
     rc = zero_fill(acc_image, acc_bytes, sm_count, st);
     if (rc) return rc;
@@ -466,11 +491,12 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
                          ? vec_eligible(d, value_dtype, flags, value, grad_output, acc_image,
                                         sampling_loc, attn_weight)
                          : VecPlan{};
-  if (BwdLauncher fn = vp.lanes == 0 ? nullptr
-                       : fused       ? pick_bwd<true>(vp, value_dtype)
-                                     : pick_bwd<false>(vp, value_dtype)) {
+  if (BwdLauncher fn = bf16_accum        ? bf16_accum
+                       : vp.lanes == 0 ? nullptr
+                       : fused         ? pick_bwd<true>(vp, value_dtype)
+                                       : pick_bwd<false>(vp, value_dtype)) {
     rc = fn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-            (float*)acc_image, grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags, fr);
+            acc_image, grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags, fr);
   } else if (fused) {
     return PCT_MSDA_E_UNSUPPORTED;
   } else {
@@ -496,7 +522,7 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
     }
   }
   if (rc) return rc;
-  if (value_dtype == PCT_MSDA_BF16)
+  if (ws_accum)
     return round_workspace_to_bf16((const float*)workspace, grad_value, n_value, sm_count, st);
   return 0;
 }

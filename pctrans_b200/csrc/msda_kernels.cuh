@@ -163,6 +163,17 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
                : "memory");
 }
 
+// bf16 accumulator (opt-in, PCT_MSDA_FLAG_BF16_ACCUM): four channels as one 8-byte packed reduction.
+// Halves the L2 sector operations of the scatter, but every reduction rounds the running sum to
+// bf16 (~48 roundings per pixel), so it is not the default.
+__device__ __forceinline__ void red_add_v4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1, %2};" ::"l"(p),
+               "r"(*reinterpret_cast<const unsigned*>(&lo)),
+               "r"(*reinterpret_cast<const unsigned*>(&hi))
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Bilinear taps (cuh:45-58 geometry, cuh:61-83 per-corner bounds, cuh:293 in-range predicate).
 //
@@ -464,12 +475,12 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 // ---------------------------------------------------------------------------------------------
 // With FUSED the kernel writes grad w.r.t. the raw offsets into `grad_loc` and grad w.r.t. the raw
 // logits into `grad_attn` (softmax backward: a_s * (g_s - sum_t a_t g_t)).
-template <typename T, int LPP, int VB, bool FUSED>
+template <typename T, int LPP, int VB, bool FUSED, typename ACC = float>
 __global__ void __launch_bounds__(FUSED ? kBwdFusedThreads : kBwdVecThreads, 1)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, const T* __restrict__ grad_out,
-                    float* __restrict__ gacc, float* __restrict__ grad_loc,
+                    ACC* __restrict__ gacc, float* __restrict__ grad_loc,
                     float* __restrict__ grad_attn, int N, int S, int M, int L, int Lq, int P,
                     FusedRef fr, SchedArgs sched) {
   using CV = ChanVec<T, VB>;
@@ -500,7 +511,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     const float* ap = attn + pair * LP;
     const long long img_off = ((long long)b * S * M + m) * D + sub * VE;
     const T* vimg = value + img_off;
-    float* gimg = gacc + img_off;
+    ACC* gimg = gacc + img_off;
 
     float go[VE];
     CV::load_stream(grad_out + pair * D + sub * VE, go);
@@ -638,8 +649,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           CV::load(p10, v10);
           CV::load(p10 + ox, v11);
           // grad_value taps: w_k * attn * grad_out  (cuh:118,130,139,148,157)
-          float* g00 = gimg + o;
-          float* g10 = g00 + oy;
+          ACC* g00 = gimg + o;
+          ACC* g10 = g00 + oy;
 #pragma unroll
           for (int i = 0; i < VE; i += 4) {
             if (b00 != 0.f) red_add_v4(g00 + i, b00 * go[i], b00 * go[i + 1], b00 * go[i + 2], b00 * go[i + 3]);
