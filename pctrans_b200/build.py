@@ -33,11 +33,33 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libpctrans_msda.so")
 
 
+def _source_hash(extra: str = "") -> str:
+    import hashlib
+    h = hashlib.sha256(extra.encode())
+    for d in DEPS:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _is_current(lib_path: str, extra: str = "") -> bool:
+    """A library is current when the hash of the sources it was built from (stored next to it)
+    matches the tree -- file mtimes do not survive the snapshot copy to the GPU box."""
+    try:
+        with open(lib_path + ".srchash") as f:
+            return os.path.exists(lib_path) and f.read().strip() == _source_hash(extra)
+    except OSError:
+        return False
+
+
+def _stamp(lib_path: str, extra: str = "") -> None:
+    with open(lib_path + ".srchash", "w") as f:
+        f.write(_source_hash(extra))
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return not _is_current(LIB_PATH)
 
 
 DEBUG_LIB_PATH = os.path.join(OUT_DIR, "libpctrans_msda_dbg.so")
@@ -49,8 +71,7 @@ def build_library(force: bool = False, verbose: bool = False, debug: bool = Fals
     checked in-kernel; used by tests/test_gpu_bounds.py through PCTRANS_MSDA_LIB)."""
     if debug:
         os.makedirs(OUT_DIR, exist_ok=True)
-        if not force and os.path.exists(DEBUG_LIB_PATH) and all(
-                os.path.getmtime(os.path.join(CSRC, d)) <= os.path.getmtime(DEBUG_LIB_PATH) for d in DEPS):
+        if not force and _is_current(DEBUG_LIB_PATH, "debug"):
             return DEBUG_LIB_PATH
         cmd = [_nvcc()] + NVCC_FLAGS + ["-DPCT_MSDA_BOUNDS_CHECK", "-o", DEBUG_LIB_PATH] + \
             [os.path.join(CSRC, s) for s in SOURCES] + ["-ccbin", "/usr/bin/g++"]
@@ -58,6 +79,7 @@ def build_library(force: bool = False, verbose: bool = False, debug: bool = Fals
         if proc.returncode != 0:
             sys.stderr.write(proc.stdout)
             raise RuntimeError("nvcc failed building the bounds-check library")
+        _stamp(DEBUG_LIB_PATH, "debug")
         return DEBUG_LIB_PATH
     if not force and not needs_build():
         return LIB_PATH
@@ -74,6 +96,7 @@ def build_library(force: bool = False, verbose: bool = False, debug: bool = Fals
         sys.stderr.write(proc.stdout)
     if proc.returncode != 0:
         raise RuntimeError(f"nvcc failed (exit {proc.returncode}); see {log_path}")
+    _stamp(LIB_PATH)
     return LIB_PATH
 
 

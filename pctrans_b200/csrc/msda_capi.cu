@@ -246,7 +246,7 @@ int zero_fill(void* p, size_t bytes, int sm_count, cudaStream_t st) {
   if (!aligned(p, 16)) return (int)cudaMemsetAsync(p, 0, bytes, st);
   const long long n16 = (long long)(bytes / 16);
   const int n_tail = (int)(bytes % 16);
-  long long want = (n16 + 255) / 256;
+  long long want = (n16 + 1023) / 1024;   // 4 stores per thread per pass
   long long cap = (long long)sm_count * 8;
   const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
   pct::msda_zero_kernel<<<grid, 256, 0, st>>>((uint4*)p, n16, (unsigned char*)p + n16 * 16, n_tail);

@@ -724,9 +724,15 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 __global__ void msda_zero_kernel(uint4* __restrict__ dst, long long n16, unsigned char* tail,
                                  int n_tail) {
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
-       i += (long long)gridDim.x * blockDim.x)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {   // four independent 16-byte stores in flight
     dst[i] = z;
+    dst[i + stride] = z;
+    dst[i + 2 * stride] = z;
+    dst[i + 3 * stride] = z;
+  }
+  for (; i < n16; i += stride) dst[i] = z;
   if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0;
 }
 
