@@ -71,6 +71,10 @@ extern "C" {
 #define PCT_MSDA_FLAG_FORCE_GENERIC 0x1u /* use the any-D scalar kernels even when a vector path fits */
 #define PCT_MSDA_FLAG_BF16_ACCUM 0x8u    /* backward, bf16 values: accumulate grad_value directly in bf16
                                             (packed bf16x2 reductions, no workspace; every tap rounds) */
+#define PCT_MSDA_FLAG_DETERMINISTIC 0x10u /* backward: bit-reproducible grad_value (64-bit fixed-point
+                                            integer reductions; needs pct_msda_backward_workspace_bytes_ex
+                                            bytes of workspace; vector-path shapes only, else
+                                            PCT_MSDA_E_UNSUPPORTED) */
 /* bits 8..15: threads/32 of the persistent CTA; bits 16..19: CTAs per SM; bits 20..24: 1 + static
  * share of the task list in sixteenths (tuning only) */
 
@@ -106,6 +110,10 @@ int pct_msda_forward_ex(const void* value, const int64_t* spatial_shapes,
  * bf16 path accumulates grad_value in an fp32 scratch image before rounding it once). */
 size_t pct_msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
                                          int value_dtype);
+
+/* Workspace for pct_msda_backward_ex with `flags` (PCT_MSDA_FLAG_DETERMINISTIC changes it). */
+size_t pct_msda_backward_workspace_bytes_ex(int batch, int spatial_size, int num_heads,
+                                            int channels, int value_dtype, unsigned flags);
 
 /* Gradients of pct_msda_forward w.r.t. value, sampling_loc and attn_weight.
  * Replaces ms_deform_attn_cuda_backward (cu:88-158).  grad_value (N,S,M,D) value_dtype,

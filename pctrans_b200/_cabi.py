@@ -24,12 +24,16 @@ DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}
 EXPORTS = (
     "pct_msda_abi_version", "pct_msda_error_string", "pct_msda_launch_count",
     "pct_msda_kernel_family", "pct_msda_forward", "pct_msda_forward_ex",
-    "pct_msda_backward_workspace_bytes", "pct_msda_backward", "pct_msda_backward_ex",
+    "pct_msda_backward_workspace_bytes", "pct_msda_backward_workspace_bytes_ex",
+    "pct_msda_backward", "pct_msda_backward_ex",
     "pct_msda_fused_forward", "pct_msda_fused_backward",
     "pct_msda_host_ctx_create", "pct_msda_host_ctx_destroy", "pct_msda_host_forward",
     "pct_msda_host_forward_backward",
 )
 E_UNSUPPORTED = 1007
+FLAG_FORCE_GENERIC = 0x1
+FLAG_BF16_ACCUM = 0x8
+FLAG_DETERMINISTIC = 0x10
 
 _lib = None
 _lock = threading.Lock()
@@ -68,6 +72,8 @@ def load():
         lib.pct_msda_forward_ex.argtypes = fwd_args + [u32]
         lib.pct_msda_backward_workspace_bytes.restype = sz
         lib.pct_msda_backward_workspace_bytes.argtypes = [i32] * 5
+        lib.pct_msda_backward_workspace_bytes_ex.restype = sz
+        lib.pct_msda_backward_workspace_bytes_ex.argtypes = [i32] * 5 + [u32]
         bwd_args = [vp] * 9 + [i32] * 8 + [vp, sz, vp]
         lib.pct_msda_backward.restype = i32
         lib.pct_msda_backward.argtypes = bwd_args
@@ -138,7 +144,7 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
         grad_attn = torch.empty_like(attn_weight)
     else:
         grad_value, grad_loc, grad_attn = out
-    ws_bytes = int(lib.pct_msda_backward_workspace_bytes(N, S, M, D, code))
+    ws_bytes = int(lib.pct_msda_backward_workspace_bytes_ex(N, S, M, D, code, flags))
     ws = workspace
     if ws_bytes and (ws is None or ws.numel() < ws_bytes):
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device)

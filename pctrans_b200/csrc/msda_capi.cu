@@ -139,7 +139,7 @@ template <typename T, int LPP, int VB, bool FUSED, typename ACC = float>
 int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                    const void* attn, const void* grad_out, void* gacc, void* grad_loc,
                    void* grad_attn, const Dims& d, int sm_count, cudaStream_t st, unsigned flags,
-                   pct::FusedRef fr) {
+                   pct::FusedRef fr, const pct::DetScratch* det) {
   constexpr int PPW = 32 / LPP;
   const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags,
@@ -147,7 +147,7 @@ int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi,
   pct::msda_bwd_vec_kernel<T, LPP, VB, FUSED, ACC><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
       (ACC*)gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, fr,
-      make_sched(n_tasks, ls.grid, ls.block / 32, flags));
+      make_sched(n_tasks, ls.grid, ls.block / 32, flags), det);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
@@ -167,7 +167,7 @@ using FwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const v
                             void*, const Dims&, int, cudaStream_t, unsigned, pct::FusedRef);
 using BwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
                             const void*, void*, void*, void*, const Dims&, int, cudaStream_t,
-                            unsigned, pct::FusedRef);
+                            unsigned, pct::FusedRef, const pct::DetScratch*);
 
 template <bool FUSED>
 FwdLauncher pick_fwd(const VecPlan& plan, int dtype) {
@@ -178,6 +178,23 @@ FwdLauncher pick_fwd(const VecPlan& plan, int dtype) {
     if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, __nv_bfloat16, 16, FUSED) }
     if (plan.vb == 8 && plan.lanes == 1) return launch_fwd_vec<__nv_bfloat16, 1, 8, FUSED>;
   }
+  return nullptr;
+}
+
+// deterministic fixed-point accumulator (opt-in): lanes of 4 channels only
+BwdLauncher pick_bwd_deterministic(const VecPlan& plan, int dtype) {
+#define PCT_DET_CASES(T, VB)                                                   \
+  switch (plan.lanes) {                                                        \
+    case 1: return launch_bwd_vec<T, 1, VB, false, long long>;                 \
+    case 2: return launch_bwd_vec<T, 2, VB, false, long long>;                 \
+    case 4: return launch_bwd_vec<T, 4, VB, false, long long>;                 \
+    case 8: return launch_bwd_vec<T, 8, VB, false, long long>;                 \
+    case 16: return launch_bwd_vec<T, 16, VB, false, long long>;               \
+    case 32: return launch_bwd_vec<T, 32, VB, false, long long>;               \
+  }
+  if (dtype == PCT_MSDA_F32 && plan.vb == 16) { PCT_DET_CASES(float, 16) }
+  if (dtype == PCT_MSDA_BF16 && plan.vb == 8) { PCT_DET_CASES(__nv_bfloat16, 8) }
+#undef PCT_DET_CASES
   return nullptr;
 }
 
@@ -411,6 +428,14 @@ int pct_msda_forward(const void* value, const int64_t* spatial_shapes,
                              num_query, num_point, value_dtype, cuda_stream, 0u);
 }
 
+size_t pct_msda_backward_workspace_bytes_ex(int batch, int spatial_size, int num_heads,
+                                            int channels, int value_dtype, unsigned flags) {
+  if (batch <= 0 || spatial_size <= 0 || num_heads <= 0 || channels <= 0) return 0;
+  const size_t n = (size_t)batch * spatial_size * num_heads * channels;
+  if (flags & PCT_MSDA_FLAG_DETERMINISTIC) return n * sizeof(long long) + 16;  // + DetScratch
+  return pct_msda_backward_workspace_bytes(batch, spatial_size, num_heads, channels, value_dtype);
+}
+
 size_t pct_msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
                                          int value_dtype) {
   if (value_dtype != PCT_MSDA_BF16) return 0;
@@ -455,8 +480,22 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
                                    attn_weight);
     if (p.lanes > 0) bf16_accum = pick_bwd_bf16_accum(p);
   }
-  const size_t need = bf16_accum ? 0 : pct_msda_backward_workspace_bytes(batch, spatial_size, num_heads,
-                                                                         channels, value_dtype);
+  // opt-in deterministic accumulator: 64-bit fixed point in the workspace (+ DetScratch tail)
+  BwdLauncher det_fn = nullptr;
+  if (flags & PCT_MSDA_FLAG_DETERMINISTIC) {
+    if (fused || value_dtype == PCT_MSDA_F64 || n_value == 0 || n_pairs == 0 || !aligned(grad_sampling_loc, 8))
+      return PCT_MSDA_E_UNSUPPORTED;
+    const VecPlan p = vec_eligible(d, value_dtype, flags, value, grad_output, workspace, sampling_loc,
+                                   attn_weight);
+    det_fn = p.lanes > 0 ? pick_bwd_deterministic(p, value_dtype) : nullptr;
+    if (!det_fn) return PCT_MSDA_E_UNSUPPORTED;
+    bf16_accum = nullptr;
+  }
+  const size_t need = det_fn ? pct_msda_backward_workspace_bytes_ex(batch, spatial_size, num_heads, channels,
+                                                                    value_dtype, flags)
+                      : bf16_accum ? 0
+                                   : pct_msda_backward_workspace_bytes(batch, spatial_size, num_heads,
+                                                                       channels, value_dtype);
   if (need > 0 && (!workspace || workspace_bytes < need || !aligned(workspace, 16)))
     return PCT_MSDA_E_WORKSPACE;
   int sm_count = 0;
@@ -465,9 +504,11 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
   cudaStream_t st = (cudaStream_t)cuda_stream;
 
   // grad_value accumulates through reductions: clear the accumulator image first.
-  const bool ws_accum = value_dtype == PCT_MSDA_BF16 && !bf16_accum;
+  const bool ws_accum = det_fn || (value_dtype == PCT_MSDA_BF16 && !bf16_accum);
   void* acc_image = ws_accum ? workspace : grad_value;
   const size_t acc_bytes = ws_accum ? need : (size_t)n_value * es;
+  pct::DetScratch* det = det_fn ? reinterpret_cast<pct::DetScratch*>((char*)workspace + (size_t)n_value * 8)
+                                : nullptr;
   if (acc_bytes > 0) {
     rc = zero_fill(acc_image, acc_bytes, sm_count, st);
     if (rc) return rc;
@@ -491,12 +532,27 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
                          ? vec_eligible(d, value_dtype, flags, value, grad_output, acc_image,
                                         sampling_loc, attn_weight)
                          : VecPlan{};
-  if (BwdLauncher fn = bf16_accum        ? bf16_accum
+  if (det_fn) {
+    // scale from max|grad_out| (accumulator and DetScratch were just zeroed)
+    const long long n_go = n_pairs * d.D;
+    long long want = (n_go + 1023) / 1024;
+    const int grid = (int)(want < 1 ? 1 : (want < (long long)sm_count * 8 ? want : (long long)sm_count * 8));
+    if (value_dtype == PCT_MSDA_F32)
+      pct::msda_absmax_kernel<float><<<grid, 256, 0, st>>>((const float*)grad_output, n_go, det);
+    else
+      pct::msda_absmax_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)grad_output, n_go, det);
+    pct::msda_det_scale_kernel<<<1, 1, 0, st>>>(det);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (BwdLauncher fn = det_fn            ? det_fn
+                       : bf16_accum      ? bf16_accum
                        : vp.lanes == 0 ? nullptr
                        : fused         ? pick_bwd<true>(vp, value_dtype)
                                        : pick_bwd<false>(vp, value_dtype)) {
     rc = fn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-            acc_image, grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags, fr);
+            acc_image, grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags, fr, det);
   } else if (fused) {
     return PCT_MSDA_E_UNSUPPORTED;
   } else {
@@ -522,6 +578,16 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
     }
   }
   if (rc) return rc;
+  if (det_fn) {
+    long long want = (n_value + 255) / 256;
+    const int grid = (int)(want < (long long)sm_count * 16 ? want : (long long)sm_count * 16);
+    if (value_dtype == PCT_MSDA_F32)
+      pct::msda_fixed_to_value_kernel<float><<<grid, 256, 0, st>>>((const long long*)workspace, (float*)grad_value, n_value, det);
+    else
+      pct::msda_fixed_to_value_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const long long*)workspace, (__nv_bfloat16*)grad_value, n_value, det);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+  }
   if (ws_accum)
     return round_workspace_to_bf16((const float*)workspace, grad_value, n_value, sm_count, st);
   return 0;

@@ -157,6 +157,27 @@ struct ChanVec<__nv_bfloat16, 8> {
   }
 };
 
+// scalar element access with conversion (generic kernels, deterministic helpers)
+template <typename T>
+struct Scalar {
+  template <typename CT>
+  static __device__ __forceinline__ CT load(const T* p) { return (CT)(*p); }
+  template <typename CT>
+  static __device__ __forceinline__ void store(T* p, CT v) { *p = (T)v; }
+};
+template <>
+struct Scalar<__nv_bfloat16> {
+  template <typename CT>
+  static __device__ __forceinline__ CT load(const __nv_bfloat16* p) { return (CT)__bfloat162float(*p); }
+  template <typename CT>
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, CT v) { *p = __float2bfloat16_rn((float)v); }
+};
+
+struct DetScratch {       // tail of the deterministic workspace
+  unsigned int max_bits;  // bit pattern of max |grad_out| (non-negative floats order like ints)
+  float scale;            // 2^(38 - exponent(max))
+};
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
                "f"(d)
@@ -173,6 +194,8 @@ __device__ __forceinline__ void red_add_v4(__nv_bfloat16* p, float a, float b, f
                "r"(*reinterpret_cast<const unsigned*>(&hi))
                : "memory");
 }
+
+__device__ __forceinline__ void red_add_v4(long long*, float, float, float, float) {}  // unused (kDet path scatters itself)
 
 // ---------------------------------------------------------------------------------------------
 // Bilinear taps (cuh:45-58 geometry, cuh:61-83 per-corner bounds, cuh:293 in-range predicate).
@@ -482,7 +505,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
                     const float* __restrict__ attn, const T* __restrict__ grad_out,
                     ACC* __restrict__ gacc, float* __restrict__ grad_loc,
                     float* __restrict__ grad_attn, int N, int S, int M, int L, int Lq, int P,
-                    FusedRef fr, SchedArgs sched) {
+                    FusedRef fr, SchedArgs sched, const DetScratch* det) {
   using CV = ChanVec<T, VB>;
   constexpr int VE = CV::kElems;
   constexpr int D = LPP * VE;
@@ -515,6 +538,18 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 
     float go[VE];
     CV::load_stream(grad_out + pair * D + sub * VE, go);
+    // deterministic mode: this lane scatters channels {i*LPP + sub} so that the LPP lanes of a
+    // pair cover contiguous 8-byte accumulators (whole sectors) with each integer reduction
+    constexpr bool kDet = sizeof(ACC) == 8;
+    float gs[VE];
+    ACC* grow = gacc;
+    if (kDet) {
+      const float scale = det->scale;
+#pragma unroll
+      for (int i = 0; i < VE; ++i)
+        gs[i] = Scalar<T>::template load<float>(grad_out + pair * D + i * LPP + sub) * scale;
+      grow = gacc + ((long long)b * S * M + m) * D + sub;
+    }
 
     // fused softmax: max and normaliser of the pair's logits before the first tap
     float lmax = 0.f, inv_sum = 1.f, ag_dot = 0.f;
@@ -651,12 +686,24 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           // grad_value taps: w_k * attn * grad_out  (cuh:118,130,139,148,157)
           ACC* g00 = gimg + o;
           ACC* g10 = g00 + oy;
+          if (kDet) {
+            unsigned long long* r00 = reinterpret_cast<unsigned long long*>(grow + o);
+            unsigned long long* r10 = r00 + oy;
 #pragma unroll
-          for (int i = 0; i < VE; i += 4) {
-            if (b00 != 0.f) red_add_v4(g00 + i, b00 * go[i], b00 * go[i + 1], b00 * go[i + 2], b00 * go[i + 3]);
-            if (b01 != 0.f) red_add_v4(g00 + ox + i, b01 * go[i], b01 * go[i + 1], b01 * go[i + 2], b01 * go[i + 3]);
-            if (b10 != 0.f) red_add_v4(g10 + i, b10 * go[i], b10 * go[i + 1], b10 * go[i + 2], b10 * go[i + 3]);
-            if (b11 != 0.f) red_add_v4(g10 + ox + i, b11 * go[i], b11 * go[i + 1], b11 * go[i + 2], b11 * go[i + 3]);
+            for (int i = 0; i < VE; ++i) {
+              if (b00 != 0.f) atomicAdd(r00 + i * LPP, (unsigned long long)__float2ll_rn(b00 * gs[i]));
+              if (b01 != 0.f) atomicAdd(r00 + ox + i * LPP, (unsigned long long)__float2ll_rn(b01 * gs[i]));
+              if (b10 != 0.f) atomicAdd(r10 + i * LPP, (unsigned long long)__float2ll_rn(b10 * gs[i]));
+              if (b11 != 0.f) atomicAdd(r10 + ox + i * LPP, (unsigned long long)__float2ll_rn(b11 * gs[i]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < VE; i += 4) {
+              if (b00 != 0.f) red_add_v4(g00 + i, b00 * go[i], b00 * go[i + 1], b00 * go[i + 2], b00 * go[i + 3]);
+              if (b01 != 0.f) red_add_v4(g00 + ox + i, b01 * go[i], b01 * go[i + 1], b01 * go[i + 2], b01 * go[i + 3]);
+              if (b10 != 0.f) red_add_v4(g10 + i, b10 * go[i], b10 * go[i + 1], b10 * go[i + 2], b10 * go[i + 3]);
+              if (b11 != 0.f) red_add_v4(g10 + ox + i, b11 * go[i], b11 * go[i + 1], b11 * go[i + 2], b11 * go[i + 3]);
+            }
           }
           float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
 #pragma unroll
@@ -736,6 +783,43 @@ __global__ void msda_zero_kernel(uint4* __restrict__ dst, long long n16, unsigne
   if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Deterministic grad_value (PCT_MSDA_FLAG_DETERMINISTIC).  Floating-point
+// atomics make the summation order -- and therefore the low bits of grad_value -- vary from run to
+// run (the reference has the same property, cuh:130-157).  Here every contribution is converted to
+// 64-bit fixed point with a power-of-two scale derived from max|grad_out| and accumulated with
+// integer reductions, which are associative: the result is bit-identical across runs and launch
+// shapes.  Costs 8-byte accumulators (twice the L2 reduction traffic) and one conversion pass.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void msda_absmax_kernel(const T* __restrict__ x, long long n, DetScratch* sc) {
+  unsigned int m = 0u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = fabsf(Scalar<T>::template load<float>(x + i));
+    if (v == v && v <= 3.4e38f) m = max(m, __float_as_uint(v));   // ignore NaN / Inf
+  }
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, w));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(&sc->max_bits, m);
+}
+
+__global__ void msda_det_scale_kernel(DetScratch* sc) {
+  const float mx = __uint_as_float(sc->max_bits);
+  // max*scale lands in [2^38, 2^39): bilinear weight * attention <= 1, so 2^24 contributions per
+  // element still fit in 63 bits
+  sc->scale = mx > 0.f ? ldexpf(1.f, 38 - ilogbf(mx)) : 1.f;
+}
+
+template <typename T>
+__global__ void msda_fixed_to_value_kernel(const long long* __restrict__ acc, T* __restrict__ dst,
+                                           long long n, const DetScratch* sc) {
+  const float inv = 1.f / sc->scale;   // exact: power of two
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    Scalar<T>::template store<float>(dst + i, __ll2float_rn(acc[i]) * inv);
+}
+
 // fp32 scratch image -> bf16 grad_value (bf16 path only)
 __global__ void msda_round_to_bf16_kernel(const float* __restrict__ src,
                                           __nv_bfloat16* __restrict__ dst, long long n8) {
@@ -763,21 +847,6 @@ __global__ void msda_round_to_bf16_tail_kernel(const float* __restrict__ src,
 // over the channels; same stream ordering.  CT = compute / location type, AT = grad_value
 // accumulator type in global memory.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-struct Scalar {
-  template <typename CT>
-  static __device__ __forceinline__ CT load(const T* p) { return (CT)(*p); }
-  template <typename CT>
-  static __device__ __forceinline__ void store(T* p, CT v) { *p = (T)v; }
-};
-template <>
-struct Scalar<__nv_bfloat16> {
-  template <typename CT>
-  static __device__ __forceinline__ CT load(const __nv_bfloat16* p) { return (CT)__bfloat162float(*p); }
-  template <typename CT>
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, CT v) { *p = __float2bfloat16_rn((float)v); }
-};
-
 template <typename CT>
 struct TapsG {
   long long off[4];

@@ -86,7 +86,20 @@ class MSDeformAttnFunction(Function):
         grad_output = grad_output.contiguous()
         if grad_output.dtype != value.dtype:
             grad_output = grad_output.to(value.dtype)
-        grad_value, grad_loc, grad_attn = _cabi.backward(value, shapes, lsi, loc, attn, grad_output)
+        flags = 0
+        if torch.are_deterministic_algorithms_enabled():
+            # bit-reproducible grad_value (fixed-point integer reductions); the reference's float
+            # atomics (cuh:130-157) have no such mode
+            N, S, M, D = value.shape
+            supported = (value.dtype in (torch.float32, torch.bfloat16) and value.numel() > 0
+                         and _cabi.kernel_family(D, shapes.shape[0], loc.shape[4], value.dtype, True) == 1)
+            if supported:
+                flags |= _cabi.FLAG_DETERMINISTIC
+            elif not torch.is_deterministic_algorithms_warn_only_enabled():
+                raise RuntimeError("MSDeformAttnFunction.backward has no deterministic implementation "
+                                   f"for value dtype {value.dtype} / head dim {D}")
+        grad_value, grad_loc, grad_attn = _cabi.backward(value, shapes, lsi, loc, attn, grad_output,
+                                                         flags=flags)
         return grad_value, None, None, grad_loc, grad_attn, None
 
 
@@ -107,6 +120,7 @@ class MSDeformAttnFusedFunction(Function):
     @staticmethod
     def supported(value, reference_points, n_levels, n_points):
         return (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16)
+                and not torch.are_deterministic_algorithms_enabled()   # deterministic mode: unfused route
                 and not reference_points.requires_grad and value.shape[1] > 0
                 and reference_points.shape[-1] in (2, 4)
                 and _cabi.kernel_family(value.shape[3], n_levels, n_points, value.dtype) == 1

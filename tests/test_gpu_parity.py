@@ -435,3 +435,43 @@ def test_opt_in_bf16_accumulator_flag():
     assert rel(gl, ref[1]) <= 1e-4 and rel(ga, ref[2]) <= 1e-4      # unaffected by the accumulator
     gv_default = _cabi.backward(d(vb), d(sh), d(lsi), d(loc), d(attn), d(gb))[0]
     assert rel(gv_default, ref[0]) <= 1e-2
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.float32, 16), (torch.bfloat16, 32)])
+def test_deterministic_backward_is_bit_reproducible(dtype, D):
+    """PCT_MSDA_FLAG_DETERMINISTIC: grad_value from 64-bit fixed-point integer reductions is
+    identical bit for bit across runs and launch shapes, and as accurate as the default path."""
+    value, sh, lsi, loc, attn = synth.make_inputs(4, synth.CVPPP_448, M=8, D=D, P=4, regime="R", seed=6)
+    loc = synth.nudge_off_grid(loc, [tuple(r) for r in sh.tolist()])
+    g = torch.randn(4, value.shape[1], 8 * D, generator=torch.Generator().manual_seed(7)) * 37.0
+    v_ref = value.to(dtype).float()
+    g_ref = g.to(dtype).float()
+    d = lambda t: t.to(DEV)
+    args = (d(value.to(dtype)), d(sh), d(lsi), d(loc), d(attn), d(g.to(dtype)))
+    runs = [_cabi.backward(*args, flags=_cabi.FLAG_DETERMINISTIC) for _ in range(3)]
+    runs.append(_cabi.backward(*args, flags=_cabi.FLAG_DETERMINISTIC | (8 << 8) | (3 << 16)))  # other launch shape
+    for r in runs[1:]:
+        assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1]) and torch.equal(r[2], runs[0][2])
+    ref = oracle.backward_c(v_ref, sh, lsi, loc, attn, g_ref)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel(runs[0][0], ref[0]) <= tol and rel(runs[0][1], ref[1]) <= tol and rel(runs[0][2], ref[2]) <= tol
+    # the default (float atomics) path usually differs in the last bits between runs
+    assert rel(_cabi.backward(*args)[0], ref[0]) <= tol
+    # through autograd: torch.use_deterministic_algorithms(True) selects it
+    torch.use_deterministic_algorithms(True)
+    try:
+        grads = []
+        for _ in range(2):
+            v = args[0].clone().requires_grad_(True)
+            out = MSDeformAttnFunction.apply(v, args[1], args[2], args[3], args[4], 128)
+            out.backward(args[5])
+            grads.append(v.grad)
+        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], runs[0][0])
+        with pytest.raises(RuntimeError):     # fp64 / odd head dims have no deterministic kernel
+            v64 = torch.randn(1, 6, 2, 30, device=DEV, dtype=torch.float64, requires_grad=True)
+            s1 = torch.tensor([[2, 3]], device=DEV)
+            l1 = torch.zeros(1, dtype=torch.long, device=DEV)
+            MSDeformAttnFunction.apply(v64, s1, l1, torch.rand(1, 4, 2, 1, 2, 2, device=DEV, dtype=torch.float64),
+                                       torch.rand(1, 4, 2, 1, 2, device=DEV, dtype=torch.float64), 128).sum().backward()
+    finally:
+        torch.use_deterministic_algorithms(False)
