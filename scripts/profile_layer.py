@@ -16,13 +16,15 @@ model = enc.MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder
 srcs = [torch.randn(n, 256, h, w, device=dev) for h, w in synth.CVPPP_512]
 pe = enc.PositionEmbeddingSine(128, normalize=True)
 pos = [pe(s) for s in srcs]
+amp = len(sys.argv) > 3 and sys.argv[3] == "bf16"
 def step():
-    if train:
-        model.zero_grad(set_to_none=True)
-        model(srcs, pos)[0].square().mean().backward()
-    else:
-        with torch.no_grad():
-            model(srcs, pos)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        if train:
+            model.zero_grad(set_to_none=True)
+            model(srcs, pos)[0].float().square().mean().backward()
+        else:
+            with torch.no_grad():
+                model(srcs, pos)
 for _ in range(5): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
