@@ -279,8 +279,21 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # NCCL prints "NCCL version ..." (and any NCCL_DEBUG output) to stdout while the
+        # communicator is created; rank 0's stdout must carry exactly one JSON line, so file
+        # descriptor 1 points at stderr until the first collective has completed
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from pctrans_b200 import _cabi
     from pctrans_b200.functions import MSDeformAttnFunction

@@ -53,6 +53,7 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     n = args.global_batch // world if args.global_batch else args.batch
