@@ -112,7 +112,7 @@ class MSDeformAttn(nn.Module):
                 value.contiguous(), input_spatial_shapes, input_level_start_index,
                 reference_points.float().contiguous(), offsets.float().contiguous(),
                 logits.float().contiguous())
-            return self.output_proj(out.to(query.dtype))
+            return self.output_proj(self._match(out, query))
 
         weights = torch.softmax(logits, dim=-1).view(n, len_q, m, lv, pt)
         locations = self._locations(reference_points, offsets, input_spatial_shapes)
@@ -123,4 +123,12 @@ class MSDeformAttn(nn.Module):
         out = MSDeformAttnFunction.apply(
             value.contiguous(), input_spatial_shapes, input_level_start_index,
             locations.contiguous(), weights.contiguous(), self.im2col_step)
-        return self.output_proj(out.to(query.dtype))
+        return self.output_proj(self._match(out, query))
+
+    @staticmethod
+    def _match(out, query):
+        """Kernel output back to the caller's dtype -- except under autocast, where the following
+        Linear casts its input anyway and a round trip through fp32 would only cost two copies."""
+        if out.dtype == query.dtype or (torch.is_autocast_enabled() and out.is_floating_point()):
+            return out
+        return out.to(query.dtype)
