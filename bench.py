@@ -100,6 +100,23 @@ def measured_peak_gbs():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def onchip_bounds(pyr_name: str, batch: int, dtype: str):
+    """The on-chip resources that actually saturate (from the committed ncu capture of the same
+    shape, profiles/*_onchip_bounds.json): the HBM roofline is not what limits this gather/scatter
+    op.  Informational; None when no capture matches."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_onchip_bounds.json")), reverse=True):
+        try:
+            with open(path) as f:
+                doc = json.load(f)
+            entry = doc.get(f"{pyr_name}/{batch}/{dtype}")
+            if entry:
+                return dict(entry, source=doc.get("source"))
+        except Exception:
+            continue
+    return None
+
+
 def ncu_traffic(pyr_name: str, batch: int, dtype: str, which: str):
     """DRAM bytes per launch of the forward / backward kernel from the committed ncu --set full
     capture of the same shape (profiles/*_ncu_dram_traffic.json), or None."""
@@ -429,6 +446,7 @@ def main():
             "backward": {"ms": bwd_ms, "queries_per_s": queries_per_step / (bwd_ms * 1e-3),
                          "algorithmic_gbs": bwd_gbs, "frac": bwd_gbs / peak},
             "step_algorithmic_gbs": step_gbs, "step_frac_of_peak": step_gbs / peak,
+            "onchip_bounds": onchip_bounds(pyr_name, N, args.dtype) if args.regime == "R" else None,
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
         print(json.dumps(line), flush=True)
