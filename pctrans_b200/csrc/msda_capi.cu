@@ -6,7 +6,6 @@
 #include "../../include/pct_msda.h"
 
 #include <atomic>
-#include <cstdio>
 
 #include "msda_kernels.cuh"
 

@@ -11,7 +11,6 @@
 
 #include <cuda_runtime.h>
 
-#include <cstdlib>
 #include <new>
 
 namespace {
