@@ -40,7 +40,11 @@ _lock = threading.Lock()
 
 
 class MSDAError(RuntimeError):
-    """A pct_msda_* entry point returned a non-zero code."""
+    """A pct_msda_* entry point returned a non-zero code (``.code``)."""
+
+    def __init__(self, msg, code=0):
+        super().__init__(msg)
+        self.code = code
 
 
 def load():
@@ -93,7 +97,7 @@ def load():
 def check(code: int, what: str) -> None:
     if code != 0:
         msg = load().pct_msda_error_string(code).decode()
-        raise MSDAError(f"{what} failed with code {code}: {msg}")
+        raise MSDAError(f"{what} failed with code {code}: {msg}", code)
 
 
 def launch_count() -> int:

@@ -323,7 +323,7 @@ const char* pct_msda_error_string(int code) {
     case PCT_MSDA_E_MISALIGNED: return "pct_msda: buffer is not aligned to its element size";
     case PCT_MSDA_E_WORKSPACE: return "pct_msda: workspace missing or too small";
     case PCT_MSDA_E_TOO_LARGE: return "pct_msda: tensor too large";
-    case PCT_MSDA_E_UNSUPPORTED: return "pct_msda: shape / dtype not supported by the fused entry points";
+    case PCT_MSDA_E_UNSUPPORTED: return "pct_msda: shape / dtype not supported by this entry point or flag (fused and deterministic paths need the vector kernels)";
     default:
       if (code > 0 && code < 1000) return cudaGetErrorString((cudaError_t)code);
       return "pct_msda: unknown error code";

@@ -98,8 +98,17 @@ class MSDeformAttnFunction(Function):
             elif not torch.is_deterministic_algorithms_warn_only_enabled():
                 raise RuntimeError("MSDeformAttnFunction.backward has no deterministic implementation "
                                    f"for value dtype {value.dtype} / head dim {D}")
-        grad_value, grad_loc, grad_attn = _cabi.backward(value, shapes, lsi, loc, attn, grad_output,
-                                                         flags=flags)
+        try:
+            grad_value, grad_loc, grad_attn = _cabi.backward(value, shapes, lsi, loc, attn,
+                                                             grad_output, flags=flags)
+        except _cabi.MSDAError as e:
+            if not (flags and e.code == _cabi.E_UNSUPPORTED):
+                raise
+            # vector-family shape without a deterministic kernel (head rows wider than 512 bytes)
+            if not torch.is_deterministic_algorithms_warn_only_enabled():
+                raise RuntimeError("MSDeformAttnFunction.backward has no deterministic implementation "
+                                   f"for value dtype {value.dtype} / head dim {value.shape[3]}") from e
+            grad_value, grad_loc, grad_attn = _cabi.backward(value, shapes, lsi, loc, attn, grad_output)
         return grad_value, None, None, grad_loc, grad_attn, None
 
 
