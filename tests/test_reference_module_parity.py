@@ -159,3 +159,68 @@ def test_encoder_matches_reference_encoder(ref_encoder_module, monkeypatch):
         mem_o, sh_o, lsi_o = ours(srcs, pos_o)
     assert torch.equal(sh_r, sh_o) and torch.equal(lsi_r, lsi_o)
     assert torch.allclose(mem_o, mem_r, rtol=1e-5, atol=1e-5)
+
+
+def test_pixel_decoder_matches_reference_decoder(ref_encoder_module, monkeypatch):
+    """MSDeformAttnPixelDecoder (PD:164-360): the reference class is instantiated with minimal
+    real stand-ins for the four detectron2 / fvcore helpers it needs (Conv2d-with-norm, get_norm,
+    ShapeSpec, c2_xavier_fill); its state_dict must load into ours with strict=True (checkpoint
+    compatibility) and forward_features must agree on CPU."""
+    import collections
+    import torch.nn.functional as F
+    from torch import nn
+    from oracle import msda_oracle as oracle
+    from pctrans_b200 import encoder as enc
+    from pctrans_b200.modules import ms_deform_attn as mod_file
+
+    class Conv2d(nn.Conv2d):                       # detectron2.layers.Conv2d semantics
+        def __init__(self, *a, norm=None, activation=None, **k):
+            super().__init__(*a, **k)
+            self.norm, self.activation = norm, activation
+
+        def forward(self, x):
+            x = super().forward(x)
+            if self.norm is not None:
+                x = self.norm(x)
+            return self.activation(x) if self.activation is not None else x
+
+    ShapeSpec = collections.namedtuple("ShapeSpec", ["channels", "stride"])
+
+    def c2_xavier_fill(m):
+        nn.init.kaiming_uniform_(m.weight, a=1)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+
+    ref_mod = ref_encoder_module
+    monkeypatch.setattr(ref_mod, "Conv2d", Conv2d)
+    monkeypatch.setattr(ref_mod, "get_norm", lambda norm, c: nn.GroupNorm(32, c) if norm == "GN" else None)
+    monkeypatch.setattr(ref_mod.weight_init, "c2_xavier_fill", c2_xavier_fill, raising=False)
+
+    class _OracleFunction:
+        @staticmethod
+        def apply(value, shapes, lsi, loc, attn, step):
+            return oracle.core_grid_sample(value, shapes, loc, attn)
+
+    monkeypatch.setattr(mod_file, "MSDeformAttnFunction", _OracleFunction)
+    chans = {"res2": (32, 4), "res3": (48, 8), "res4": (64, 16), "res5": (96, 32)}
+    torch.manual_seed(5)
+    ref = ref_mod.MSDeformAttnPixelDecoder(
+        {k: ShapeSpec(*v) for k, v in chans.items()}, transformer_dropout=0.0, transformer_nheads=4,
+        transformer_dim_feedforward=128, transformer_enc_layers=2, conv_dim=64, mask_dim=64, norm="GN",
+        transformer_in_features=["res3", "res4", "res5"], common_stride=4).eval()
+    ours = enc.MSDeformAttnPixelDecoder(
+        chans, transformer_dropout=0.0, transformer_nheads=4, transformer_dim_feedforward=128,
+        transformer_enc_layers=2, conv_dim=64, mask_dim=64, norm="GN",
+        transformer_in_features=("res3", "res4", "res5"), common_stride=4).eval()
+    missing = ours.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    g = torch.Generator().manual_seed(6)
+    feats = {k: torch.randn(2, c, 64 // s, 96 // s, generator=g) for k, (c, s) in chans.items()}
+    with torch.no_grad():
+        r_mask, r_low, r_multi = ref.forward_features(feats)
+        o_mask, o_low, o_multi = ours.forward_features(feats)
+    assert torch.allclose(o_mask, r_mask, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(o_low, r_low, rtol=1e-4, atol=1e-5)
+    assert len(o_multi) == len(r_multi) == 3
+    for a, b in zip(o_multi, r_multi):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
