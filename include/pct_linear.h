@@ -1,0 +1,59 @@
+/*
+ * pct_linear.h -- C ABI of the tensor-core Linear used around the MSDeformAttn op
+ * (the encoder layer's projections and their epilogues).
+ *
+ * Replaces, for fp32 activations on B200, the cuBLAS SIMT-fp32 GEMMs behind the reference's
+ *   value_proj / sampling_offsets / attention_weights / output_proj   OPS/modules/ms_deform_attn.py:55-58
+ *   linear1 / linear2 (FFN) and the residual + LayerNorm after them   PD/msdeformattn.py:107-120,125-126
+ * which the reference runs in fp32 with autocast disabled (PD/msdeformattn.py:314-320).
+ *
+ *   y = epilogue(x @ W^T + bias)        x (rows, in) fp32, W (out, in) fp32, y (rows, out) fp32
+ *
+ * Arithmetic: tcgen05 tensor cores, kind::tf32, with the 3xTF32 split
+ *   x = x_hi + x_lo,  W = W_hi + W_lo,  x@W^T ~= x_hi@W_hi^T + x_hi@W_lo^T + x_lo@W_hi^T
+ * (the dropped x_lo@W_lo^T term is ~2^-22 relative), fp32 accumulation in tensor memory.  The
+ * result matches an fp32 GEMM to a few 1e-7 relative, so the encoder keeps the reference's fp32
+ * parity bar while the GEMMs run on the tensor cores.  The activation is split inside the kernel;
+ * the weight is split and re-tiled once by pct_linear_pack_weight into the order the kernel's
+ * shared-memory stages use, so a stage is one bulk copy (cache the packed copy per weight version).
+ *
+ * Same conventions as pct_msda.h: device pointers, caller-owned buffers, asynchronous on
+ * `cuda_stream`, 0 or an error code (pct_msda_error_string understands them), no CPU fallback.
+ */
+#ifndef PCT_LINEAR_H_
+#define PCT_LINEAR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* epilogue flags */
+#define PCT_LINEAR_RELU 0x1u      /* y = max(., 0)                                        */
+#define PCT_LINEAR_RESIDUAL 0x2u  /* y = residual + (x W^T + b); residual (rows, out)      */
+#define PCT_LINEAR_LAYERNORM 0x4u /* y = LayerNorm(. ) * gamma + beta over the out dim;
+                                     needs out_features <= 256 (one tile holds a whole row) */
+
+/* Constraints everywhere: in_features % 16 == 0, out_features % 16 == 0, 16-byte aligned pointers. */
+
+/* Bytes of the packed weight (0 if the dimensions are not supported). */
+size_t pct_linear_packed_bytes(int in_features, int out_features);
+
+/* w (out, in) fp32 -> packed: per 256-column tile and 16-float K step, the tf32 head of the tile
+ * followed by the fp32 remainder (w - head), each in tensor-core core-matrix order. */
+int pct_linear_pack_weight(const float* w, void* packed, int in_features, int out_features,
+                           void* cuda_stream);
+
+/* y (rows, out) = epilogue(x (rows, in) @ W^T + bias).  bias may be NULL.  residual / ln_gamma /
+ * ln_beta are read only when their flag is set.  rows >= 1. */
+int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
+                       const float* residual, const float* ln_gamma, const float* ln_beta,
+                       float ln_eps, float* y, int rows, int in_features, int out_features,
+                       unsigned flags, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCT_LINEAR_H_ */

@@ -30,6 +30,8 @@ EXPORTS = (
     "pct_msda_host_ctx_create", "pct_msda_host_ctx_destroy", "pct_msda_host_forward",
     "pct_msda_host_forward_backward",
 )
+LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_forward")
+LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM = 0x1, 0x2, 0x4
 E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
 FLAG_BF16_ACCUM = 0x8
@@ -87,6 +89,13 @@ def load():
         lib.pct_msda_fused_forward.argtypes = [vp] * 4 + [i32] + [vp] * 3 + [i32] * 8 + [vp]
         lib.pct_msda_fused_backward.restype = i32
         lib.pct_msda_fused_backward.argtypes = [vp] * 4 + [i32] + [vp] * 6 + [i32] * 8 + [vp, sz, vp]
+        # include/pct_linear.h
+        lib.pct_linear_packed_bytes.restype = sz
+        lib.pct_linear_packed_bytes.argtypes = [i32, i32]
+        lib.pct_linear_pack_weight.restype = i32
+        lib.pct_linear_pack_weight.argtypes = [vp, vp, i32, i32, vp]
+        lib.pct_linear_forward.restype = i32
+        lib.pct_linear_forward.argtypes = [vp] * 6 + [ctypes.c_float, vp] + [i32] * 3 + [u32, vp]
         got = lib.pct_msda_abi_version()
         if got != ABI_VERSION:
             raise ImportError(f"{LIB_PATH}: ABI version {got}, expected {ABI_VERSION}; rebuild")
@@ -209,3 +218,34 @@ def fused_backward(value, spatial_shapes, level_start_index, reference_points, s
             ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(value.device))
     check(rc, "pct_msda_fused_backward")
     return grad_value, grad_off, grad_logits
+
+
+def linear_pack_weight(weight):
+    """(out, in) fp32 weight -> packed 3xTF32 operand (uint8 tensor) for linear_forward."""
+    w = weight.detach().contiguous()
+    n, k = w.shape
+    nbytes = load().pct_linear_packed_bytes(k, n)
+    if nbytes == 0:
+        raise MSDAError(f"pct_linear: unsupported Linear dimensions in={k} out={n}", 1002)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    with torch.cuda.device_of(w):
+        check(load().pct_linear_pack_weight(w.data_ptr(), packed.data_ptr(), k, n,
+                                            _stream_ptr(w.device)), "pct_linear_pack_weight")
+    return packed
+
+
+def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weight=None,
+                   ln_bias=None, ln_eps: float = 1e-5, relu: bool = False, out=None):
+    """y = epilogue(x @ W^T + bias) on the tensor cores (3xTF32); x (rows, in) fp32 contiguous."""
+    rows, k = x.shape
+    n = out_features
+    flags = (LINEAR_RELU if relu else 0) | (LINEAR_RESIDUAL if residual is not None else 0) | \
+        (LINEAR_LAYERNORM if ln_weight is not None else 0)
+    y = out if out is not None else torch.empty((rows, n), dtype=x.dtype, device=x.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device_of(x):
+        check(load().pct_linear_forward(
+            x.data_ptr(), w_packed.data_ptr(), ptr(bias), ptr(residual), ptr(ln_weight),
+            ptr(ln_bias), float(ln_eps), y.data_ptr(), rows, k, n, flags,
+            _stream_ptr(x.device)), "pct_linear_forward")
+    return y

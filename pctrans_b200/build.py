@@ -15,8 +15,9 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libpctrans_msda.so")
-SOURCES = ["msda_capi.cu", "msda_host.cu"]
-DEPS = ["msda_capi.cu", "msda_host.cu", "msda_kernels.cuh", os.path.join("..", "..", "include", "pct_msda.h")]
+SOURCES = ["msda_capi.cu", "msda_host.cu", "linear_tc.cu"]
+DEPS = ["msda_capi.cu", "msda_host.cu", "linear_tc.cu", "msda_kernels.cuh",
+        os.path.join("..", "..", "include", "pct_msda.h"), os.path.join("..", "..", "include", "pct_linear.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

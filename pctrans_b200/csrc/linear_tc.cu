@@ -1,0 +1,578 @@
+// linear_tc.cu -- fp32 Linear on the tcgen05 tensor cores (3xTF32 split), with the encoder layer's
+// epilogues fused: bias, ReLU, residual add, LayerNorm.  C ABI in include/pct_linear.h.
+//
+// One CTA computes a 128-row x (<=256)-column tile of y = x @ W^T:
+//   * the accumulator is a 128-lane x 256-column fp32 block of tensor memory (TMEM);
+//   * the K dimension is streamed in 16-float steps through a two-stage shared-memory ring.  The
+//     weight was split and re-tiled once (pct_linear_pack_weight) into exactly the bytes a stage
+//     holds, so one thread fetches a step's W pieces with a single 32 KB bulk copy (TMA, no
+//     tensor map) that bypasses the load/store pipe.  Four loader warps read the activation step
+//     with 16-byte loads, split it into its tf32 head and the fp32 remainder on the fly, and store
+//     the pieces as 8-row x 16-byte core matrices (the K-major, no-swizzle canonical layout of the
+//     tensor-core shared-memory descriptor);
+//   * one thread of a fifth warp issues six tcgen05.mma (2 k-steps x {hi*hi, hi*lo, lo*hi}) per
+//     stage and commits them to the stage's mbarrier, which hands the stage back to the loaders;
+//     the roles talk through mbarriers only, so loads, copies and MMAs of different steps overlap;
+//   * the epilogue reads the accumulator with tcgen05.ld -- thread t of loader warp w owns row
+//     32*w+t and walks all its columns -- so bias / ReLU / LayerNorm are per-thread arithmetic
+//     (two-pass mean / variance, the pre-norm row parked in TMEM in between, no exchange).
+//     Global traffic of the epilogue (residual in, y out) is transposed through a per-warp
+//     shared-memory patch so that every warp access covers whole 128-byte lines: the kernel is
+//     bound by load/store-pipe wavefronts, not by the tensor core (profiles/r01_linear_*).
+// Two CTAs fit per SM (96 KB of shared memory, 256 TMEM columns each), so one CTA's loads and
+// epilogue overlap the other's MMAs.
+#include "../../include/pct_linear.h"
+#include "../../include/pct_msda.h"
+
+#include <cuda_runtime.h>
+
+namespace pct {
+void count_launch();   // msda_capi.cu
+}
+
+namespace {
+
+constexpr int kBlockM = 128;   // rows per tile = TMEM lanes
+constexpr int kBlockN = 256;   // max columns per tile = TMEM columns allocated
+constexpr int kBlockK = 16;    // floats of K per stage: four 16-byte core-matrix columns
+constexpr int kStages = 2;
+constexpr int kLoaderWarps = 4;                 // load/split x, then run the epilogue
+constexpr int kThreads = (kLoaderWarps + 2) * 32;   // + MMA issuer warp (TMEM owner) + W-copy warp
+constexpr int kMmaK = 8;       // K of one tcgen05.mma.kind::tf32
+
+constexpr int kCoreBytes = 128;                       // one 8 x 16 B core matrix
+constexpr int kLbo = kCoreBytes;                      // K-adjacent core matrices
+constexpr int kSbo = (kBlockK / 4) * kCoreBytes;      // next 8-row group
+constexpr int kABytes = kBlockM * kBlockK * 4;        // one piece (hi or lo) of the x tile
+constexpr int kBBytes = kBlockN * kBlockK * 4;        // one piece of the W tile
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+constexpr int kWStepBytes = 2 * kBBytes;              // packed W: hi piece then lo piece of one K step
+constexpr int kBarrierBytes = 64;
+constexpr int kVecBytes = 3 * kBlockN * 4;            // bias, gamma, beta of the tile's columns
+constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kVecBytes;
+constexpr int kAhead = 3;                             // K steps of x in flight per loader thread
+constexpr int kPatchStride = 36;                      // floats per patch row: conflict-free both ways
+static_assert(kLoaderWarps * 32 * kPatchStride * 4 <= kStages * kStageBytes, "epilogue patches reuse the ring");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kLbo >> 4) << 16) |
+         ((uint64_t)(kSbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+// Instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_instr_desc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+// Bounded wait: a pipeline bug traps (launch error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+
+// 1-D bulk copy global -> shared (TMA without a tensor map); completion counted on `bar`.
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ float tf32_head(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// TMEM -> registers, 16 columns of this thread's lane.  Asynchronous: the registers are valid only
+// after tmem_ld_wait() and tmem_tie16() (which pins later uses of r[] behind the wait).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_tie16(uint32_t* r) {
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),
+                 "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+      "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+      "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+      "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+
+struct LinearArgs {
+  const float* x;
+  const unsigned char* w_packed;
+  const float* bias;
+  const float* residual;
+  const float* gamma;
+  const float* beta;
+  float* y;
+  float eps;
+  int rows, K, N;
+  unsigned flags;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const LinearArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int n0 = blockIdx.x * kBlockN;
+  const int m0 = blockIdx.y * kBlockM;
+  const int n_tile = min(kBlockN, a.N - n0);
+
+  // barriers, kStages each: stage free (its MMAs are done) | x pieces stored | W pieces landed;
+  // then one for "accumulator complete"
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  float* vec_bias = reinterpret_cast<float*>(smem + kStages * kStageBytes + kBarrierBytes);
+  float* vec_gamma = vec_bias + kBlockN;
+  float* vec_beta = vec_gamma + kBlockN;
+  const uint32_t bar_empty = smem_u32(bars);
+  const uint32_t bar_xfull = bar_empty + 8 * kStages;
+  const uint32_t bar_wfull = bar_empty + 16 * kStages;
+  const uint32_t bar_done = bar_empty + 24 * kStages;
+
+  if (warp == kLoaderWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)kBlockN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_xfull + 8 * s, kLoaderWarps * 32);
+      mbar_init(bar_wfull + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int c = tid; c < n_tile; c += kThreads) {   // L1 is streamed through by x: keep these close
+    vec_bias[c] = a.bias ? a.bias[n0 + c] : 0.f;
+    if (a.flags & PCT_LINEAR_LAYERNORM) vec_gamma[c] = a.gamma[n0 + c], vec_beta[c] = a.beta[n0 + c];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const int n_steps = a.K / kBlockK;
+  const uint32_t smem0 = smem_u32(smem);
+
+  if (warp == kLoaderWarps) {
+    // ---- issuer: one thread feeds the tensor core ----------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(n_tile);
+      for (int step = 0; step < n_steps; ++step) {
+        const int s = step % kStages;
+        const uint32_t parity = (step / kStages) & 1;
+        mbar_wait(bar_wfull + 8 * s, parity);
+        mbar_wait(bar_xfull + 8 * s, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem0 + s * kStageBytes;
+#pragma unroll
+        for (int ks = 0; ks < kBlockK / kMmaK; ++ks) {
+          const uint32_t koff = ks * (kMmaK / 4) * kLbo;
+          const uint64_t d_ahi = make_smem_desc(sa + koff);
+          const uint64_t d_alo = make_smem_desc(sa + kABytes + koff);
+          const uint64_t d_bhi = make_smem_desc(sa + 2 * kABytes + koff);
+          const uint64_t d_blo = make_smem_desc(sa + 2 * kABytes + kBBytes + koff);
+          mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);   // small terms first
+          mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
+          mma_tf32(tmem, d_ahi, d_bhi, idesc, 1u);
+        }
+        mma_commit(bar_empty + 8 * s);             // stage free once these MMAs have read it
+        if (step == n_steps - 1) mma_commit(bar_done);
+      }
+    }
+  } else if (warp == kLoaderWarps + 1) {
+    // ---- W producer: one thread streams the packed weight steps with bulk copies --------------
+    const unsigned char* w_tile = a.w_packed + (size_t)blockIdx.x * n_steps * kWStepBytes;
+    auto fetch_w = [&](int step) {
+      const int s = step % kStages;
+      mbar_expect_tx(bar_wfull + 8 * s, kWStepBytes);
+      bulk_load(smem0 + s * kStageBytes + 2 * kABytes, w_tile + (size_t)step * kWStepBytes,
+                kWStepBytes, bar_wfull + 8 * s);
+    };
+    if (lane == 0)
+      for (int step = 0; step < kStages && step < n_steps; ++step) fetch_w(step);
+    // pull this tile's activations (whole rows: one contiguous block) and residual rows towards
+    // L2 now, so the loaders' and the epilogue's dependent loads see L2 latency, not DRAM latency
+    const int tile_rows = min(kBlockM, a.rows - m0);
+    if (tile_rows > 0) {
+      const size_t x_bytes = (size_t)tile_rows * a.K * 4;
+      const char* xp = reinterpret_cast<const char*>(a.x + (size_t)m0 * a.K);
+      for (size_t off = (size_t)lane * 32768; off < x_bytes; off += 32 * 32768) {
+        const size_t nb = x_bytes - off < 32768 ? x_bytes - off : 32768;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xp + off), "r"((uint32_t)nb)
+                     : "memory");
+      }
+      if (a.flags & PCT_LINEAR_RESIDUAL) {
+        for (int r = lane; r < tile_rows; r += 32)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                           a.residual + (size_t)(m0 + r) * a.N + n0),
+                       "r"((uint32_t)(n_tile * 4))
+                       : "memory");
+      }
+    }
+    if (lane == 0)
+      for (int step = kStages; step < n_steps; ++step) {
+        mbar_wait(bar_empty + 8 * (step % kStages), ((step / kStages) - 1) & 1);
+        fetch_w(step);
+      }
+  } else {
+    // ---- loaders: read a K step of x, split it, store the pieces in core-matrix order ---------
+    // float4 i of a piece lives at byte 16*i with i = 32*(row/8) + 8*(k/4) + row%8: eight
+    // consecutive threads fill one core matrix and a warp reads 8 rows x 64 contiguous bytes.
+    const int r8 = tid & 7, kc = (tid >> 3) & 3, rg = tid >> 5;
+    constexpr int kPerThread = kBlockM * kBlockK / 4 / (kLoaderWarps * 32);
+    const float* xrow[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int row = m0 + (rg + kLoaderWarps * j) * 8 + r8;
+      xrow[j] = row < a.rows ? a.x + (size_t)row * a.K + kc * 4 : nullptr;
+    }
+    float4 xq[kAhead][kPerThread];   // kAhead K steps in flight: the loads are DRAM-latency bound
+    auto fetch_x = [&](float4* dst, int step) {
+#pragma unroll
+      for (int j = 0; j < kPerThread; ++j)
+        dst[j] = xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + step * kBlockK))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+#pragma unroll
+    for (int d = 0; d < kAhead; ++d)
+      if (d < n_steps) fetch_x(xq[d], d);
+    for (int step0 = 0; step0 < n_steps; step0 += kAhead) {
+#pragma unroll
+      for (int d = 0; d < kAhead; ++d) {
+        const int step = step0 + d;
+        if (step < n_steps) {
+          const int s = step % kStages;
+          if (step >= kStages) mbar_wait(bar_empty + 8 * s, ((step / kStages) - 1) & 1);
+          float4* a_hi = reinterpret_cast<float4*>(smem + s * kStageBytes);
+          float4* a_lo = reinterpret_cast<float4*>(smem + s * kStageBytes + kABytes);
+#pragma unroll
+          for (int j = 0; j < kPerThread; ++j) {
+            const float4 x4 = xq[d][j];
+            float4 h, l;
+            h.x = tf32_head(x4.x), h.y = tf32_head(x4.y), h.z = tf32_head(x4.z), h.w = tf32_head(x4.w);
+            l.x = x4.x - h.x, l.y = x4.y - h.y, l.z = x4.z - h.z, l.w = x4.w - h.w;
+            a_hi[tid + kLoaderWarps * 32 * j] = h;
+            a_lo[tid + kLoaderWarps * 32 * j] = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_xfull + 8 * s) : "memory");
+          if (step + kAhead < n_steps) fetch_x(xq[d], step + kAhead);
+        }
+      }
+    }
+
+    // ---- epilogue (the loader warps; warp w owns rows 32w .. 32w+31 of the tile) --------------
+    // Row domain: this thread owns one row and walks its columns in TMEM order.
+    // Line domain: a warp instruction covers 4 rows x 128 contiguous bytes of global memory.
+    mbar_wait(bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const bool relu = a.flags & PCT_LINEAR_RELU, has_res = a.flags & PCT_LINEAR_RESIDUAL;
+    float* patch = reinterpret_cast<float*>(smem) + warp * (32 * kPatchStride);
+    float* patch_row = patch + lane * kPatchStride;
+    const int l_row = lane >> 3, l_c4 = (lane & 7) * 4;
+    const size_t warp_off = (size_t)(m0 + warp * 32) * a.N + n0;   // first row of this warp
+    const int rows_left = a.rows - (m0 + warp * 32);
+    float v[32];
+
+    // residual block (32 rows x cw columns at column c): line-domain loads into registers (issued
+    // one block ahead of their use), then through the patch into the row domain
+    float4 res[8];
+    auto fetch_residual = [&](int c, int cw) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = 4 * j + l_row;
+        if (l_c4 < cw && r < rows_left)
+          res[j] = __ldg(
+              reinterpret_cast<const float4*>(a.residual + warp_off + (size_t)r * a.N + c + l_c4));
+      }
+    };
+    auto add_residual = [&](int cw) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4) = res[j];
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (4 * q < cw) {
+          const float4 t = *reinterpret_cast<const float4*>(patch_row + 4 * q);
+          v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
+        }
+      __syncwarp();
+    };
+    // v (row domain) -> y block, through the patch
+    auto store_block = [&](int c, int cw) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (4 * q < cw)
+          *reinterpret_cast<float4*>(patch_row + 4 * q) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      __syncwarp();
+      float4 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        t[j] = *reinterpret_cast<const float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = 4 * j + l_row;
+        if (l_c4 < cw && r < rows_left)
+          *reinterpret_cast<float4*>(a.y + warp_off + (size_t)r * a.N + c + l_c4) = t[j];
+      }
+    };
+    auto load_acc = [&](int c, int cw) {
+      uint32_t u[32];
+      tmem_ld16(t_row + c, u);
+      if (cw > 16) tmem_ld16(t_row + c + 16, u + 16);
+      tmem_ld_wait();
+      tmem_tie16(u);
+      tmem_tie16(u + 16);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+    };
+    auto add_bias = [&](int c, int cw) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (4 * q < cw) {
+          const float4 b = *reinterpret_cast<const float4*>(vec_bias + c + 4 * q);
+          v[4 * q] += b.x, v[4 * q + 1] += b.y, v[4 * q + 2] += b.z, v[4 * q + 3] += b.w;
+        }
+    };
+
+    if (!(a.flags & PCT_LINEAR_LAYERNORM)) {
+      if (has_res) fetch_residual(0, min(32, n_tile));
+      for (int c = 0; c < n_tile; c += 32) {
+        const int cw = min(32, n_tile - c);
+        load_acc(c, cw);
+        add_bias(c, cw);
+        if (has_res) {
+          add_residual(cw);
+          if (c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        store_block(c, cw);
+      }
+    } else {
+      // pass 1: pre-norm row = acc + bias (+ residual), parked back in TMEM; row sum
+      float sum = 0.f;
+      if (has_res) fetch_residual(0, min(32, n_tile));
+      for (int c = 0; c < n_tile; c += 32) {
+        const int cw = min(32, n_tile - c);
+        load_acc(c, cw);
+        add_bias(c, cw);
+        if (has_res) {
+          add_residual(cw);
+          if (c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < cw) sum += v[i];
+        tmem_st16(t_row + c, v);
+        if (cw > 16) tmem_st16(t_row + c + 16, v + 16);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      const float mean = sum / (float)a.N;
+      // pass 2: centred sum of squares
+      float ssq = 0.f;
+      for (int c = 0; c < n_tile; c += 32) {
+        const int cw = min(32, n_tile - c);
+        load_acc(c, cw);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < cw) ssq += (v[i] - mean) * (v[i] - mean);
+      }
+      const float rstd = rsqrtf(ssq / (float)a.N + a.eps);
+      // pass 3: normalise, scale, shift, store
+      for (int c = 0; c < n_tile; c += 32) {
+        const int cw = min(32, n_tile - c);
+        load_acc(c, cw);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (4 * q < cw) {
+            const float4 g = *reinterpret_cast<const float4*>(vec_gamma + c + 4 * q);
+            const float4 b = *reinterpret_cast<const float4*>(vec_beta + c + 4 * q);
+            v[4 * q] = (v[4 * q] - mean) * rstd * g.x + b.x;
+            v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * g.y + b.y;
+            v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * g.z + b.z;
+            v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * g.w + b.w;
+          }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        store_block(c, cw);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kLoaderWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
+                 "r"((uint32_t)kBlockN)
+                 : "memory");
+  }
+}
+
+// W (N, K) fp32 -> per (256-column tile, 16-float K step): [hi piece 16 KB][lo piece 16 KB], each in
+// the stage's core-matrix order (float4 i <-> column 8*(i/32) + i%8, k-quad (i/8)%4); columns
+// past N are zero.
+__global__ void pack_weight_kernel(const float* __restrict__ w, float4* __restrict__ packed, int N,
+                                   int K) {
+  const int n_steps = K / kBlockK;
+  const size_t per_piece = kBBytes / 16;                       // float4 per piece
+  const size_t total = (size_t)((N + kBlockN - 1) / kBlockN) * n_steps * per_piece;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % per_piece);
+    const size_t ts = idx / per_piece;                         // tile * n_steps + step
+    const int step = (int)(ts % n_steps), tile = (int)(ts / n_steps);
+    const int col = tile * kBlockN + (i >> 5) * 8 + (i & 7);
+    const int k = step * kBlockK + ((i >> 3) & 3) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < N) x = *reinterpret_cast<const float4*>(w + (size_t)col * K + k);
+    float4 h, l;
+    h.x = tf32_head(x.x), h.y = tf32_head(x.y), h.z = tf32_head(x.z), h.w = tf32_head(x.w);
+    l.x = x.x - h.x, l.y = x.y - h.y, l.z = x.z - h.z, l.w = x.w - h.w;
+    packed[ts * 2 * per_piece + i] = h;
+    packed[ts * 2 * per_piece + per_piece + i] = l;
+  }
+}
+
+bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+bool bad_dims(int in_features, int out_features) {
+  return in_features < kBlockK || out_features < 16 || in_features % kBlockK || out_features % 16;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t pct_linear_packed_bytes(int in_features, int out_features) {
+  if (bad_dims(in_features, out_features)) return 0;
+  return (size_t)((out_features + kBlockN - 1) / kBlockN) * (in_features / kBlockK) * kWStepBytes;
+}
+
+int pct_linear_pack_weight(const float* w, void* packed, int in_features, int out_features,
+                           void* cuda_stream) {
+  if (!w || !packed) return PCT_MSDA_E_NULL_POINTER;
+  if (bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
+  if (misaligned(w) || misaligned(packed)) return PCT_MSDA_E_MISALIGNED;
+  const size_t total = pct_linear_packed_bytes(in_features, out_features) / 32;
+  const int block = 256;
+  const size_t want = (total + block - 1) / block;
+  pack_weight_kernel<<<(int)(want < 1184 ? want : 1184), block, 0, (cudaStream_t)cuda_stream>>>(
+      w, reinterpret_cast<float4*>(packed), out_features, in_features);
+  pct::count_launch();
+  return (int)cudaGetLastError();
+}
+
+int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
+                       const float* residual, const float* ln_gamma, const float* ln_beta,
+                       float ln_eps, float* y, int rows, int in_features, int out_features,
+                       unsigned flags, void* cuda_stream) {
+  if (!x || !w_packed || !y) return PCT_MSDA_E_NULL_POINTER;
+  if ((flags & PCT_LINEAR_RESIDUAL) && !residual) return PCT_MSDA_E_NULL_POINTER;
+  if ((flags & PCT_LINEAR_LAYERNORM) && (!ln_gamma || !ln_beta)) return PCT_MSDA_E_NULL_POINTER;
+  if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
+  if ((flags & PCT_LINEAR_LAYERNORM) && out_features > kBlockN) return PCT_MSDA_E_UNSUPPORTED;
+  if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM))
+    return PCT_MSDA_E_UNSUPPORTED;
+  if (misaligned(x) || misaligned(w_packed) || misaligned(y) || misaligned(bias) ||
+      misaligned(residual) || misaligned(ln_gamma) || misaligned(ln_beta))
+    return PCT_MSDA_E_MISALIGNED;
+  const long long m_tiles = ((long long)rows + kBlockM - 1) / kBlockM;
+  if (m_tiles > 65535) return PCT_MSDA_E_TOO_LARGE;
+
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  LinearArgs a{x, static_cast<const unsigned char*>(w_packed), bias, residual, ln_gamma, ln_beta,
+               y, ln_eps, rows, in_features, out_features, flags};
+  dim3 grid((out_features + kBlockN - 1) / kBlockN, (unsigned)m_tiles);
+  linear_tf32x3_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)cuda_stream>>>(a);
+  pct::count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -18,6 +18,15 @@ std::atomic<unsigned> g_sched_seq{0};   // ring position of the next persistent 
 // (value + 1) to override.
 constexpr int kStaticSixteenths = 14;
 
+}  // namespace
+
+namespace pct {
+// launch accounting shared with linear_tc.cu
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace pct
+
+namespace {
+
 pct::SchedArgs make_sched(long long n_tasks, int grid, int warps, unsigned flags) {
   int sixteenths = kStaticSixteenths;
   const int f = (int)((flags >> 20) & 0x1fu);
