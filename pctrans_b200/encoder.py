@@ -20,6 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .functions import linear_tc
 from .modules import MSDeformAttn
 
 
@@ -81,15 +82,29 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
     def with_pos_embed(tensor, pos):
         return tensor if pos is None else tensor + pos
 
+    def _fusable(self, *dropouts):
+        """The Linear epilogues (ReLU, residual add, LayerNorm) can be fused into the tensor-core
+        GEMMs when no dropout sits between them (p = 0 or eval mode)."""
+        return self.self_attn.tensor_core_linears and all(d.p == 0.0 or not self.training for d in dropouts)
+
     def forward_ffn(self, src):
+        if self._fusable(self.dropout2, self.dropout3) and self.activation is F.relu:
+            hidden = linear_tc.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
+            return linear_tc.linear_residual_layernorm(hidden, self.linear2.weight, self.linear2.bias,
+                                                       src, self.norm2)
         hidden = self.dropout2(self.activation(self.linear1(src)))
         return self.norm2(src + self.dropout3(self.linear2(hidden)))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         # query = src + pos, value source = src (PD:124)
-        attn = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
-                              level_start_index, padding_mask)
-        src = self.norm1(src + self.dropout1(attn))
+        query = self.with_pos_embed(src, pos)
+        if self._fusable(self.dropout1):
+            src = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index,
+                                 padding_mask, residual=src, norm=self.norm1)
+        else:
+            attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index,
+                                  padding_mask)
+            src = self.norm1(src + self.dropout1(attn))
         return self.forward_ffn(src)
 
 

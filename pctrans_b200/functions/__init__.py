@@ -2,3 +2,4 @@ from .ms_deform_attn_func import (MSDeformAttnFunction, MSDeformAttnFusedFunctio
                                   ms_deform_attn_core_pytorch)
 
 __all__ = ["MSDeformAttnFunction", "MSDeformAttnFusedFunction", "ms_deform_attn_core_pytorch"]
+from . import linear_tc  # noqa: E402,F401  (tensor-core Linear for the encoder layer)

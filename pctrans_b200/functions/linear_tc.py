@@ -1,0 +1,111 @@
+"""fp32 ``Linear`` on the B200 tensor cores for the encoder layer around the op
+(C ABI in include/pct_linear.h, kernel in csrc/linear_tc.cu).
+
+The reference runs its pixel decoder in fp32 with autocast off (PD/msdeformattn.py:314-320), so
+the projections of ``MSDeformAttn`` (OPS/modules/ms_deform_attn.py:55-58) and the FFN of the
+encoder layer (PD/msdeformattn.py:107-120) are SIMT fp32 GEMMs.  ``linear`` computes the same
+``x @ W^T + b`` with ``tcgen05.mma.kind::tf32`` and the 3xTF32 split (error ~1e-6 relative, i.e.
+fp32-level, not TF32-level), with bias, ReLU and the residual add fused; for inference
+``linear_residual_layernorm`` also fuses the LayerNorm that follows ``output_proj`` / ``linear2``.
+
+Scope: CUDA fp32 tensors with in/out features multiples of 16, outside autocast.  Anything else
+(CPU tensors, bf16/autocast, odd sizes) is simply not this kernel's job and goes to
+``torch.nn.functional.linear`` exactly as the reference does; this is the caller's GEMM, not the
+MSDeformAttn op, which never has a fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import _cabi
+
+ENABLED = True            # process-wide switch (tests flip it to compare against torch)
+
+
+def packed_weight(weight: torch.Tensor, transposed: bool = False) -> torch.Tensor:
+    """Packed 3xTF32 operand of ``weight`` (or of ``weight.T`` for the input gradient), cached
+    until the weight changes in place (optimizer step) or is reallocated."""
+    slot = weight.__dict__.setdefault("_pct_packed", {})
+    tag = (weight._version, weight.data_ptr(), weight.device)
+    hit = slot.get(transposed)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    w = weight.detach()
+    packed = _cabi.linear_pack_weight(w.t().contiguous() if transposed else w)
+    slot[transposed] = (tag, packed)
+    return packed
+
+
+def eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (ENABLED and x.is_cuda and weight.is_cuda and x.dtype == torch.float32
+            and weight.dtype == torch.float32 and not torch.is_autocast_enabled()
+            and weight.shape[0] % 16 == 0 and weight.shape[1] % 16 == 0 and x.numel() > 0)
+
+
+class TensorCoreLinearFunction(Function):
+    """y = [relu](x @ W^T + b [+ residual]); gradients for x, W, b and residual."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, relu):
+        n, k = weight.shape
+        x2 = x.reshape(-1, k).contiguous()
+        res2 = residual.reshape(-1, n).contiguous() if residual is not None else None
+        b = bias.detach().contiguous() if bias is not None else None
+        y = _cabi.linear_forward(x2, packed_weight(weight), n, b, res2, relu=relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.x_shape = x.shape
+        ctx.save_for_backward(x2, weight, y if relu else None)
+        return y.view(*x.shape[:-1], n)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        x2, weight, y = ctx.saved_tensors
+        n, k = weight.shape
+        g = grad_y.reshape(-1, n).contiguous()
+        if ctx.relu:
+            g = g * (y > 0)
+        gx = gw = gb = gres = None
+        if ctx.needs_input_grad[0]:
+            # dX = dY @ W: the same kernel with the transposed weight as its operand
+            gx = _cabi.linear_forward(g, packed_weight(weight, transposed=True), k).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            gw = g.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            gres = g.view(*ctx.x_shape[:-1], n)
+        return gx, gw, gb, gres, None
+
+
+def linear(x, weight, bias=None, residual=None, relu: bool = False):
+    """``[relu](F.linear(x, weight, bias) [+ residual])`` -- on the tensor cores when eligible."""
+    if eligible(x, weight):
+        return TensorCoreLinearFunction.apply(x, weight, bias, residual, relu)
+    y = F.linear(x, weight, bias)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+def linear_residual_layernorm(x, weight, bias, residual, norm: torch.nn.LayerNorm):
+    """``norm(residual + F.linear(x, weight, bias))``.  Without autograd (inference) the whole
+    expression is one kernel; with autograd the LayerNorm stays a torch op (its backward needs
+    the pre-norm tensor) and only bias + residual are fused."""
+    n = weight.shape[0]
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (x, weight, bias, residual, norm.weight, norm.bias))
+    fusable = (eligible(x, weight) and not needs_grad and n <= 256 and norm.elementwise_affine
+               and norm.bias is not None and tuple(norm.normalized_shape) == (n,)
+               and norm.weight.dtype == torch.float32)
+    if not fusable:
+        return norm(linear(x, weight, bias, residual=residual))
+    x2 = x.reshape(-1, weight.shape[1]).contiguous()
+    y = _cabi.linear_forward(x2, packed_weight(weight), n, bias, residual.reshape(-1, n).contiguous(),
+                             norm.weight, norm.bias, norm.eps)
+    return y.view(*x.shape[:-1], n)

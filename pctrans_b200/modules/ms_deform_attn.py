@@ -13,7 +13,11 @@ What differs on purpose:
     and silently takes its slow path, mod.py:116-121): a failing CUDA call raises;
   * when the call qualifies, softmax and location arithmetic run inside the kernels
     (``fused_prologue``); otherwise they are composed here and the plain Function is used.  Both
-    routes end in the same sm_100a kernels.
+    routes end in the same sm_100a kernels;
+  * the four projections run on the tensor cores at fp32 accuracy when they qualify
+    (``tensor_core_linears``, functions/linear_tc.py); ``forward`` takes two optional keyword
+    arguments so that the encoder layer can have its residual add and LayerNorm fused into
+    ``output_proj``.
 """
 from __future__ import annotations
 
@@ -23,7 +27,7 @@ import warnings
 import torch
 from torch import nn
 
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, linear_tc
 
 
 def compass_offsets(n_heads: int, n_levels: int, n_points: int) -> torch.Tensor:
@@ -54,6 +58,7 @@ class MSDeformAttn(nn.Module):
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
         self.im2col_step = 128       # accepted by the Function for compatibility, ignored by the kernels
         self.fused_prologue = True   # softmax + location arithmetic inside the kernels when possible
+        self.tensor_core_linears = True   # 3xTF32 tcgen05 GEMMs for the projections when eligible
 
         samples = n_heads * n_levels * n_points
         self.sampling_offsets = nn.Linear(d_model, samples * 2)
@@ -76,7 +81,7 @@ class MSDeformAttn(nn.Module):
     # -- pieces of forward ---------------------------------------------------------------------
     def _values(self, input_flatten, input_padding_mask):
         """(N, S, M, D) projected values with padded positions zeroed (mod.py:98-101)."""
-        value = self.value_proj(input_flatten)
+        value = self._proj(self.value_proj, input_flatten)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         n, s, _ = value.shape
@@ -90,12 +95,28 @@ class MSDeformAttn(nn.Module):
             return ref + offsets / wh[None, None, None, :, None, :]
         return ref[..., :2] + offsets / self.n_points * ref[..., 2:] * 0.5
 
+    def _proj(self, layer, x):
+        if self.tensor_core_linears:
+            return linear_tc.linear(x, layer.weight, layer.bias)
+        return layer(x)
+
+    def _output(self, out, query, residual, norm):
+        """output_proj, plus the caller's ``norm(residual + .)`` when it was handed in."""
+        out = self._match(out, query)
+        if norm is None:
+            return self._proj(self.output_proj, out)
+        if self.tensor_core_linears:
+            return linear_tc.linear_residual_layernorm(out, self.output_proj.weight,
+                                                       self.output_proj.bias, residual, norm)
+        return norm(residual + self.output_proj(out))
+
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
-                input_level_start_index, input_padding_mask=None):
+                input_level_start_index, input_padding_mask=None, *, residual=None, norm=None):
         """query (N, Lq, C); reference_points (N, Lq, L, 2) in [0,1] or (N, Lq, L, 4) boxes
         (cx, cy, w, h); input_flatten (N, sum_l H_l*W_l, C); input_spatial_shapes (L, 2) rows
         (H_l, W_l); input_level_start_index (L,); input_padding_mask (N, S) bool, True = padding.
-        Returns (N, Lq, C)."""
+        Returns (N, Lq, C) -- or ``norm(residual + that)`` when the two keyword arguments (not in
+        the reference's signature) are given."""
         n, len_q, _ = query.shape
         len_in = input_flatten.shape[1]
         assert int(input_spatial_shapes.prod(1).sum()) == len_in
@@ -104,15 +125,15 @@ class MSDeformAttn(nn.Module):
                              .format(reference_points.shape[-1]))
         m, lv, pt = self.n_heads, self.n_levels, self.n_points
         value = self._values(input_flatten, input_padding_mask)
-        offsets = self.sampling_offsets(query).view(n, len_q, m, lv, pt, 2)
-        logits = self.attention_weights(query).view(n, len_q, m, lv * pt)
+        offsets = self._proj(self.sampling_offsets, query).view(n, len_q, m, lv, pt, 2)
+        logits = self._proj(self.attention_weights, query).view(n, len_q, m, lv * pt)
 
         if self.fused_prologue and MSDeformAttnFusedFunction.supported(value, reference_points, lv, pt):
             out = MSDeformAttnFusedFunction.apply(
                 value.contiguous(), input_spatial_shapes, input_level_start_index,
                 reference_points.float().contiguous(), offsets.float().contiguous(),
                 logits.float().contiguous())
-            return self.output_proj(self._match(out, query))
+            return self._output(out, query, residual, norm)
 
         weights = torch.softmax(logits, dim=-1).view(n, len_q, m, lv, pt)
         locations = self._locations(reference_points, offsets, input_spatial_shapes)
@@ -123,7 +144,7 @@ class MSDeformAttn(nn.Module):
         out = MSDeformAttnFunction.apply(
             value.contiguous(), input_spatial_shapes, input_level_start_index,
             locations.contiguous(), weights.contiguous(), self.im2col_step)
-        return self.output_proj(self._match(out, query))
+        return self._output(out, query, residual, norm)
 
     @staticmethod
     def _match(out, query):

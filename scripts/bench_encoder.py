@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--core", default="cuda", choices=["cuda", "gridsample"])
     ap.add_argument("--fused", type=int, default=1, help="use the fused-prologue kernels (default)")
+    ap.add_argument("--tc-linears", type=int, default=1,
+                    help="fp32 Linears on the tensor cores (3xTF32, functions/linear_tc.py)")
     ap.add_argument("--tf32", type=int, default=0, help="allow TF32 tensor cores for the Linears")
     ap.add_argument("--autocast", default="none", choices=["none", "bf16"],
                     help="run the encoder under bf16 autocast (the reference disables autocast here "
@@ -69,6 +71,8 @@ def main():
         mod_file.MSDeformAttnFunction = _Core
 
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    from pctrans_b200.functions import linear_tc
+    linear_tc.ENABLED = bool(args.tc_linears)
     torch.manual_seed(0)   # identical initial weights on every rank, as DDP broadcasts them
     model = enc.MSDeformAttnTransformerEncoderOnly(
         d_model=args.d_model, nhead=8, num_encoder_layers=args.layers, dim_feedforward=1024,
@@ -127,7 +131,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "bench": "encoder", "mode": args.mode, "core": args.core, "fused": bool(args.fused),
-            "tf32": bool(args.tf32), "autocast": args.autocast, "pyramid": args.pyramid,
+            "tf32": bool(args.tf32), "tc_linears": bool(args.tc_linears), "autocast": args.autocast, "pyramid": args.pyramid,
             "d_model": args.d_model, "layers": args.layers, "n_gpus": world, "batch_per_gpu": n,
             "global_batch": n * world, "ms_per_step": ms,
             "query_layers_per_s": world * n * lq * args.layers / (ms * 1e-3),

@@ -11,9 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_symbols():
-    text = open(os.path.join(ROOT, "include", "pct_msda.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(pct_msda_\w+)\s*\(", text)))
+    syms = set()
+    for name in ("pct_msda.h", "pct_linear.h"):
+        text = open(os.path.join(ROOT, "include", name)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        syms |= set(re.findall(r"\b(pct_(?:msda|linear)_\w+)\s*\(", text))
+    return sorted(syms)
 
 
 def test_header_declares_expected_entry_points():
@@ -28,8 +31,8 @@ def test_library_exports_every_declared_symbol():
     build.build_library()
     lib = ctypes.CDLL(_cabi.LIB_PATH)
     for s in _header_symbols():
-        assert hasattr(lib, s), f"{s} declared in include/pct_msda.h but not exported"
-    assert set(_cabi.EXPORTS) <= set(_header_symbols())
+        assert hasattr(lib, s), f"{s} declared in include/*.h but not exported"
+    assert set(_cabi.EXPORTS) | set(_cabi.LINEAR_EXPORTS) <= set(_header_symbols())
 
 
 def test_abi_scalar_entry_points_without_gpu():
@@ -44,6 +47,10 @@ def test_abi_scalar_entry_points_without_gpu():
     assert _cabi.kernel_family(32, 3, 4, torch.float32) == 1
     assert _cabi.kernel_family(16, 3, 4, torch.float32, backward=True) == 1
     assert _cabi.kernel_family(71, 3, 4, torch.float32) == 0
+    # include/pct_linear.h: packed weight = 256-column tiles x 16-float K steps x (hi + lo) 16 KB
+    assert lib.pct_linear_packed_bytes(256, 256) == 16 * 32768
+    assert lib.pct_linear_packed_bytes(256, 288) == 2 * 16 * 32768
+    assert lib.pct_linear_packed_bytes(250, 256) == 0 and lib.pct_linear_packed_bytes(256, 8) == 0
     assert _cabi.kernel_family(32, 33, 4, torch.float32) == 0   # L*P > 128 sample table
     # argument validation happens before any CUDA call
     assert lib.pct_msda_forward(None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 7, None) == 1003

@@ -1,0 +1,187 @@
+"""Tensor-core Linear (include/pct_linear.h) against fp64 references.
+
+The bar is the reference's fp32 one (the pixel decoder runs in fp32 with autocast off,
+PD/msdeformattn.py:314-320): results must sit at fp32-GEMM accuracy, not TF32 accuracy.  Tolerances
+are relative to the largest reference magnitude: 1e-5 forward (BASELINE's fp32 forward bar),
+1e-4 for gradients."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, ref):
+    return float((a.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def _case(rows, k, n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).cuda()
+    b = torch.randn(n, generator=g).cuda()
+    res = torch.randn(rows, n, generator=g).cuda()
+    return x, w, b, res
+
+
+@pytest.mark.parametrize("rows,k,n", [
+    (1, 16, 16), (127, 32, 48), (128, 256, 256), (129, 256, 192), (1000, 256, 96),
+    (777, 256, 1024), (513, 1024, 256), (300, 128, 288), (5376, 256, 256)])
+def test_forward_epilogues_match_fp64(rows, k, n):
+    from pctrans_b200 import _cabi
+    x, w, b, res = _case(rows, k, n)
+    wp = _cabi.linear_pack_weight(w)
+    ref = x.double() @ w.double().t()
+    assert _rel(_cabi.linear_forward(x, wp, n), ref) < 1e-5
+    ref_b = ref + b.double()
+    assert _rel(_cabi.linear_forward(x, wp, n, b), ref_b) < 1e-5
+    assert _rel(_cabi.linear_forward(x, wp, n, b, relu=True), ref_b.relu()) < 1e-5
+    assert _rel(_cabi.linear_forward(x, wp, n, b, res), ref_b + res.double()) < 1e-5
+    assert _rel(_cabi.linear_forward(x, wp, n, b, res, relu=True), (ref_b + res.double()).relu()) < 1e-5
+    if n <= 256:
+        gamma, beta = torch.randn(n).cuda(), torch.randn(n).cuda()
+        ln = F.layer_norm(ref_b + res.double(), (n,), gamma.double(), beta.double(), 1e-5)
+        assert _rel(_cabi.linear_forward(x, wp, n, b, res, gamma, beta, 1e-5), ln) < 1e-5
+        ln0 = F.layer_norm(ref_b, (n,), gamma.double(), beta.double(), 1e-5)
+        assert _rel(_cabi.linear_forward(x, wp, n, b, None, gamma, beta, 1e-5), ln0) < 1e-5
+
+
+def test_accuracy_is_fp32_class_not_tf32_class():
+    from pctrans_b200 import _cabi
+    x, w, b, _ = _case(4096, 256, 256, seed=1)
+    ref = x.double() @ w.double().t() + b.double()
+    ours = _rel(_cabi.linear_forward(x, _cabi.linear_pack_weight(w), 256, b), ref)
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        tf32 = _rel(F.linear(x, w, b), ref)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert ours < 5e-6 and ours * 20 < tf32
+
+
+def test_untouched_rows_and_columns_stay_untouched():
+    """Row / column tails: nothing outside (rows, n) is written."""
+    from pctrans_b200 import _cabi
+    rows, k, n = 130, 64, 48
+    x, w, b, _ = _case(rows, k, n)
+    buf = torch.full((rows + 4, n), 7.0).cuda()
+    _cabi.linear_forward(x, _cabi.linear_pack_weight(w), n, b, out=buf[:rows])
+    torch.cuda.synchronize()
+    assert bool((buf[rows:] == 7.0).all())
+    assert _rel(buf[:rows], x.double() @ w.double().t() + b.double()) < 1e-5
+
+
+def test_bad_arguments_are_error_codes():
+    from pctrans_b200 import _cabi
+    x = torch.randn(8, 24).cuda()
+    with pytest.raises(_cabi.MSDAError):
+        _cabi.linear_pack_weight(torch.randn(16, 24).cuda())          # in % 16
+    wp = _cabi.linear_pack_weight(torch.randn(512, 32).cuda())
+    g = torch.ones(512).cuda()
+    with pytest.raises(_cabi.MSDAError) as e:                           # LayerNorm wider than a tile
+        _cabi.linear_forward(torch.randn(8, 32).cuda(), wp, 512, None, None, g, g)
+    assert e.value.code == _cabi.E_UNSUPPORTED
+    del x
+
+
+def test_autograd_function_matches_fp64_gradients():
+    from pctrans_b200.functions import linear_tc
+    rows, k, n = 700, 256, 192
+    x, w, b, res = _case(rows, k, n, seed=2)
+    gy = torch.randn(rows, n).cuda()
+    for relu in (False, True):
+        leaves = [t.clone().requires_grad_(True) for t in (x, w, b, res)]
+        y = linear_tc.linear(leaves[0].view(7, 100, k), leaves[1], leaves[2],
+                             residual=leaves[3].view(7, 100, n), relu=relu)
+        assert y.shape == (7, 100, n) and isinstance(y.grad_fn, torch.autograd.function.BackwardCFunction)
+        y.backward(gy.view(7, 100, n))
+        ref_leaves = [t.double().clone().requires_grad_(True) for t in (x, w, b, res)]
+        yr = F.linear(ref_leaves[0], ref_leaves[1], ref_leaves[2]) + ref_leaves[3]
+        yr = yr.relu() if relu else yr
+        yr.backward(gy.double())
+        assert _rel(y.reshape(rows, n), yr.detach()) < 1e-5
+        for ours, ref in zip(leaves, ref_leaves):
+            assert _rel(ours.grad, ref.grad) < 1e-4
+
+
+def test_packed_weight_cache_follows_in_place_updates():
+    from pctrans_b200.functions import linear_tc
+    lin = torch.nn.Linear(64, 32).cuda()
+    x = torch.randn(50, 64).cuda()
+    with torch.no_grad():
+        y0 = linear_tc.linear(x, lin.weight, lin.bias)
+        p0 = linear_tc.packed_weight(lin.weight)
+        assert linear_tc.packed_weight(lin.weight) is p0            # cached
+        lin.weight.mul_(2.0)                                         # optimizer-style in-place step
+        y1 = linear_tc.linear(x, lin.weight, lin.bias)
+    assert linear_tc.packed_weight(lin.weight) is not p0
+    assert _rel(y1 - lin.bias, 2.0 * (y0 - lin.bias).double()) < 1e-5
+
+
+def test_ineligible_inputs_take_the_torch_linear():
+    """bf16 / autocast / odd sizes are not this kernel's job: same result as F.linear."""
+    from pctrans_b200.functions import linear_tc
+    lin = torch.nn.Linear(20, 12).cuda()
+    x = torch.randn(9, 20).cuda()
+    assert not linear_tc.eligible(x, lin.weight)
+    assert torch.equal(linear_tc.linear(x, lin.weight, lin.bias), lin(x))
+    lin2 = torch.nn.Linear(32, 32).cuda()
+    x2 = torch.randn(9, 32).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert not linear_tc.eligible(x2, lin2.weight)
+        assert linear_tc.linear(x2, lin2.weight, lin2.bias).dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("mode", ["infer", "train"])
+def test_encoder_with_tensor_core_linears_matches_torch_linears(mode):
+    """The 6-layer encoder with the tensor-core projections / FFN (and, without autograd, the fused
+    residual + LayerNorm epilogues) against the same weights through torch's fp32 Linears."""
+    from pctrans_b200 import encoder as enc, synth
+    from pctrans_b200.functions import linear_tc
+    torch.manual_seed(0)
+    pyramid = synth.CVPPP_448
+    model = enc.MSDeformAttnTransformerEncoderOnly(
+        d_model=128, nhead=8, num_encoder_layers=3, dim_feedforward=1024, dropout=0.0,
+        num_feature_levels=len(pyramid)).cuda()
+    with torch.no_grad():                     # generic offsets, not the on-grid initial ones
+        for m in model.modules():
+            if isinstance(m, enc.MSDeformAttn):
+                m.sampling_offsets.weight.normal_(0, 0.02)
+                m.attention_weights.weight.normal_(0, 0.1)
+    srcs = [torch.randn(2, 128, h, w).cuda() for h, w in pyramid]
+    pos = [enc.PositionEmbeddingSine(64, normalize=True)(s) for s in srcs]
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    outs, grads = [], []
+    try:
+        for enabled in (True, False):
+            linear_tc.ENABLED = enabled
+            model.zero_grad(set_to_none=True)
+            if mode == "infer":
+                with torch.no_grad():
+                    outs.append(model(srcs, pos)[0])
+            else:
+                out = model(srcs, pos)[0]
+                out.square().mean().backward()
+                outs.append(out.detach())
+                grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+    finally:
+        linear_tc.ENABLED = True
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    assert _rel(outs[0], outs[1].double()) < 1e-5
+    if mode == "train":
+        # relative L2 per parameter.  Same bar as the whole-model gradient test in
+        # test_encoder.py: the 1e-6 perturbation of the offsets moves a few samples across pixel
+        # boundaries, where the location gradient is discontinuous, so the offset / attention
+        # Linears (gradient norms ~1e-6 of the largest) differ by ~1e-2 between ANY two fp32
+        # evaluation orders (measured 1.4e-2 worst).
+        worst = {}
+        for k in grads[0]:
+            den = float(grads[1][k].double().norm().clamp_min(1e-30))
+            worst[k] = float((grads[0][k].double() - grads[1][k].double()).norm()) / den
+        bad = {k: v for k, v in worst.items() if v > 3e-2}
+        assert not bad, sorted(bad.items(), key=lambda t: -t[1])[:5]
+        direct = [v for k, v in worst.items() if "sampling_offsets" not in k
+                  and "attention_weights" not in k and k != "level_embed"]
+        assert max(direct) < 2e-3, sorted(worst.items(), key=lambda t: -t[1])[:8]
