@@ -30,7 +30,8 @@ EXPORTS = (
     "pct_msda_host_ctx_create", "pct_msda_host_ctx_destroy", "pct_msda_host_forward",
     "pct_msda_host_forward_backward",
 )
-LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_forward")
+LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_forward",
+                  "pct_linear_wgrad")
 LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM = 0x1, 0x2, 0x4
 E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
@@ -94,6 +95,8 @@ def load():
         lib.pct_linear_packed_bytes.argtypes = [i32, i32]
         lib.pct_linear_pack_weight.restype = i32
         lib.pct_linear_pack_weight.argtypes = [vp, vp, i32, i32, vp]
+        lib.pct_linear_wgrad.restype = i32
+        lib.pct_linear_wgrad.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         lib.pct_linear_forward.restype = i32
         lib.pct_linear_forward.argtypes = [vp] * 6 + [ctypes.c_float, vp] + [i32] * 3 + [u32, vp]
         got = lib.pct_msda_abi_version()
@@ -249,3 +252,14 @@ def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weigh
             ptr(ln_bias), float(ln_eps), y.data_ptr(), rows, k, n, flags,
             _stream_ptr(x.device)), "pct_linear_forward")
     return y
+
+
+def linear_wgrad(grad_y, x):
+    """grad_w (out, in) = grad_y (rows, out)^T @ x (rows, in) on the tensor cores (3xTF32)."""
+    rows, n = grad_y.shape
+    k = x.shape[1]
+    gw = torch.empty((n, k), dtype=x.dtype, device=x.device)
+    with torch.cuda.device_of(x):
+        check(load().pct_linear_wgrad(grad_y.data_ptr(), x.data_ptr(), gw.data_ptr(), rows, k, n,
+                                      _stream_ptr(x.device)), "pct_linear_wgrad")
+    return gw

@@ -511,6 +511,212 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float4* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: dW (N, K) = dY^T (N, rows) @ X (rows, K), the reduction running over the rows.
+// Both operands are activations, so both are split on the fly, and both arrive transposed: global
+// memory is contiguous along the features, the tensor core wants 16-byte chunks along the
+// reduction (row) dimension.  A loader thread therefore reads a 4-row x 4-feature block (four
+// 16-byte loads, a warp covering 512 contiguous bytes of each row), transposes it in registers and
+// stores four 16-byte chunks in the same K-major core-matrix order the forward kernel uses; the
+// 8-row groups are padded to 528 bytes so those stores are bank-conflict free.  A CTA owns a
+// 128 x (<=256) tile of dW and a slice of the rows (split-K); slices are combined with vector fp32
+// reductions into the zero-filled dW.
+constexpr int kWgLoaderWarps = 8;
+constexpr int kWgThreads = (kWgLoaderWarps + 1) * 32;
+constexpr int kWgAhead = 2;
+constexpr int kWgSbo = kSbo + 16;                              // padded 8-feature group
+constexpr int kWgABytes = (kBlockM / 8) * kWgSbo;              // one piece of the dY^T tile
+constexpr int kWgBBytes = (kBlockN / 8) * kWgSbo;              // one piece of the X^T tile
+constexpr int kWgStageBytes = 2 * kWgABytes + 2 * kWgBBytes;
+constexpr int kWgSmemBytes = kStages * kWgStageBytes + kBarrierBytes;
+constexpr int kWgUnitsA = (kBlockM / 4) * (kBlockK / 4);       // 4x4 blocks of the dY tile per step
+constexpr int kWgUnits = kWgUnitsA + (kBlockN / 4) * (kBlockK / 4);
+constexpr int kWgPer = (kWgUnits + kWgLoaderWarps * 32 - 1) / (kWgLoaderWarps * 32);
+
+__device__ __forceinline__ uint64_t make_smem_desc_wg(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kLbo >> 4) << 16) |
+         ((uint64_t)(kWgSbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+struct WgradArgs {
+  const float* gy;   // (rows, N)
+  const float* x;    // (rows, K)
+  float* gw;         // (N, K), zero on entry
+  int rows, K, N;
+  int steps_per_split;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const WgradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int n0 = blockIdx.x * kBlockM;                   // dW rows = output features
+  const int k0 = blockIdx.y * kBlockN;                   // dW columns = input features
+  const int n_valid = min(kBlockM, a.N - n0);
+  const int k_tile = min(kBlockN, a.K - k0);
+  const int total_steps = (a.rows + kBlockK - 1) / kBlockK;
+  const int step_lo = blockIdx.z * a.steps_per_split;
+  const int n_steps = min(a.steps_per_split, total_steps - step_lo);
+  if (n_steps <= 0) return;                              // uniform per CTA, before any barrier
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kWgStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  const uint32_t bar_empty = smem_u32(bars);
+  const uint32_t bar_full = bar_empty + 8 * kStages;
+  const uint32_t bar_done = bar_empty + 16 * kStages;
+
+  if (warp == kWgLoaderWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)kBlockN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, kWgLoaderWarps * 32);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t smem0 = smem_u32(smem);
+
+  if (warp == kWgLoaderWarps) {
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(k_tile);
+      for (int step = 0; step < n_steps; ++step) {
+        const int s = step % kStages;
+        mbar_wait(bar_full + 8 * s, (step / kStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem0 + s * kWgStageBytes;
+#pragma unroll
+        for (int ks = 0; ks < kBlockK / kMmaK; ++ks) {
+          const uint32_t koff = ks * (kMmaK / 4) * kLbo;
+          const uint64_t d_ahi = make_smem_desc_wg(sa + koff);
+          const uint64_t d_alo = make_smem_desc_wg(sa + kWgABytes + koff);
+          const uint64_t d_bhi = make_smem_desc_wg(sa + 2 * kWgABytes + koff);
+          const uint64_t d_blo = make_smem_desc_wg(sa + 2 * kWgABytes + kWgBBytes + koff);
+          mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);
+          mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
+          mma_tf32(tmem, d_ahi, d_bhi, idesc, 1u);
+        }
+        mma_commit(bar_empty + 8 * s);
+        if (step == n_steps - 1) mma_commit(bar_done);
+      }
+    }
+  } else {
+    // ---- loaders.  Unit = 4 rows x 4 features; unit ids [0, kWgUnitsA) belong to the dY tile,
+    // the rest to the X tile; within a tile, id = featureGroup + groups * rowQuad, so a warp reads
+    // 512 contiguous bytes of one row per load.
+    const float* src[kWgPer];     // first of the unit's 4 features, row 0 (nullptr: past the edge)
+    int rq[kWgPer];               // row quad within the step
+    uint32_t dst[kWgPer];         // byte offset of the unit's first chunk within the hi piece
+    uint32_t lo_off[kWgPer];      // distance from the hi piece to the lo piece
+    int ld[kWgPer];               // row pitch of the source
+#pragma unroll
+    for (int j = 0; j < kWgPer; ++j) {
+      const int u = tid + kWgLoaderWarps * 32 * j;
+      const bool is_a = u < kWgUnitsA;
+      const int v = is_a ? u : u - kWgUnitsA;
+      const int groups = is_a ? kBlockM / 4 : kBlockN / 4;
+      const int g = v % groups;
+      rq[j] = v / groups;
+      const bool ok = u < kWgUnits && 4 * g < (is_a ? n_valid : k_tile);
+      src[j] = !ok ? nullptr : is_a ? a.gy + n0 + 4 * g : a.x + k0 + 4 * g;
+      ld[j] = is_a ? a.N : a.K;
+      // features 4g..4g+3 are rows (4g+i)%8 of 8-row group (4g)/8; the row quad is the k-chunk
+      dst[j] = (is_a ? 0 : 2 * kWgABytes) + (g >> 1) * kWgSbo + rq[j] * kCoreBytes + (g & 1) * 64;
+      lo_off[j] = is_a ? kWgABytes : kWgBBytes;
+      if (u >= kWgUnits) dst[j] = 0xffffffffu;
+    }
+    float4 q[kWgAhead][kWgPer][4];
+    auto fetch = [&](float4 (*d)[4], int step) {
+      const int row0 = (step_lo + step) * kBlockK;
+#pragma unroll
+      for (int j = 0; j < kWgPer; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = row0 + 4 * rq[j] + i;
+          d[j][i] = (src[j] && row < a.rows)
+                        ? __ldg(reinterpret_cast<const float4*>(src[j] + (size_t)row * ld[j]))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto split_store = [&](unsigned char* hi, unsigned char* lo, float x0, float x1, float x2, float x3) {
+      float4 h, l;
+      h.x = tf32_head(x0), h.y = tf32_head(x1), h.z = tf32_head(x2), h.w = tf32_head(x3);
+      l.x = x0 - h.x, l.y = x1 - h.y, l.z = x2 - h.z, l.w = x3 - h.w;
+      *reinterpret_cast<float4*>(hi) = h;
+      *reinterpret_cast<float4*>(lo) = l;
+    };
+#pragma unroll
+    for (int d = 0; d < kWgAhead; ++d)
+      if (d < n_steps) fetch(q[d], d);
+    for (int step0 = 0; step0 < n_steps; step0 += kWgAhead) {
+#pragma unroll
+      for (int d = 0; d < kWgAhead; ++d) {
+        const int step = step0 + d;
+        if (step < n_steps) {
+          const int s = step % kStages;
+          if (step >= kStages) mbar_wait(bar_empty + 8 * s, ((step / kStages) - 1) & 1);
+          unsigned char* stage = smem + s * kWgStageBytes;
+#pragma unroll
+          for (int j = 0; j < kWgPer; ++j)
+            if (dst[j] != 0xffffffffu) {
+              unsigned char* hi = stage + dst[j];
+              unsigned char* lo = hi + lo_off[j];
+              const float4* r = q[d][j];      // r[i] = features 4g..4g+3 of row i: transpose
+              split_store(hi, lo, r[0].x, r[1].x, r[2].x, r[3].x);
+              split_store(hi + 16, lo + 16, r[0].y, r[1].y, r[2].y, r[3].y);
+              split_store(hi + 32, lo + 32, r[0].z, r[1].z, r[2].z, r[3].z);
+              split_store(hi + 48, lo + 48, r[0].w, r[1].w, r[2].w, r[3].w);
+            }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+          if (step + kWgAhead < n_steps) fetch(q[d], step + kWgAhead);
+        }
+      }
+    }
+
+    // ---- epilogue: this thread owns dW row n0 + 32*(warp%4) + lane, one half of the columns ----
+    mbar_wait(bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int c_lo = (warp >> 2) * (kBlockN / 2);
+    const int c_hi = min(k_tile, c_lo + kBlockN / 2);
+    float* out = a.gw + (size_t)(n0 + row) * a.K + k0;
+    for (int c = c_lo; c < c_hi; c += 16) {
+      uint32_t u[16];
+      tmem_ld16(t_row + c, u);
+      tmem_ld_wait();
+      tmem_tie16(u);
+      if (row < n_valid) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c + 4 * qd),
+                       "f"(__uint_as_float(u[4 * qd])), "f"(__uint_as_float(u[4 * qd + 1])),
+                       "f"(__uint_as_float(u[4 * qd + 2])), "f"(__uint_as_float(u[4 * qd + 3]))
+                       : "memory");
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kWgLoaderWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
+                 "r"((uint32_t)kBlockN)
+                 : "memory");
+  }
+}
+
 bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
 bool bad_dims(int in_features, int out_features) {
@@ -571,6 +777,41 @@ int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
                y, ln_eps, rows, in_features, out_features, flags};
   dim3 grid((out_features + kBlockN - 1) / kBlockN, (unsigned)m_tiles);
   linear_tf32x3_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)cuda_stream>>>(a);
+  pct::count_launch();
+  return (int)cudaGetLastError();
+}
+
+int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, int rows, int in_features,
+                     int out_features, void* cuda_stream) {
+  if (!grad_y || !x || !grad_w) return PCT_MSDA_E_NULL_POINTER;
+  if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
+  if (misaligned(grad_y) || misaligned(x) || misaligned(grad_w)) return PCT_MSDA_E_MISALIGNED;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaError_t e = cudaMemsetAsync(grad_w, 0, (size_t)in_features * out_features * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+
+  static bool attr_set[64] = {};
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kWgSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  // split the rows so that about two CTAs per SM are busy; at least 8 K steps per slice
+  const int tiles = ((out_features + kBlockM - 1) / kBlockM) * ((in_features + kBlockN - 1) / kBlockN);
+  const int total_steps = (rows + kBlockK - 1) / kBlockK;
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  if (splits > (total_steps + 7) / 8) splits = (total_steps + 7) / 8;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  const int steps_per_split = (total_steps + splits - 1) / splits;
+  splits = (total_steps + steps_per_split - 1) / steps_per_split;
+  WgradArgs a{grad_y, x, grad_w, rows, in_features, out_features, steps_per_split};
+  dim3 grid((out_features + kBlockM - 1) / kBlockM, (in_features + kBlockN - 1) / kBlockN, splits);
+  wgrad_tf32x3_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
   pct::count_launch();
   return (int)cudaGetLastError();
 }

@@ -75,7 +75,7 @@ class TensorCoreLinearFunction(Function):
             # dX = dY @ W: the same kernel with the transposed weight as its operand
             gx = _cabi.linear_forward(g, packed_weight(weight, transposed=True), k).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            gw = g.t() @ x2
+            gw = _cabi.linear_wgrad(g, x2)      # dW = dY^T @ X, split over the rows
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g.sum(0)
         if ctx.has_res and ctx.needs_input_grad[3]:

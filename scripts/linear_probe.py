@@ -78,6 +78,10 @@ def main():
             rec["us_torch_tf32"] = timeit(torch_path)
             torch.backends.cuda.matmul.allow_tf32 = False
             rec["tflops_tc"] = 2.0 * rows * k * n / rec["us_tc"] / 1e6
+            gy = torch.randn(rows, n, device=dev)
+            rec["err_wgrad"] = rel(_cabi.linear_wgrad(gy, x), gy.double().t() @ x.double())
+            rec["us_wgrad_tc"] = timeit(lambda: _cabi.linear_wgrad(gy, x))
+            rec["us_wgrad_torch_fp32"] = timeit(lambda: gy.t() @ x)
         out.append(rec)
         print(json.dumps(rec), flush=True)
 
