@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Two launches of the tensor-core Linear for an ncu capture (LayerNorm epilogue, ReLU epilogue)."""
+"""Launches of the tensor-core Linear kernels for an ncu capture: forward with the LayerNorm and
+the ReLU epilogue, and the weight gradient of both shapes."""
 import os
 import sys
 
@@ -20,5 +21,7 @@ for k, n, mode in ((256, 256, "ln"), (256, 1024, "relu")):
     wp = _cabi.linear_pack_weight(w)
     for _ in range(2):
         y = _cabi.linear_forward(x, wp, n, b, res, g, g, 1e-5, relu=(mode == "relu"))
+    gy = torch.randn(rows, n, device=dev)
+    _cabi.linear_wgrad(gy, x)
     torch.cuda.synchronize()
 print("ok")
