@@ -240,9 +240,10 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
           const uint64_t d_alo = make_smem_desc(sa + kABytes + koff);
           const uint64_t d_bhi = make_smem_desc(sa + 2 * kABytes + koff);
           const uint64_t d_blo = make_smem_desc(sa + 2 * kABytes + kBBytes + koff);
-          mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);   // small terms first
-          mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
+          // consecutive MMAs share one operand (W_hi, then x_hi)
+          mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);
           mma_tf32(tmem, d_ahi, d_bhi, idesc, 1u);
+          mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
         }
         mma_commit(bar_empty + 8 * s);             // stage free once these MMAs have read it
         if (step == n_steps - 1) mma_commit(bar_done);
@@ -603,8 +604,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
           const uint64_t d_bhi = make_smem_desc_wg(sa + 2 * kWgABytes + koff);
           const uint64_t d_blo = make_smem_desc_wg(sa + 2 * kWgABytes + kWgBBytes + koff);
           mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);
-          mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
           mma_tf32(tmem, d_ahi, d_bhi, idesc, 1u);
+          mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
         }
         mma_commit(bar_empty + 8 * s);
         if (step == n_steps - 1) mma_commit(bar_done);
