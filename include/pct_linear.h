@@ -56,9 +56,10 @@ int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
 /* grad_w (out, in) = grad_y (rows, out)^T @ x (rows, in): the weight gradient of the Linear, same
  * 3xTF32 arithmetic, the row dimension split over CTAs and combined with fp32 reductions (so, like
  * the reference's atomicAdd backward, not bit-reproducible run to run).  grad_w is fully
- * overwritten (cleared by the callee on `cuda_stream`). */
-int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, int rows, int in_features,
-                     int out_features, void* cuda_stream);
+ * overwritten (cleared by the callee on `cuda_stream`).  If grad_bias (out,) is not NULL it receives
+ * the bias gradient, the column sums of grad_y, from the same pass over grad_y. */
+int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
+                     int in_features, int out_features, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -96,7 +96,7 @@ def load():
         lib.pct_linear_pack_weight.restype = i32
         lib.pct_linear_pack_weight.argtypes = [vp, vp, i32, i32, vp]
         lib.pct_linear_wgrad.restype = i32
-        lib.pct_linear_wgrad.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        lib.pct_linear_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
         lib.pct_linear_forward.restype = i32
         lib.pct_linear_forward.argtypes = [vp] * 6 + [ctypes.c_float, vp] + [i32] * 3 + [u32, vp]
         got = lib.pct_msda_abi_version()
@@ -254,12 +254,15 @@ def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weigh
     return y
 
 
-def linear_wgrad(grad_y, x):
-    """grad_w (out, in) = grad_y (rows, out)^T @ x (rows, in) on the tensor cores (3xTF32)."""
+def linear_wgrad(grad_y, x, with_bias: bool = False):
+    """grad_w (out, in) = grad_y (rows, out)^T @ x (rows, in) on the tensor cores (3xTF32);
+    ``with_bias`` also returns grad_b (out,) = grad_y.sum(0) from the same pass."""
     rows, n = grad_y.shape
     k = x.shape[1]
     gw = torch.empty((n, k), dtype=x.dtype, device=x.device)
+    gb = torch.empty((n,), dtype=x.dtype, device=x.device) if with_bias else None
     with torch.cuda.device_of(x):
-        check(load().pct_linear_wgrad(grad_y.data_ptr(), x.data_ptr(), gw.data_ptr(), rows, k, n,
+        check(load().pct_linear_wgrad(grad_y.data_ptr(), x.data_ptr(), gw.data_ptr(),
+                                      gb.data_ptr() if with_bias else None, rows, k, n,
                                       _stream_ptr(x.device)), "pct_linear_wgrad")
-    return gw
+    return (gw, gb) if with_bias else gw

@@ -543,6 +543,7 @@ struct WgradArgs {
   const float* gy;   // (rows, N)
   const float* x;    // (rows, K)
   float* gw;         // (N, K), zero on entry
+  float* gb;         // (N,) column sums of gy, zero on entry; may be null
   int rows, K, N;
   int steps_per_split;
 };
@@ -637,6 +638,10 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
       if (u >= kWgUnits) dst[j] = 0xffffffffu;
     }
     float4 q[kWgAhead][kWgPer][4];
+    // bias gradient = column sums of dY: the threads that load dY blocks keep running sums of
+    // their four features (first k tile only, so that every (row, feature) is counted once)
+    const bool sum_bias = a.gb != nullptr && blockIdx.y == 0 && tid < kWgUnitsA && src[0] != nullptr;
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     auto fetch = [&](float4 (*d)[4], int step) {
       const int row0 = (step_lo + step) * kBlockK;
 #pragma unroll
@@ -667,6 +672,12 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
           const int s = step % kStages;
           if (step >= kStages) mbar_wait(bar_empty + 8 * s, ((step / kStages) - 1) & 1);
           unsigned char* stage = smem + s * kWgStageBytes;
+          if (sum_bias) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              bsum.x += q[d][0][i].x, bsum.y += q[d][0][i].y, bsum.z += q[d][0][i].z,
+                  bsum.w += q[d][0][i].w;
+          }
 #pragma unroll
           for (int j = 0; j < kWgPer; ++j)
             if (dst[j] != 0xffffffffu) {
@@ -684,6 +695,11 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
         }
       }
     }
+
+    if (sum_bias)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.gb + n0 + 4 * (tid & (kBlockM / 4 - 1))),
+                   "f"(bsum.x), "f"(bsum.y), "f"(bsum.z), "f"(bsum.w)
+                   : "memory");
 
     // ---- epilogue: this thread owns dW row n0 + 32*(warp%4) + lane, one half of the columns ----
     mbar_wait(bar_done, 0);
@@ -782,14 +798,19 @@ int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
   return (int)cudaGetLastError();
 }
 
-int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, int rows, int in_features,
-                     int out_features, void* cuda_stream) {
+int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
+                     int in_features, int out_features, void* cuda_stream) {
   if (!grad_y || !x || !grad_w) return PCT_MSDA_E_NULL_POINTER;
   if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
-  if (misaligned(grad_y) || misaligned(x) || misaligned(grad_w)) return PCT_MSDA_E_MISALIGNED;
+  if (misaligned(grad_y) || misaligned(x) || misaligned(grad_w) || misaligned(grad_bias))
+    return PCT_MSDA_E_MISALIGNED;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   cudaError_t e = cudaMemsetAsync(grad_w, 0, (size_t)in_features * out_features * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
+  if (grad_bias) {
+    e = cudaMemsetAsync(grad_bias, 0, (size_t)out_features * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+  }
 
   static bool attr_set[64] = {};
   int dev = 0;
@@ -810,7 +831,7 @@ int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, int row
   if (splits > 65535) splits = 65535;
   const int steps_per_split = (total_steps + splits - 1) / splits;
   splits = (total_steps + steps_per_split - 1) / steps_per_split;
-  WgradArgs a{grad_y, x, grad_w, rows, in_features, out_features, steps_per_split};
+  WgradArgs a{grad_y, x, grad_w, grad_bias, rows, in_features, out_features, steps_per_split};
   dim3 grid((out_features + kBlockM - 1) / kBlockM, (in_features + kBlockN - 1) / kBlockN, splits);
   wgrad_tf32x3_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
   pct::count_launch();

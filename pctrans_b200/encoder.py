@@ -185,8 +185,11 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         level_start_index = torch.cat(
             (spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         valid_ratios = torch.stack(ratios, 1)
+        # the masks were created all-False right here (as the reference does, PD:62), so the
+        # layers are told there is no padding instead of running masked_fill over every value
+        del mask_flatten
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios,
-                              pos_flatten, mask_flatten)
+                              pos_flatten, None)
         return memory, spatial_shapes, level_start_index
 
 

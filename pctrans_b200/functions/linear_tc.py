@@ -69,14 +69,18 @@ class TensorCoreLinearFunction(Function):
         n, k = weight.shape
         g = grad_y.reshape(-1, n).contiguous()
         if ctx.relu:
-            g = g * (y > 0)
+            g = torch.ops.aten.threshold_backward(g, y, 0.0)     # one pass: g where y > 0 else 0
         gx = gw = gb = gres = None
         if ctx.needs_input_grad[0]:
             # dX = dY @ W: the same kernel with the transposed weight as its operand
             gx = _cabi.linear_forward(g, packed_weight(weight, transposed=True), k).view(ctx.x_shape)
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            gw = _cabi.linear_wgrad(g, x2)      # dW = dY^T @ X, split over the rows
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            # dW = dY^T @ X split over the rows; the bias gradient rides on the same pass over dY
+            gw = _cabi.linear_wgrad(g, x2, with_bias=want_b)
+            if want_b:
+                gw, gb = gw
+        elif want_b:
             gb = g.sum(0)
         if ctx.has_res and ctx.needs_input_grad[3]:
             gres = g.view(*ctx.x_shape[:-1], n)

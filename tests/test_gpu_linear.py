@@ -56,8 +56,11 @@ def test_weight_gradient_matches_fp64(rows, k, n):
     gw = _cabi.linear_wgrad(gy, x)
     assert gw.shape == (n, k)
     assert _rel(gw, gy.double().t() @ x.double()) < 1e-5
-    # fully overwritten: a second call into a dirty buffer gives the same answer
-    assert _rel(_cabi.linear_wgrad(gy, x), gy.double().t() @ x.double()) < 1e-5
+    # fully overwritten: a second call into a dirty buffer gives the same answer; the bias
+    # gradient (column sums of gy) comes out of the same pass
+    gw2, gb = _cabi.linear_wgrad(gy, x, with_bias=True)
+    assert _rel(gw2, gy.double().t() @ x.double()) < 1e-5
+    assert _rel(gb, gy.double().sum(0)) < 1e-5
 
 
 def test_accuracy_is_fp32_class_not_tf32_class():
