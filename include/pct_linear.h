@@ -53,6 +53,15 @@ int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
                        float ln_eps, float* y, int rows, int in_features, int out_features,
                        unsigned flags, void* cuda_stream);
 
+/* Same, for training with PCT_LINEAR_LAYERNORM: also writes what LayerNorm's backward needs --
+ * pre_norm (rows, out) = x W^T + b (+ residual), ln_mean / ln_rstd (rows,) -- each may be NULL
+ * (mean and rstd together). */
+int pct_linear_forward_train(const float* x, const void* w_packed, const float* bias,
+                             const float* residual, const float* ln_gamma, const float* ln_beta,
+                             float ln_eps, float* y, float* pre_norm, float* ln_mean,
+                             float* ln_rstd, int rows, int in_features, int out_features,
+                             unsigned flags, void* cuda_stream);
+
 /* grad_w (out, in) = grad_y (rows, out)^T @ x (rows, in): the weight gradient of the Linear, same
  * 3xTF32 arithmetic, the row dimension split over CTAs and combined with fp32 reductions (so, like
  * the reference's atomicAdd backward, not bit-reproducible run to run).  grad_w is fully

@@ -31,7 +31,7 @@ EXPORTS = (
     "pct_msda_host_forward_backward",
 )
 LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_forward",
-                  "pct_linear_wgrad")
+                  "pct_linear_forward_train", "pct_linear_wgrad")
 LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM = 0x1, 0x2, 0x4
 E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
@@ -97,6 +97,8 @@ def load():
         lib.pct_linear_pack_weight.argtypes = [vp, vp, i32, i32, vp]
         lib.pct_linear_wgrad.restype = i32
         lib.pct_linear_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+        lib.pct_linear_forward_train.restype = i32
+        lib.pct_linear_forward_train.argtypes = [vp] * 6 + [ctypes.c_float] + [vp] * 4 + [i32] * 3 + [u32, vp]
         lib.pct_linear_forward.restype = i32
         lib.pct_linear_forward.argtypes = [vp] * 6 + [ctypes.c_float, vp] + [i32] * 3 + [u32, vp]
         got = lib.pct_msda_abi_version()
@@ -238,20 +240,27 @@ def linear_pack_weight(weight):
 
 
 def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weight=None,
-                   ln_bias=None, ln_eps: float = 1e-5, relu: bool = False, out=None):
-    """y = epilogue(x @ W^T + bias) on the tensor cores (3xTF32); x (rows, in) fp32 contiguous."""
+                   ln_bias=None, ln_eps: float = 1e-5, relu: bool = False, out=None,
+                   save_for_backward: bool = False):
+    """y = epilogue(x @ W^T + bias) on the tensor cores (3xTF32); x (rows, in) fp32 contiguous.
+    With ``save_for_backward`` (LayerNorm epilogue only) returns (y, pre_norm, mean, rstd)."""
     rows, k = x.shape
     n = out_features
     flags = (LINEAR_RELU if relu else 0) | (LINEAR_RESIDUAL if residual is not None else 0) | \
         (LINEAR_LAYERNORM if ln_weight is not None else 0)
     y = out if out is not None else torch.empty((rows, n), dtype=x.dtype, device=x.device)
     ptr = lambda t: t.data_ptr() if t is not None else None
+    pre = mean = rstd = None
+    if save_for_backward:
+        pre = torch.empty_like(y)
+        mean = torch.empty((rows, 1), dtype=x.dtype, device=x.device)
+        rstd = torch.empty((rows, 1), dtype=x.dtype, device=x.device)
     with torch.cuda.device_of(x):
-        check(load().pct_linear_forward(
+        check(load().pct_linear_forward_train(
             x.data_ptr(), w_packed.data_ptr(), ptr(bias), ptr(residual), ptr(ln_weight),
-            ptr(ln_bias), float(ln_eps), y.data_ptr(), rows, k, n, flags,
-            _stream_ptr(x.device)), "pct_linear_forward")
-    return y
+            ptr(ln_bias), float(ln_eps), y.data_ptr(), ptr(pre), ptr(mean), ptr(rstd), rows, k, n,
+            flags, _stream_ptr(x.device)), "pct_linear_forward")
+    return (y, pre, mean, rstd) if save_for_backward else y
 
 
 def linear_wgrad(grad_y, x, with_bias: bool = False):

@@ -168,6 +168,9 @@ struct LinearArgs {
   const float* gamma;
   const float* beta;
   float* y;
+  float* pre_norm;   // LayerNorm only, may be null: the normalised tensor's input (rows, N)
+  float* mean;       // LayerNorm only, may be null: row statistics for the backward pass
+  float* rstd;
   float eps;
   int rows, K, N;
   unsigned flags;
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
       __syncwarp();
     };
     // v (row domain) -> y block, through the patch
-    auto store_block = [&](int c, int cw) {
+    auto store_block = [&](float* dst_base, int c, int cw) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if (4 * q < cw)
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
       for (int j = 0; j < 8; ++j) {
         const int r = 4 * j + l_row;
         if (l_c4 < cw && r < rows_left)
-          *reinterpret_cast<float4*>(a.y + warp_off + (size_t)r * a.N + c + l_c4) = t[j];
+          *reinterpret_cast<float4*>(dst_base + warp_off + (size_t)r * a.N + c + l_c4) = t[j];
       }
     };
     auto load_acc = [&](int c, int cw) {
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        store_block(c, cw);
+        store_block(a.y, c, cw);
       }
     } else {
       // pass 1: pre-norm row = acc + bias (+ residual), parked back in TMEM; row sum
@@ -442,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
           if (i < cw) sum += v[i];
         tmem_st16(t_row + c, v);
         if (cw > 16) tmem_st16(t_row + c + 16, v + 16);
+        if (a.pre_norm) store_block(a.pre_norm, c, cw);   // training: LayerNorm's input is saved
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       const float mean = sum / (float)a.N;
@@ -455,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
           if (i < cw) ssq += (v[i] - mean) * (v[i] - mean);
       }
       const float rstd = rsqrtf(ssq / (float)a.N + a.eps);
+      if (a.mean && m0 + tid < a.rows) a.mean[m0 + tid] = mean, a.rstd[m0 + tid] = rstd;
       // pass 3: normalise, scale, shift, store
       for (int c = 0; c < n_tile; c += 32) {
         const int cw = min(32, n_tile - c);
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        store_block(c, cw);
+        store_block(a.y, c, cw);
       }
     }
   }
@@ -767,7 +772,20 @@ int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
                        const float* residual, const float* ln_gamma, const float* ln_beta,
                        float ln_eps, float* y, int rows, int in_features, int out_features,
                        unsigned flags, void* cuda_stream) {
+  return pct_linear_forward_train(x, w_packed, bias, residual, ln_gamma, ln_beta, ln_eps, y, nullptr,
+                                  nullptr, nullptr, rows, in_features, out_features, flags,
+                                  cuda_stream);
+}
+
+int pct_linear_forward_train(const float* x, const void* w_packed, const float* bias,
+                             const float* residual, const float* ln_gamma, const float* ln_beta,
+                             float ln_eps, float* y, float* pre_norm, float* ln_mean,
+                             float* ln_rstd, int rows, int in_features, int out_features,
+                             unsigned flags, void* cuda_stream) {
   if (!x || !w_packed || !y) return PCT_MSDA_E_NULL_POINTER;
+  if ((ln_mean == nullptr) != (ln_rstd == nullptr)) return PCT_MSDA_E_NULL_POINTER;
+  if ((pre_norm || ln_mean) && !(flags & PCT_LINEAR_LAYERNORM)) return PCT_MSDA_E_UNSUPPORTED;
+  if (misaligned(pre_norm)) return PCT_MSDA_E_MISALIGNED;
   if ((flags & PCT_LINEAR_RESIDUAL) && !residual) return PCT_MSDA_E_NULL_POINTER;
   if ((flags & PCT_LINEAR_LAYERNORM) && (!ln_gamma || !ln_beta)) return PCT_MSDA_E_NULL_POINTER;
   if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
@@ -791,7 +809,7 @@ int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   LinearArgs a{x, static_cast<const unsigned char*>(w_packed), bias, residual, ln_gamma, ln_beta,
-               y, ln_eps, rows, in_features, out_features, flags};
+               y, pre_norm, ln_mean, ln_rstd, ln_eps, rows, in_features, out_features, flags};
   dim3 grid((out_features + kBlockN - 1) / kBlockN, (unsigned)m_tiles);
   linear_tf32x3_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)cuda_stream>>>(a);
   pct::count_launch();

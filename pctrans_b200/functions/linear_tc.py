@@ -5,8 +5,9 @@ The reference runs its pixel decoder in fp32 with autocast off (PD/msdeformattn.
 the projections of ``MSDeformAttn`` (OPS/modules/ms_deform_attn.py:55-58) and the FFN of the
 encoder layer (PD/msdeformattn.py:107-120) are SIMT fp32 GEMMs.  ``linear`` computes the same
 ``x @ W^T + b`` with ``tcgen05.mma.kind::tf32`` and the 3xTF32 split (error ~1e-6 relative, i.e.
-fp32-level, not TF32-level), with bias, ReLU and the residual add fused; for inference
-``linear_residual_layernorm`` also fuses the LayerNorm that follows ``output_proj`` / ``linear2``.
+fp32-level, not TF32-level), with bias, ReLU and the residual add fused;
+``linear_residual_layernorm`` also fuses the LayerNorm that follows ``output_proj`` / ``linear2``
+(with autograd it additionally writes what LayerNorm's backward needs).
 
 Scope: CUDA fp32 tensors with in/out features multiples of 16, outside autocast.  Anything else
 (CPU tensors, bf16/autocast, odd sizes) is simply not this kernel's job and goes to
@@ -87,6 +88,47 @@ class TensorCoreLinearFunction(Function):
         return gx, gw, gb, gres, None
 
 
+class LinearResidualLayerNormFunction(Function):
+    """y = LayerNorm(x @ W^T + b + residual) in one kernel, with autograd: the kernel also writes
+    LayerNorm's input and row statistics, the backward is aten's LayerNorm backward followed by the
+    tensor-core input / weight gradients."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, ln_weight, ln_bias, eps):
+        n, k = weight.shape
+        x2 = x.reshape(-1, k).contiguous()
+        res2 = residual.reshape(-1, n).contiguous()
+        b = bias.detach().contiguous() if bias is not None else None
+        y, pre, mean, rstd = _cabi.linear_forward(
+            x2, packed_weight(weight), n, b, res2, ln_weight.detach(), ln_bias.detach(), eps,
+            save_for_backward=True)
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        ctx.save_for_backward(x2, weight, pre, mean, rstd, ln_weight, ln_bias)
+        return y.view(*x.shape[:-1], n)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        x2, weight, pre, mean, rstd, ln_weight, ln_bias = ctx.saved_tensors
+        n, k = weight.shape
+        gy = grad_y.reshape(-1, n).contiguous()
+        g, g_lnw, g_lnb = torch.ops.aten.native_layer_norm_backward(
+            gy, pre, [n], mean, rstd, ln_weight, ln_bias, [True, True, True])
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _cabi.linear_forward(g, packed_weight(weight, transposed=True), k).view(ctx.x_shape)
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1]:
+            gw = _cabi.linear_wgrad(g, x2, with_bias=want_b)
+            if want_b:
+                gw, gb = gw
+        elif want_b:
+            gb = g.sum(0)
+        gres = g.view(*ctx.x_shape[:-1], n) if ctx.needs_input_grad[3] else None
+        return gx, gw, gb, gres, g_lnw, g_lnb, None
+
+
 def linear(x, weight, bias=None, residual=None, relu: bool = False):
     """``[relu](F.linear(x, weight, bias) [+ residual])`` -- on the tensor cores when eligible."""
     if eligible(x, weight):
@@ -98,17 +140,19 @@ def linear(x, weight, bias=None, residual=None, relu: bool = False):
 
 
 def linear_residual_layernorm(x, weight, bias, residual, norm: torch.nn.LayerNorm):
-    """``norm(residual + F.linear(x, weight, bias))``.  Without autograd (inference) the whole
-    expression is one kernel; with autograd the LayerNorm stays a torch op (its backward needs
-    the pre-norm tensor) and only bias + residual are fused."""
+    """``norm(residual + F.linear(x, weight, bias))`` as one kernel.  With autograd the kernel also
+    writes LayerNorm's input and row statistics for the backward pass."""
     n = weight.shape[0]
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (x, weight, bias, residual, norm.weight, norm.bias))
-    fusable = (eligible(x, weight) and not needs_grad and n <= 256 and norm.elementwise_affine
+    fusable = (eligible(x, weight) and n <= 256 and norm.elementwise_affine
                and norm.bias is not None and tuple(norm.normalized_shape) == (n,)
                and norm.weight.dtype == torch.float32)
     if not fusable:
         return norm(linear(x, weight, bias, residual=residual))
+    if needs_grad:
+        return LinearResidualLayerNormFunction.apply(x, weight, bias, residual, norm.weight,
+                                                     norm.bias, norm.eps)
     x2 = x.reshape(-1, weight.shape[1]).contiguous()
     y = _cabi.linear_forward(x2, packed_weight(weight), n, bias, residual.reshape(-1, n).contiguous(),
                              norm.weight, norm.bias, norm.eps)

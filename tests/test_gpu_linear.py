@@ -122,6 +122,31 @@ def test_autograd_function_matches_fp64_gradients():
             assert _rel(ours.grad, ref.grad) < 1e-4
 
 
+def test_fused_layernorm_autograd_matches_fp64_gradients():
+    """norm(residual + linear(x)) as one kernel in training: output and all six gradients."""
+    from pctrans_b200.functions import linear_tc
+    rows, k, n = 900, 1024, 256
+    x, w, b, res = _case(rows, k, n, seed=5)
+    norm = torch.nn.LayerNorm(n).cuda()
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.normal_()
+    gy = torch.randn(rows, n).cuda()
+    leaves = [t.clone().requires_grad_(True) for t in (x, w, b, res)]
+    y = linear_tc.linear_residual_layernorm(leaves[0].view(9, 100, k), leaves[1], leaves[2],
+                                            leaves[3].view(9, 100, n), norm)
+    assert type(y.grad_fn).__name__ == "LinearResidualLayerNormFunctionBackward"
+    y.backward(gy.view(9, 100, n))
+    ref_leaves = [t.double().clone().requires_grad_(True) for t in (x, w, b, res)]
+    lw, lb = (p.detach().double().clone().requires_grad_(True) for p in (norm.weight, norm.bias))
+    yr = F.layer_norm(F.linear(ref_leaves[0], ref_leaves[1], ref_leaves[2]) + ref_leaves[3], (n,),
+                      lw, lb, norm.eps)
+    yr.backward(gy.double())
+    assert _rel(y.detach().reshape(rows, n), yr.detach()) < 1e-5
+    for ours, ref in zip(leaves + [norm.weight, norm.bias], ref_leaves + [lw, lb]):
+        assert _rel(ours.grad, ref.grad) < 1e-4
+
+
 def test_packed_weight_cache_follows_in_place_updates():
     from pctrans_b200.functions import linear_tc
     lin = torch.nn.Linear(64, 32).cuda()
