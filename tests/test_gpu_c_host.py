@@ -24,3 +24,19 @@ def test_plain_c_client_roundtrip(tmp_path):
     proc = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert proc.returncode == 0, proc.stdout + proc.stderr
     assert "C_HOST_ROUNDTRIP PASS" in proc.stdout, proc.stdout
+
+
+def test_plain_c_client_of_the_linear_abi(tmp_path):
+    """include/pct_linear.h from plain C with CUDA-runtime device buffers (tests/c/linear_client.c)."""
+    from pctrans_b200 import build
+    lib = build.build_library()
+    exe = str(tmp_path / "linear_client")
+    libdir = os.path.dirname(lib)
+    cmd = ["/usr/bin/gcc", "-O1", "-std=c11", os.path.join(ROOT, "tests", "c", "linear_client.c"),
+           "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", "-L", libdir,
+           "-L", "/usr/local/cuda/lib64", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64",
+           "-lpctrans_msda", "-lcudart", "-lm", "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    proc = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert "C_LINEAR_CLIENT PASS" in proc.stdout, proc.stdout

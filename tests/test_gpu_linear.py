@@ -99,6 +99,11 @@ def test_bad_arguments_are_error_codes():
     with pytest.raises(_cabi.MSDAError) as e:                           # LayerNorm wider than a tile
         _cabi.linear_forward(torch.randn(8, 32).cuda(), wp, 512, None, None, g, g)
     assert e.value.code == _cabi.E_UNSUPPORTED
+    wp2 = _cabi.linear_pack_weight(torch.randn(32, 32).cuda())
+    flat = torch.randn(8 * 32 + 1).cuda()
+    with pytest.raises(_cabi.MSDAError) as e:                           # x not 16-byte aligned
+        _cabi.linear_forward(flat[1:].view(8, 32), wp2, 32)
+    assert e.value.code == 1004
     del x
 
 
