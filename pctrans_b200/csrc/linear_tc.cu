@@ -25,6 +25,10 @@
 #include "../../include/pct_msda.h"
 
 #include <cuda_runtime.h>
+#ifndef PCT_PAIR_STAGES
+#define PCT_PAIR_STAGES 3
+#endif
+#include <stdlib.h>
 
 namespace pct {
 void count_launch();   // msda_capi.cu
@@ -175,6 +179,158 @@ struct LinearArgs {
   int rows, K, N;
   unsigned flags;
 };
+
+// Epilogue of one 128 x n_tile accumulator, run by the four loader warps (warp w owns rows
+// 32w .. 32w+31 of the tile).  Row domain: a thread owns one row and walks its columns in TMEM
+// order.  Line domain: a warp instruction covers 4 rows x 128 contiguous bytes of global memory;
+// the two are bridged by a per-warp 32 x 36-float patch at the start of shared memory.
+__device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned char* smem, uint32_t tmem,
+                                                const float* vec_bias, const float* vec_gamma,
+                                                const float* vec_beta, int warp, int lane, int tid,
+                                                int m0, int n0, int n_tile) {
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const bool relu = a.flags & PCT_LINEAR_RELU, has_res = a.flags & PCT_LINEAR_RESIDUAL;
+  float* patch = reinterpret_cast<float*>(smem) + warp * (32 * kPatchStride);
+  float* patch_row = patch + lane * kPatchStride;
+  const int l_row = lane >> 3, l_c4 = (lane & 7) * 4;
+  const size_t warp_off = (size_t)(m0 + warp * 32) * a.N + n0;   // first row of this warp
+  const int rows_left = a.rows - (m0 + warp * 32);
+  float v[32];
+
+  // residual block (32 rows x cw columns at column c): line-domain loads into registers (issued
+  // one block ahead of their use), then through the patch into the row domain
+  float4 res[8];
+  auto fetch_residual = [&](int c, int cw) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = 4 * j + l_row;
+      if (l_c4 < cw && r < rows_left)
+        res[j] = __ldg(
+            reinterpret_cast<const float4*>(a.residual + warp_off + (size_t)r * a.N + c + l_c4));
+    }
+  };
+  auto add_residual = [&](int cw) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4) = res[j];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (4 * q < cw) {
+        const float4 t = *reinterpret_cast<const float4*>(patch_row + 4 * q);
+        v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
+      }
+    __syncwarp();
+  };
+  // v (row domain) -> y block, through the patch
+  auto store_block = [&](float* dst_base, int c, int cw) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (4 * q < cw)
+        *reinterpret_cast<float4*>(patch_row + 4 * q) =
+            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+    float4 t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      t[j] = *reinterpret_cast<const float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = 4 * j + l_row;
+      if (l_c4 < cw && r < rows_left)
+        *reinterpret_cast<float4*>(dst_base + warp_off + (size_t)r * a.N + c + l_c4) = t[j];
+    }
+  };
+  auto load_acc = [&](int c, int cw) {
+    uint32_t u[32];
+    tmem_ld16(t_row + c, u);
+    if (cw > 16) tmem_ld16(t_row + c + 16, u + 16);
+    tmem_ld_wait();
+    tmem_tie16(u);
+    tmem_tie16(u + 16);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+  };
+  auto add_bias = [&](int c, int cw) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (4 * q < cw) {
+        const float4 b = *reinterpret_cast<const float4*>(vec_bias + c + 4 * q);
+        v[4 * q] += b.x, v[4 * q + 1] += b.y, v[4 * q + 2] += b.z, v[4 * q + 3] += b.w;
+      }
+  };
+
+  if (!(a.flags & PCT_LINEAR_LAYERNORM)) {
+    if (has_res) fetch_residual(0, min(32, n_tile));
+    for (int c = 0; c < n_tile; c += 32) {
+      const int cw = min(32, n_tile - c);
+      load_acc(c, cw);
+      add_bias(c, cw);
+      if (has_res) {
+        add_residual(cw);
+        if (c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      store_block(a.y, c, cw);
+    }
+  } else {
+    // pass 1: pre-norm row = acc + bias (+ residual), parked back in TMEM; row sum
+    float sum = 0.f;
+    if (has_res) fetch_residual(0, min(32, n_tile));
+    for (int c = 0; c < n_tile; c += 32) {
+      const int cw = min(32, n_tile - c);
+      load_acc(c, cw);
+      add_bias(c, cw);
+      if (has_res) {
+        add_residual(cw);
+        if (c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < cw) sum += v[i];
+      tmem_st16(t_row + c, v);
+      if (cw > 16) tmem_st16(t_row + c + 16, v + 16);
+      if (a.pre_norm) store_block(a.pre_norm, c, cw);   // training: LayerNorm's input is saved
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    const float mean = sum / (float)a.N;
+    // pass 2: centred sum of squares
+    float ssq = 0.f;
+    for (int c = 0; c < n_tile; c += 32) {
+      const int cw = min(32, n_tile - c);
+      load_acc(c, cw);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < cw) ssq += (v[i] - mean) * (v[i] - mean);
+    }
+    const float rstd = rsqrtf(ssq / (float)a.N + a.eps);
+    if (a.mean && m0 + tid < a.rows) a.mean[m0 + tid] = mean, a.rstd[m0 + tid] = rstd;
+    // pass 3: normalise, scale, shift, store
+    for (int c = 0; c < n_tile; c += 32) {
+      const int cw = min(32, n_tile - c);
+      load_acc(c, cw);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (4 * q < cw) {
+          const float4 g = *reinterpret_cast<const float4*>(vec_gamma + c + 4 * q);
+          const float4 b = *reinterpret_cast<const float4*>(vec_beta + c + 4 * q);
+          v[4 * q] = (v[4 * q] - mean) * rstd * g.x + b.x;
+          v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * g.y + b.y;
+          v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * g.z + b.z;
+          v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * g.w + b.w;
+        }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      store_block(a.y, c, cw);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const LinearArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -339,154 +495,263 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
     // Line domain: a warp instruction covers 4 rows x 128 contiguous bytes of global memory.
     mbar_wait(bar_done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
-    const bool relu = a.flags & PCT_LINEAR_RELU, has_res = a.flags & PCT_LINEAR_RESIDUAL;
-    float* patch = reinterpret_cast<float*>(smem) + warp * (32 * kPatchStride);
-    float* patch_row = patch + lane * kPatchStride;
-    const int l_row = lane >> 3, l_c4 = (lane & 7) * 4;
-    const size_t warp_off = (size_t)(m0 + warp * 32) * a.N + n0;   // first row of this warp
-    const int rows_left = a.rows - (m0 + warp * 32);
-    float v[32];
-
-    // residual block (32 rows x cw columns at column c): line-domain loads into registers (issued
-    // one block ahead of their use), then through the patch into the row domain
-    float4 res[8];
-    auto fetch_residual = [&](int c, int cw) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = 4 * j + l_row;
-        if (l_c4 < cw && r < rows_left)
-          res[j] = __ldg(
-              reinterpret_cast<const float4*>(a.residual + warp_off + (size_t)r * a.N + c + l_c4));
-      }
-    };
-    auto add_residual = [&](int cw) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4) = res[j];
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (4 * q < cw) {
-          const float4 t = *reinterpret_cast<const float4*>(patch_row + 4 * q);
-          v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
-        }
-      __syncwarp();
-    };
-    // v (row domain) -> y block, through the patch
-    auto store_block = [&](float* dst_base, int c, int cw) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (4 * q < cw)
-          *reinterpret_cast<float4*>(patch_row + 4 * q) =
-              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      __syncwarp();
-      float4 t[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        t[j] = *reinterpret_cast<const float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = 4 * j + l_row;
-        if (l_c4 < cw && r < rows_left)
-          *reinterpret_cast<float4*>(dst_base + warp_off + (size_t)r * a.N + c + l_c4) = t[j];
-      }
-    };
-    auto load_acc = [&](int c, int cw) {
-      uint32_t u[32];
-      tmem_ld16(t_row + c, u);
-      if (cw > 16) tmem_ld16(t_row + c + 16, u + 16);
-      tmem_ld_wait();
-      tmem_tie16(u);
-      tmem_tie16(u + 16);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
-    };
-    auto add_bias = [&](int c, int cw) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (4 * q < cw) {
-          const float4 b = *reinterpret_cast<const float4*>(vec_bias + c + 4 * q);
-          v[4 * q] += b.x, v[4 * q + 1] += b.y, v[4 * q + 2] += b.z, v[4 * q + 3] += b.w;
-        }
-    };
-
-    if (!(a.flags & PCT_LINEAR_LAYERNORM)) {
-      if (has_res) fetch_residual(0, min(32, n_tile));
-      for (int c = 0; c < n_tile; c += 32) {
-        const int cw = min(32, n_tile - c);
-        load_acc(c, cw);
-        add_bias(c, cw);
-        if (has_res) {
-          add_residual(cw);
-          if (c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
-        }
-        if (relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        store_block(a.y, c, cw);
-      }
-    } else {
-      // pass 1: pre-norm row = acc + bias (+ residual), parked back in TMEM; row sum
-      float sum = 0.f;
-      if (has_res) fetch_residual(0, min(32, n_tile));
-      for (int c = 0; c < n_tile; c += 32) {
-        const int cw = min(32, n_tile - c);
-        load_acc(c, cw);
-        add_bias(c, cw);
-        if (has_res) {
-          add_residual(cw);
-          if (c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < cw) sum += v[i];
-        tmem_st16(t_row + c, v);
-        if (cw > 16) tmem_st16(t_row + c + 16, v + 16);
-        if (a.pre_norm) store_block(a.pre_norm, c, cw);   // training: LayerNorm's input is saved
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      const float mean = sum / (float)a.N;
-      // pass 2: centred sum of squares
-      float ssq = 0.f;
-      for (int c = 0; c < n_tile; c += 32) {
-        const int cw = min(32, n_tile - c);
-        load_acc(c, cw);
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < cw) ssq += (v[i] - mean) * (v[i] - mean);
-      }
-      const float rstd = rsqrtf(ssq / (float)a.N + a.eps);
-      if (a.mean && m0 + tid < a.rows) a.mean[m0 + tid] = mean, a.rstd[m0 + tid] = rstd;
-      // pass 3: normalise, scale, shift, store
-      for (int c = 0; c < n_tile; c += 32) {
-        const int cw = min(32, n_tile - c);
-        load_acc(c, cw);
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (4 * q < cw) {
-            const float4 g = *reinterpret_cast<const float4*>(vec_gamma + c + 4 * q);
-            const float4 b = *reinterpret_cast<const float4*>(vec_beta + c + 4 * q);
-            v[4 * q] = (v[4 * q] - mean) * rstd * g.x + b.x;
-            v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * g.y + b.y;
-            v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * g.z + b.z;
-            v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * g.w + b.w;
-          }
-        if (relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        store_block(a.y, c, cw);
-      }
-    }
+    linear_epilogue(a, smem, tmem, vec_bias, vec_gamma, vec_beta, warp, lane, tid, m0, n0, n_tile);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == kLoaderWarps) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
+                 "r"((uint32_t)kBlockN)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, compute 256 rows
+// x n_tile columns with one M=256 MMA stream issued by the leader.  Each CTA keeps its own 128
+// rows of x and only HALF of the W step (n_tile/2 columns) in shared memory; the tensor cores of
+// both SMs read the other half from the partner.  Per K step a CTA therefore moves 80 KB through
+// its shared memory instead of 120 KB (the single-CTA kernel loads the shared-memory data pipe to
+// ~100 %) and the ring holds three stages in the same 96 KB.
+// Status (round 1): bit-for-bit the same results as the single-CTA kernel and 33 % fewer
+// tensor-core shared-memory wavefronts (ncu), but not yet faster -- the cross-CTA hand-offs (remote
+// arrivals, multicast commits) leave the pair latency-bound -- so it is opt-in:
+// PCT_LINEAR_PAIR=1 in the environment selects it (tests/test_gpu_linear.py runs it that way).
+constexpr int kPairStages = PCT_PAIR_STAGES;
+constexpr int kPairStageBytes = 2 * kABytes + kBBytes;          // x hi/lo + half of W hi/lo
+constexpr int kPairBarrierBytes = 128;
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kPairBarrierBytes + kVecBytes;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+
+__device__ __forceinline__ void mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// completion of the pair's MMAs, signalled on the same barrier offset in both CTAs
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_pair_kernel(const LinearArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
+  // the pair sits along x (cluster 2x1x1: cta_group::2 pairs the CTAs of ranks 2i, 2i+1)
+  const int n0 = blockIdx.y * kBlockN;
+  const int m0 = blockIdx.x * kBlockM;                     // may lie past the last row (padding CTA)
+  const int n_tile = min(kBlockN, a.N - n0);
+  const int half_bytes = n_tile * 32;                      // this CTA's n_tile/2 columns of a W piece
+
+  // barriers, kPairStages each: stage free | stage ready (leader's copy counts: both CTAs' x
+  // pieces and the partner's W) | this CTA's W landed; then "accumulator complete"
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kPairStages + 1);
+  float* vec_bias = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + kPairBarrierBytes);
+  float* vec_gamma = vec_bias + kBlockN;
+  float* vec_beta = vec_gamma + kBlockN;
+  const uint32_t bar_empty = smem_u32(bars);
+  const uint32_t bar_ready = bar_empty + 8 * kPairStages;
+  const uint32_t bar_wloc = bar_empty + 16 * kPairStages;
+  const uint32_t bar_done = bar_empty + 24 * kPairStages;
+  const uint32_t leader_ready = map_to_cta(bar_ready, 0);
+
+  if (warp == kLoaderWarps) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)kBlockN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_ready + 8 * s, 2 * kLoaderWarps * 32 + 1);
+      mbar_init(bar_wloc + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int c = tid; c < n_tile; c += kThreads) {
+    vec_bias[c] = a.bias ? a.bias[n0 + c] : 0.f;
+    if (a.flags & PCT_LINEAR_LAYERNORM) vec_gamma[c] = a.gamma[n0 + c], vec_beta[c] = a.beta[n0 + c];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                                      // both CTAs' barriers exist from here on
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const int n_steps = a.K / kBlockK;
+  const uint32_t smem0 = smem_u32(smem);
+
+  if (warp == kLoaderWarps) {
+    if (lane == 0 && rank == 0) {
+      // ---- leader: issue the M=256 MMAs of the pair ------------------------------------------
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_tile >> 3) << 17) |
+                             ((uint32_t)(2 * kBlockM >> 4) << 24);
+      for (int step = 0; step < n_steps; ++step) {
+        const int s = step % kPairStages;
+        const uint32_t parity = (step / kPairStages) & 1;
+        mbar_wait(bar_wloc + 8 * s, parity);               // own half of W
+        mbar_wait_cluster(bar_ready + 8 * s, parity);      // both CTAs' x pieces, partner's W
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem0 + s * kPairStageBytes;
+#pragma unroll
+        for (int ks = 0; ks < kBlockK / kMmaK; ++ks) {
+          const uint32_t koff = ks * (kMmaK / 4) * kLbo;
+          const uint64_t d_ahi = make_smem_desc(sa + koff);
+          const uint64_t d_alo = make_smem_desc(sa + kABytes + koff);
+          const uint64_t d_bhi = make_smem_desc(sa + 2 * kABytes + koff);
+          const uint64_t d_blo = make_smem_desc(sa + 2 * kABytes + kBBytes / 2 + koff);
+          mma_tf32_pair(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);
+          mma_tf32_pair(tmem, d_ahi, d_bhi, idesc, 1u);
+          mma_tf32_pair(tmem, d_ahi, d_blo, idesc, 1u);
+        }
+        mma_commit_pair(bar_empty + 8 * s);
+        if (step == n_steps - 1) mma_commit_pair(bar_done);
+      }
+    } else if (lane == 0) {
+      // ---- partner: tell the leader when this CTA's half of W has landed ----------------------
+      for (int step = 0; step < n_steps; ++step) {
+        const int s = step % kPairStages;
+        mbar_wait(bar_wloc + 8 * s, (step / kPairStages) & 1);
+        mbar_arrive_remote(leader_ready + 8 * s);
+      }
+    }
+  } else if (warp == kLoaderWarps + 1) {
+    // ---- W producer (both CTAs): this CTA's columns of the hi piece, then of the lo piece ------
+    const unsigned char* w_tile =
+        a.w_packed + (size_t)blockIdx.y * n_steps * kWStepBytes + (size_t)rank * half_bytes;
+    auto fetch_w = [&](int step) {
+      const int s = step % kPairStages;
+      const uint32_t dst = smem0 + s * kPairStageBytes + 2 * kABytes;
+      mbar_expect_tx(bar_wloc + 8 * s, 2 * half_bytes);
+      bulk_load(dst, w_tile + (size_t)step * kWStepBytes, half_bytes, bar_wloc + 8 * s);
+      bulk_load(dst + kBBytes / 2, w_tile + (size_t)step * kWStepBytes + kBBytes, half_bytes,
+                bar_wloc + 8 * s);
+    };
+    if (lane == 0)
+      for (int step = 0; step < kPairStages && step < n_steps; ++step) fetch_w(step);
+    const int tile_rows = min(kBlockM, a.rows - m0);
+    if (tile_rows > 0) {
+      const size_t x_bytes = (size_t)tile_rows * a.K * 4;
+      const char* xp = reinterpret_cast<const char*>(a.x + (size_t)m0 * a.K);
+      for (size_t off = (size_t)lane * 32768; off < x_bytes; off += 32 * 32768) {
+        const size_t nb = x_bytes - off < 32768 ? x_bytes - off : 32768;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xp + off), "r"((uint32_t)nb)
+                     : "memory");
+      }
+      if (a.flags & PCT_LINEAR_RESIDUAL) {
+        for (int r = lane; r < tile_rows; r += 32)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                           a.residual + (size_t)(m0 + r) * a.N + n0),
+                       "r"((uint32_t)(n_tile * 4))
+                       : "memory");
+      }
+    }
+    if (lane == 0)
+      for (int step = kPairStages; step < n_steps; ++step) {
+        mbar_wait(bar_empty + 8 * (step % kPairStages), ((step / kPairStages) - 1) & 1);
+        fetch_w(step);
+      }
+  } else {
+    // ---- loaders (both CTAs): as in the single-CTA kernel, arriving on the LEADER's barrier ----
+    const int r8 = tid & 7, kc = (tid >> 3) & 3, rg = tid >> 5;
+    constexpr int kPerThread = kBlockM * kBlockK / 4 / (kLoaderWarps * 32);
+    const float* xrow[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int row = m0 + (rg + kLoaderWarps * j) * 8 + r8;
+      xrow[j] = row < a.rows ? a.x + (size_t)row * a.K + kc * 4 : nullptr;
+    }
+    float4 xq[kAhead][kPerThread];
+    auto fetch_x = [&](float4* dst, int step) {
+#pragma unroll
+      for (int j = 0; j < kPerThread; ++j)
+        dst[j] = xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + step * kBlockK))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+#pragma unroll
+    for (int d = 0; d < kAhead; ++d)
+      if (d < n_steps) fetch_x(xq[d], d);
+    for (int step0 = 0; step0 < n_steps; step0 += kAhead) {
+#pragma unroll
+      for (int d = 0; d < kAhead; ++d) {
+        const int step = step0 + d;
+        if (step < n_steps) {
+          const int s = step % kPairStages;
+          if (step >= kPairStages)
+            mbar_wait(bar_empty + 8 * s, ((step / kPairStages) - 1) & 1);
+          float4* a_hi = reinterpret_cast<float4*>(smem + s * kPairStageBytes);
+          float4* a_lo = reinterpret_cast<float4*>(smem + s * kPairStageBytes + kABytes);
+#pragma unroll
+          for (int j = 0; j < kPerThread; ++j) {
+            const float4 x4 = xq[d][j];
+            float4 h, l;
+            h.x = tf32_head(x4.x), h.y = tf32_head(x4.y), h.z = tf32_head(x4.z), h.w = tf32_head(x4.w);
+            l.x = x4.x - h.x, l.y = x4.y - h.y, l.z = x4.z - h.z, l.w = x4.w - h.w;
+            a_hi[tid + kLoaderWarps * 32 * j] = h;
+            a_lo[tid + kLoaderWarps * 32 * j] = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive_remote(leader_ready + 8 * s);
+          if (step + kAhead < n_steps) fetch_x(xq[d], step + kAhead);
+        }
+      }
+    }
+
+    mbar_wait_cluster(bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    linear_epilogue(a, smem, tmem, vec_bias, vec_gamma, vec_beta, warp, lane, tid, m0, n0, n_tile);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                  // nobody leaves while the partner may still signal or read
+  if (warp == kLoaderWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                  "r"((uint32_t)kBlockN)
                  : "memory");
   }
@@ -811,6 +1076,35 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
   LinearArgs a{x, static_cast<const unsigned char*>(w_packed), bias, residual, ln_gamma, ln_beta,
                y, pre_norm, ln_mean, ln_rstd, ln_eps, rows, in_features, out_features, flags};
   dim3 grid((out_features + kBlockN - 1) / kBlockN, (unsigned)m_tiles);
+  static const int use_pair = [] {
+    const char* e = getenv("PCT_LINEAR_PAIR");
+    return e ? atoi(e) : 0;
+  }();
+  if (use_pair) {
+    static bool pair_attr[64] = {};
+    if (dev < 0 || dev >= 64 || !pair_attr[dev]) {
+      e = cudaFuncSetAttribute(linear_tf32x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kPairSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      if (dev >= 0 && dev < 64) pair_attr[dev] = true;
+    }
+    grid = dim3((unsigned)((m_tiles + 1) / 2 * 2), grid.x);   // whole pairs along x; a padding CTA has no rows
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kPairSmemBytes;
+    cfg.stream = (cudaStream_t)cuda_stream;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, linear_tf32x3_pair_kernel, a);
+    pct::count_launch();
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
+  }
   linear_tf32x3_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)cuda_stream>>>(a);
   pct::count_launch();
   return (int)cudaGetLastError();

@@ -152,6 +152,42 @@ def test_fused_layernorm_autograd_matches_fp64_gradients():
         assert _rel(ours.grad, ref.grad) < 1e-4
 
 
+def test_cta_pair_kernel_gives_the_same_results():
+    """The opt-in cta_group::2 variant (PCT_LINEAR_PAIR=1, read once per process): same shapes and
+    epilogues, in a subprocess, against fp64."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import sys; sys.path.insert(0, %r)
+import torch, torch.nn.functional as F
+from pctrans_b200 import _cabi
+torch.manual_seed(0)
+worst = 0.0
+for rows, k, n in [(1, 16, 16), (129, 256, 192), (300, 64, 48), (1000, 256, 96), (777, 256, 1024),
+                   (513, 1024, 256), (5376, 256, 256), (5000, 128, 288)]:
+    x = torch.randn(rows, k).cuda(); w = (torch.randn(n, k) / k ** 0.5).cuda()
+    b = torch.randn(n).cuda(); res = torch.randn(rows, n).cuda()
+    wp = _cabi.linear_pack_weight(w)
+    ref = x.double() @ w.double().t() + b.double()
+    outs = [(_cabi.linear_forward(x, wp, n, b, relu=True), ref.relu()),
+            (_cabi.linear_forward(x, wp, n, b, res), ref + res.double())]
+    if n <= 256:
+        g, be = torch.rand(n).cuda() + 0.5, torch.randn(n).cuda()
+        outs.append((_cabi.linear_forward(x, wp, n, b, res, g, be, 1e-5),
+                     F.layer_norm(ref + res.double(), (n,), g.double(), be.double(), 1e-5)))
+    for y, r in outs:
+        worst = max(worst, float((y.double() - r).abs().max() / r.abs().max()))
+print("PAIR_WORST", worst)
+""" % root
+    env = dict(os.environ, PCT_LINEAR_PAIR="1")
+    proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    worst = float(proc.stdout.split("PAIR_WORST")[1])
+    assert worst < 1e-5, worst
+
+
 def test_packed_weight_cache_follows_in_place_updates():
     from pctrans_b200.functions import linear_tc
     lin = torch.nn.Linear(64, 32).cuda()
