@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_empty + 8 * s, 1);
-      mbar_init(bar_xfull + 8 * s, kLoaderWarps * 32);
+      mbar_init(bar_xfull + 8 * s, kLoaderWarps);
       mbar_init(bar_wfull + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
@@ -484,7 +484,9 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
             a_lo[tid + kLoaderWarps * 32 * j] = l;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_xfull + 8 * s) : "memory");
+          __syncwarp();                                                    // one arrival per warp
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_xfull + 8 * s) : "memory");
           if (step + kAhead < n_steps) fetch_x(xq[d], step + kAhead);
         }
       }
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_pair_kernel(const L
   if (tid == 0) {
     for (int s = 0; s < kPairStages; ++s) {
       mbar_init(bar_empty + 8 * s, 1);
-      mbar_init(bar_ready + 8 * s, 2 * kLoaderWarps * 32 + 1);
+      mbar_init(bar_ready + 8 * s, 2 * kLoaderWarps + 1);
       mbar_init(bar_wloc + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
@@ -737,7 +739,8 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_pair_kernel(const L
             a_lo[tid + kLoaderWarps * 32 * j] = l;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive_remote(leader_ready + 8 * s);
+          __syncwarp();                                  // one (remote) arrival per warp
+          if (lane == 0) mbar_arrive_remote(leader_ready + 8 * s);
           if (step + kAhead < n_steps) fetch_x(xq[d], step + kAhead);
         }
       }
@@ -848,7 +851,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_empty + 8 * s, 1);
-      mbar_init(bar_full + 8 * s, kWgLoaderWarps * 32);
+      mbar_init(bar_full + 8 * s, kWgLoaderWarps);
     }
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -960,7 +963,9 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
               split_store(hi + 48, lo + 48, r[0].w, r[1].w, r[2].w, r[3].w);
             }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
           if (step + kWgAhead < n_steps) fetch(q[d], step + kWgAhead);
         }
       }
