@@ -117,7 +117,8 @@ class MSDeformAttnTransformerEncoder(nn.Module):
     @staticmethod
     def get_reference_points(spatial_shapes, valid_ratios, device):
         """(N, S, L, 2): normalised pixel centres of every pyramid position, replicated to all
-        levels and scaled by the valid ratios (PD:141-153)."""
+        levels and scaled by the valid ratios (PD:141-153).  ``spatial_shapes`` may be the (L, 2)
+        tensor (as in the reference; reading it costs a device sync) or a sequence of (H, W)."""
         per_level = []
         for lvl, (H_, W_) in enumerate(spatial_shapes):
             H_, W_ = int(H_), int(W_)
@@ -130,9 +131,13 @@ class MSDeformAttnTransformerEncoder(nn.Module):
         ref = torch.cat(per_level, 1)
         return ref[:, :, None] * valid_ratios[:, None]
 
-    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
+                *, shapes_hint=None):
+        """``shapes_hint``: the pyramid as Python (H, W) pairs when the caller has them, so the
+        reference points are built without reading the shape tensor back from the device."""
         out = src
-        ref = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        ref = self.get_reference_points(spatial_shapes if shapes_hint is None else shapes_hint,
+                                        valid_ratios, device=src.device)
         for layer in self.layers:
             out = layer(out, pos, ref, spatial_shapes, level_start_index, padding_mask)
         return out
@@ -159,6 +164,19 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
                 m._reset_parameters()
         nn.init.normal_(self.level_embed)
 
+    def _level_tensors(self, shapes, device):
+        """(L, 2) shapes and (L,) start indices on the device, built once per pyramid: the host ->
+        device copy of a Python list each forward would be a sync point (and is not capturable in
+        a CUDA graph)."""
+        cache = self.__dict__.setdefault("_level_cache", {})
+        key = (shapes, str(device))
+        if key not in cache:
+            spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=device)
+            level_start_index = torch.cat(
+                (spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+            cache[key] = (spatial_shapes, level_start_index)
+        return cache[key]
+
     @staticmethod
     def get_valid_ratio(mask):
         _, H, W = mask.shape
@@ -181,15 +199,13 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         src_flatten = torch.cat(flat_src, 1)
         pos_flatten = torch.cat(flat_pos, 1)
         mask_flatten = torch.cat(flat_mask, 1)
-        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=src_flatten.device)
-        level_start_index = torch.cat(
-            (spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        spatial_shapes, level_start_index = self._level_tensors(tuple(shapes), src_flatten.device)
         valid_ratios = torch.stack(ratios, 1)
         # the masks were created all-False right here (as the reference does, PD:62), so the
         # layers are told there is no padding instead of running masked_fill over every value
         del mask_flatten
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios,
-                              pos_flatten, None)
+                              pos_flatten, None, shapes_hint=shapes)
         return memory, spatial_shapes, level_start_index
 
 

@@ -78,9 +78,7 @@ class TensorCoreLinearFunction(Function):
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             # dW = dY^T @ X split over the rows; the bias gradient rides on the same pass over dY
-            gw = _cabi.linear_wgrad(g, x2, with_bias=want_b)
-            if want_b:
-                gw, gb = gw
+            gw, gb = _wgrad(g, x2, want_b)
         elif want_b:
             gb = g.sum(0)
         if ctx.has_res and ctx.needs_input_grad[3]:
@@ -120,13 +118,21 @@ class LinearResidualLayerNormFunction(Function):
             gx = _cabi.linear_forward(g, packed_weight(weight, transposed=True), k).view(ctx.x_shape)
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            gw = _cabi.linear_wgrad(g, x2, with_bias=want_b)
-            if want_b:
-                gw, gb = gw
+            gw, gb = _wgrad(g, x2, want_b)
         elif want_b:
             gb = g.sum(0)
         gres = g.view(*ctx.x_shape[:-1], n) if ctx.needs_input_grad[3] else None
         return gx, gw, gb, gres, g_lnw, g_lnb, None
+
+
+def _wgrad(g, x2, want_bias):
+    """(dW, db): split-K tensor-core kernel (fp32 reductions, order varies run to run) -- or, under
+    ``torch.use_deterministic_algorithms(True)``, torch's deterministic GEMM and column sum."""
+    if torch.are_deterministic_algorithms_enabled():
+        return g.t() @ x2, (g.sum(0) if want_bias else None)
+    if want_bias:
+        return _cabi.linear_wgrad(g, x2, with_bias=True)
+    return _cabi.linear_wgrad(g, x2), None
 
 
 def linear(x, weight, bias=None, residual=None, relu: bool = False):

@@ -95,6 +95,14 @@ class MSDeformAttn(nn.Module):
             return ref + offsets / wh[None, None, None, :, None, :]
         return ref[..., :2] + offsets / self.n_points * ref[..., 2:] * 0.5
 
+    def _check_lengths(self, spatial_shapes, len_in):
+        """``sum_l H_l*W_l == Len_in`` (mod.py:96).  Reading the shapes back is a device sync, so a
+        given shapes tensor is checked once, not in every layer of every step."""
+        key = (spatial_shapes.data_ptr(), spatial_shapes._version, len_in)
+        if self.__dict__.get("_lengths_ok") != key:
+            assert int(spatial_shapes.prod(1).sum()) == len_in
+            self.__dict__["_lengths_ok"] = key
+
     def _proj(self, layer, x):
         if self.tensor_core_linears:
             return linear_tc.linear(x, layer.weight, layer.bias)
@@ -119,7 +127,7 @@ class MSDeformAttn(nn.Module):
         the reference's signature) are given."""
         n, len_q, _ = query.shape
         len_in = input_flatten.shape[1]
-        assert int(input_spatial_shapes.prod(1).sum()) == len_in
+        self._check_lengths(input_spatial_shapes, len_in)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead."
                              .format(reference_points.shape[-1]))

@@ -188,6 +188,60 @@ print("PAIR_WORST", worst)
     assert worst < 1e-5, worst
 
 
+def test_deterministic_mode_gives_bit_identical_weight_gradients():
+    """The split-K wgrad combines slices with fp32 reductions; under
+    torch.use_deterministic_algorithms the Function must not use it."""
+    from pctrans_b200.functions import linear_tc
+    x, w, b, _ = _case(20000, 256, 192, seed=6)
+    gy = torch.randn(20000, 192).cuda()
+
+    def grads():
+        leaves = [t.clone().requires_grad_(True) for t in (x, w, b)]
+        linear_tc.linear(leaves[0], leaves[1], leaves[2]).backward(gy)
+        return [t.grad.clone() for t in leaves]
+
+    torch.use_deterministic_algorithms(True)
+    try:
+        first, second = grads(), grads()
+    finally:
+        torch.use_deterministic_algorithms(False)
+    for a_, b_ in zip(first, second):
+        assert torch.equal(a_, b_)
+    ref_w = gy.double().t() @ x.double()
+    assert _rel(first[1], ref_w) < 1e-4
+
+
+def test_encoder_inference_replays_from_a_cuda_graph():
+    """Kernels, packed-weight cache and fused epilogues under CUDA graph capture: a captured
+    3-layer encoder forward replays to the eager result (launch-bound inference loops, B200 guide)."""
+    from pctrans_b200 import encoder as enc, synth
+    torch.manual_seed(1)
+    pyramid = synth.CVPPP_448
+    model = enc.MSDeformAttnTransformerEncoderOnly(
+        d_model=128, nhead=8, num_encoder_layers=3, dim_feedforward=512, dropout=0.0,
+        num_feature_levels=len(pyramid)).cuda().eval()
+    srcs = [torch.randn(2, 128, h, w).cuda() for h, w in pyramid]
+    pos = [enc.PositionEmbeddingSine(64, normalize=True)(s) for s in srcs]
+    with torch.no_grad():
+        eager = model(srcs, pos)[0].clone()          # also warms the packed-weight cache
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                model(srcs, pos)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            captured = model(srcs, pos)[0]
+        for s in srcs:
+            s.mul_(0.5)                               # new inputs in the captured buffers
+        graph.replay()
+        torch.cuda.synchronize()
+        expect = model(srcs, pos)[0]
+    assert _rel(captured, expect.double()) < 1e-6
+    assert not torch.equal(captured, eager)
+
+
 def test_packed_weight_cache_follows_in_place_updates():
     from pctrans_b200.functions import linear_tc
     lin = torch.nn.Linear(64, 32).cuda()
