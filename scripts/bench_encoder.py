@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--fused", type=int, default=1, help="use the fused-prologue kernels (default)")
     ap.add_argument("--tc-linears", type=int, default=1,
                     help="fp32 Linears on the tensor cores (3xTF32, functions/linear_tc.py)")
+    ap.add_argument("--cuda-graph", type=int, default=0,
+                    help="inference only: capture the forward once and time graph replays")
     ap.add_argument("--tf32", type=int, default=0, help="allow TF32 tensor cores for the Linears")
     ap.add_argument("--autocast", default="none", choices=["none", "bf16"],
                     help="run the encoder under bf16 autocast (the reference disables autocast here "
@@ -118,6 +120,14 @@ def main():
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
+    if args.cuda_graph and args.mode == "infer":
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        step = graph.replay
+        for _ in range(3):
+            step()
+        barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -131,7 +141,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "bench": "encoder", "mode": args.mode, "core": args.core, "fused": bool(args.fused),
-            "tf32": bool(args.tf32), "tc_linears": bool(args.tc_linears), "autocast": args.autocast, "pyramid": args.pyramid,
+            "tf32": bool(args.tf32), "tc_linears": bool(args.tc_linears), "cuda_graph": bool(args.cuda_graph), "autocast": args.autocast, "pyramid": args.pyramid,
             "d_model": args.d_model, "layers": args.layers, "n_gpus": world, "batch_per_gpu": n,
             "global_batch": n * world, "ms_per_step": ms,
             "query_layers_per_s": world * n * lq * args.layers / (ms * 1e-3),
