@@ -132,12 +132,21 @@ class MSDeformAttnTransformerEncoder(nn.Module):
         return ref[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
-                *, shapes_hint=None):
+                *, shapes_hint=None, unit_ratios=False):
         """``shapes_hint``: the pyramid as Python (H, W) pairs when the caller has them, so the
-        reference points are built without reading the shape tensor back from the device."""
+        reference points are built without reading the shape tensor back from the device.
+        ``unit_ratios``: the caller guarantees ``valid_ratios == 1`` (no padding), which makes the
+        reference points a constant of the pyramid: they are built once and reused."""
         out = src
-        ref = self.get_reference_points(spatial_shapes if shapes_hint is None else shapes_hint,
-                                        valid_ratios, device=src.device)
+        if shapes_hint is not None and unit_ratios:
+            cache = self.__dict__.setdefault("_ref_cache", {})
+            key = (tuple(shapes_hint), src.shape[0], str(src.device))
+            if key not in cache:
+                cache[key] = self.get_reference_points(shapes_hint, valid_ratios, device=src.device)
+            ref = cache[key]
+        else:
+            ref = self.get_reference_points(spatial_shapes if shapes_hint is None else shapes_hint,
+                                            valid_ratios, device=src.device)
         for layer in self.layers:
             out = layer(out, pos, ref, spatial_shapes, level_start_index, padding_mask)
         return out
@@ -187,25 +196,22 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
     def forward(self, srcs: Sequence[torch.Tensor], pos_embeds: Sequence[torch.Tensor]):
         """srcs / pos_embeds: per level (N, C, H_l, W_l), low -> high resolution.  Returns
         (memory (N, S, C), spatial_shapes (L, 2), level_start_index (L,))."""
-        flat_src, flat_pos, flat_mask, shapes, ratios = [], [], [], [], []
+        # No padding anywhere (the reference builds all-False masks here, PD:62, and derives
+        # valid_ratios == 1 from them): the masks are not materialised, the ratios are ones.
+        flat_src, flat_pos, shapes = [], [], []
         for lvl, (src, pos) in enumerate(zip(srcs, pos_embeds)):
             n, _, h, w = src.shape
-            mask = torch.zeros((n, h, w), device=src.device, dtype=torch.bool)   # PD:62: no padding
             shapes.append((h, w))
             flat_src.append(src.flatten(2).transpose(1, 2))
             flat_pos.append(pos.flatten(2).transpose(1, 2) + self.level_embed[lvl].view(1, 1, -1))
-            flat_mask.append(mask.flatten(1))
-            ratios.append(self.get_valid_ratio(mask))
         src_flatten = torch.cat(flat_src, 1)
         pos_flatten = torch.cat(flat_pos, 1)
-        mask_flatten = torch.cat(flat_mask, 1)
         spatial_shapes, level_start_index = self._level_tensors(tuple(shapes), src_flatten.device)
-        valid_ratios = torch.stack(ratios, 1)
-        # the masks were created all-False right here (as the reference does, PD:62), so the
-        # layers are told there is no padding instead of running masked_fill over every value
-        del mask_flatten
+        valid_ratios = src_flatten.new_ones((src_flatten.shape[0], len(shapes), 2))
+        # ... and the layers are told there is no padding instead of running masked_fill over every
+        # value with an all-False mask
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios,
-                              pos_flatten, None, shapes_hint=shapes)
+                              pos_flatten, None, shapes_hint=shapes, unit_ratios=True)
         return memory, spatial_shapes, level_start_index
 
 
