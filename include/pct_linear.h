@@ -36,7 +36,8 @@ extern "C" {
 #define PCT_LINEAR_LAYERNORM 0x4u /* y = LayerNorm(. ) * gamma + beta over the out dim;
                                      needs out_features <= 256 (one tile holds a whole row) */
 
-/* Constraints everywhere: in_features % 16 == 0, out_features % 16 == 0, 16-byte aligned pointers. */
+/* Constraints everywhere: in_features % 16 == 0, out_features % 16 == 0; x, packed weight, residual,
+ * y, pre_norm, grad_y, grad_w, grad_bias 16-byte aligned (bias / LayerNorm vectors: 4-byte). */
 
 /* Bytes of the packed weight (0 if the dimensions are not supported). */
 size_t pct_linear_packed_bytes(int in_features, int out_features);

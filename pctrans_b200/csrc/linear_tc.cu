@@ -1062,8 +1062,11 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
   if ((flags & PCT_LINEAR_LAYERNORM) && out_features > kBlockN) return PCT_MSDA_E_UNSUPPORTED;
   if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM))
     return PCT_MSDA_E_UNSUPPORTED;
-  if (misaligned(x) || misaligned(w_packed) || misaligned(y) || misaligned(bias) ||
-      misaligned(residual) || misaligned(ln_gamma) || misaligned(ln_beta))
+  // 16-byte accesses: x, packed W, residual, y, pre_norm; bias / gamma / beta are read as scalars
+  if (misaligned(x) || misaligned(w_packed) || misaligned(y) || misaligned(residual))
+    return PCT_MSDA_E_MISALIGNED;
+  if (((uintptr_t)bias | (uintptr_t)ln_gamma | (uintptr_t)ln_beta | (uintptr_t)ln_mean |
+       (uintptr_t)ln_rstd) & 3u)
     return PCT_MSDA_E_MISALIGNED;
   const long long m_tiles = ((long long)rows + kBlockM - 1) / kBlockM;
   if (m_tiles > 65535) return PCT_MSDA_E_TOO_LARGE;

@@ -43,7 +43,8 @@ def packed_weight(weight: torch.Tensor, transposed: bool = False) -> torch.Tenso
 def eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
     return (ENABLED and x.is_cuda and weight.is_cuda and x.dtype == torch.float32
             and weight.dtype == torch.float32 and not torch.is_autocast_enabled()
-            and weight.shape[0] % 16 == 0 and weight.shape[1] % 16 == 0 and x.numel() > 0)
+            and weight.shape[0] % 16 == 0 and weight.shape[1] % 16 == 0 and x.numel() > 0
+            and x.data_ptr() % 16 == 0 and x.storage_offset() % 4 == 0)
 
 
 class TensorCoreLinearFunction(Function):
