@@ -152,3 +152,18 @@ def test_config4_bbbc_encoder_forward_backward(monkeypatch):
         # parity is pinned tightly in test_gpu_parity.py
         err = float((grads[k] - grads_ref[k]).norm() / grads_ref[k].norm())
         assert err <= 3e-2, (k, err)
+
+
+def test_linear_helpers_on_cpu_are_plain_torch():
+    """functions/linear_tc.py only takes over CUDA fp32 GEMMs; on CPU tensors its helpers are the
+    torch expressions they replace (the encoder's CPU path, used with the oracle above)."""
+    from pctrans_b200.functions import linear_tc
+    torch.manual_seed(0)
+    lin, norm = torch.nn.Linear(32, 48), torch.nn.LayerNorm(48)
+    x, res = torch.randn(5, 7, 32), torch.randn(5, 7, 48)
+    assert not linear_tc.eligible(x, lin.weight)
+    assert torch.equal(linear_tc.linear(x, lin.weight, lin.bias), lin(x))
+    assert torch.equal(linear_tc.linear(x, lin.weight, lin.bias, residual=res, relu=True),
+                       torch.relu(lin(x) + res))
+    assert torch.equal(linear_tc.linear_residual_layernorm(x, lin.weight, lin.bias, res, norm),
+                       norm(res + lin(x)))
