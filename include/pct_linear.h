@@ -33,6 +33,9 @@ extern "C" {
 /* epilogue flags */
 #define PCT_LINEAR_RELU 0x1u      /* y = max(., 0)                                        */
 #define PCT_LINEAR_RESIDUAL 0x2u  /* y = residual + (x W^T + b); residual (rows, out)      */
+#define PCT_LINEAR_GATE 0x8u      /* y = (x W^T + b) where gate > 0, else 0; the (rows, out) gate is passed
+                                     in `residual` (ReLU backward fused into the input-gradient GEMM);
+                                     not combinable with RESIDUAL / LAYERNORM */
 #define PCT_LINEAR_LAYERNORM 0x4u /* y = LayerNorm(. ) * gamma + beta over the out dim;
                                      needs out_features <= 256 (one tile holds a whole row) */
 

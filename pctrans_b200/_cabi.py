@@ -32,7 +32,7 @@ EXPORTS = (
 )
 LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_forward",
                   "pct_linear_forward_train", "pct_linear_wgrad")
-LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM = 0x1, 0x2, 0x4
+LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM, LINEAR_GATE = 0x1, 0x2, 0x4, 0x8
 E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
 FLAG_BF16_ACCUM = 0x8
@@ -241,13 +241,18 @@ def linear_pack_weight(weight):
 
 def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weight=None,
                    ln_bias=None, ln_eps: float = 1e-5, relu: bool = False, out=None,
-                   save_for_backward: bool = False):
+                   save_for_backward: bool = False, gate=None):
     """y = epilogue(x @ W^T + bias) on the tensor cores (3xTF32); x (rows, in) fp32 contiguous.
-    With ``save_for_backward`` (LayerNorm epilogue only) returns (y, pre_norm, mean, rstd)."""
+    With ``save_for_backward`` (LayerNorm epilogue only) returns (y, pre_norm, mean, rstd).
+    ``gate`` (rows, out): y is zeroed where gate <= 0 (ReLU backward fused into a dgrad GEMM)."""
     rows, k = x.shape
     n = out_features
     flags = (LINEAR_RELU if relu else 0) | (LINEAR_RESIDUAL if residual is not None else 0) | \
-        (LINEAR_LAYERNORM if ln_weight is not None else 0)
+        (LINEAR_LAYERNORM if ln_weight is not None else 0) | (LINEAR_GATE if gate is not None else 0)
+    if gate is not None:
+        if residual is not None:
+            raise ValueError("gate and residual share an argument slot of the C ABI")
+        residual = gate
     y = out if out is not None else torch.empty((rows, n), dtype=x.dtype, device=x.device)
     ptr = lambda t: t.data_ptr() if t is not None else None
     pre = mean = rstd = None

@@ -190,6 +190,7 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
                                                 int m0, int n0, int n_tile) {
   const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
   const bool relu = a.flags & PCT_LINEAR_RELU, has_res = a.flags & PCT_LINEAR_RESIDUAL;
+  const bool has_gate = a.flags & PCT_LINEAR_GATE;   // `residual` holds the gate tensor instead
   float* patch = reinterpret_cast<float*>(smem) + warp * (32 * kPatchStride);
   float* patch_row = patch + lane * kPatchStride;
   const int l_row = lane >> 3, l_c4 = (lane & 7) * 4;
@@ -223,7 +224,7 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
     __syncwarp();
   };
   // v (row domain) -> y block, through the patch
-  auto store_block = [&](float* dst_base, int c, int cw) {
+  auto store_block = [&](float* dst_base, int c, int cw, bool gated = false) {
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       if (4 * q < cw)
@@ -235,6 +236,13 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
     for (int j = 0; j < 8; ++j)
       t[j] = *reinterpret_cast<const float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4);
     __syncwarp();
+    if (gated) {   // res[] holds the gate block in exactly this (line-domain) arrangement
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        t[j].x = res[j].x > 0.f ? t[j].x : 0.f, t[j].y = res[j].y > 0.f ? t[j].y : 0.f;
+        t[j].z = res[j].z > 0.f ? t[j].z : 0.f, t[j].w = res[j].w > 0.f ? t[j].w : 0.f;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int r = 4 * j + l_row;
@@ -262,7 +270,7 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
   };
 
   if (!(a.flags & PCT_LINEAR_LAYERNORM)) {
-    if (has_res) fetch_residual(0, min(32, n_tile));
+    if (has_res || has_gate) fetch_residual(0, min(32, n_tile));
     for (int c = 0; c < n_tile; c += 32) {
       const int cw = min(32, n_tile - c);
       load_acc(c, cw);
@@ -275,7 +283,8 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
       }
-      store_block(a.y, c, cw);
+      store_block(a.y, c, cw, has_gate);
+      if (has_gate && c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
     }
   } else {
     // pass 1: pre-norm row = acc + bias (+ residual), parked back in TMEM; row sum
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xp + off), "r"((uint32_t)nb)
                      : "memory");
       }
-      if (a.flags & PCT_LINEAR_RESIDUAL) {
+      if (a.flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE)) {
         for (int r = lane; r < tile_rows; r += 32)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
                            a.residual + (size_t)(m0 + r) * a.N + n0),
@@ -686,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_pair_kernel(const L
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xp + off), "r"((uint32_t)nb)
                      : "memory");
       }
-      if (a.flags & PCT_LINEAR_RESIDUAL) {
+      if (a.flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE)) {
         for (int r = lane; r < tile_rows; r += 32)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
                            a.residual + (size_t)(m0 + r) * a.N + n0),
@@ -1056,11 +1065,13 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
   if ((ln_mean == nullptr) != (ln_rstd == nullptr)) return PCT_MSDA_E_NULL_POINTER;
   if ((pre_norm || ln_mean) && !(flags & PCT_LINEAR_LAYERNORM)) return PCT_MSDA_E_UNSUPPORTED;
   if (misaligned(pre_norm)) return PCT_MSDA_E_MISALIGNED;
-  if ((flags & PCT_LINEAR_RESIDUAL) && !residual) return PCT_MSDA_E_NULL_POINTER;
+  if ((flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE)) && !residual) return PCT_MSDA_E_NULL_POINTER;
   if ((flags & PCT_LINEAR_LAYERNORM) && (!ln_gamma || !ln_beta)) return PCT_MSDA_E_NULL_POINTER;
   if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
   if ((flags & PCT_LINEAR_LAYERNORM) && out_features > kBlockN) return PCT_MSDA_E_UNSUPPORTED;
-  if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM))
+  if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM | PCT_LINEAR_GATE))
+    return PCT_MSDA_E_UNSUPPORTED;
+  if ((flags & PCT_LINEAR_GATE) && (flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM)))
     return PCT_MSDA_E_UNSUPPORTED;
   // 16-byte accesses: x, packed W, residual, y, pre_norm; bias / gamma / beta are read as scalars
   if (misaligned(x) || misaligned(w_packed) || misaligned(y) || misaligned(residual))

@@ -89,9 +89,7 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
 
     def forward_ffn(self, src):
         if self._fusable(self.dropout2, self.dropout3) and self.activation is F.relu:
-            hidden = linear_tc.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
-            return linear_tc.linear_residual_layernorm(hidden, self.linear2.weight, self.linear2.bias,
-                                                       src, self.norm2)
+            return linear_tc.ffn_block(src, self.linear1, self.linear2, self.norm2)
         hidden = self.dropout2(self.activation(self.linear1(src)))
         return self.norm2(src + self.dropout3(self.linear2(hidden)))
 

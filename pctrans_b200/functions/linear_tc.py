@@ -136,6 +136,58 @@ def _wgrad(g, x2, want_bias):
     return _cabi.linear_wgrad(g, x2), None
 
 
+class FFNFunction(Function):
+    """y = LayerNorm(src + linear2(relu(linear1(src)))) -- the encoder layer's FFN block
+    (PD/msdeformattn.py:107-120) as three kernels forward (GEMM+ReLU, GEMM+residual+LayerNorm) and
+    five backward: aten's LayerNorm backward, two weight-gradient GEMMs (bias gradients included)
+    and two input-gradient GEMMs whose epilogues carry the ReLU mask and the residual branch."""
+
+    @staticmethod
+    def forward(ctx, src, w1, b1, w2, b2, ln_weight, ln_bias, eps):
+        c, f = w1.shape[1], w1.shape[0]
+        x2 = src.reshape(-1, c).contiguous()
+        h = _cabi.linear_forward(x2, packed_weight(w1), f, b1.detach(), relu=True)
+        y, pre, mean, rstd = _cabi.linear_forward(
+            h, packed_weight(w2), c, b2.detach(), x2, ln_weight.detach(), ln_bias.detach(), eps,
+            save_for_backward=True)
+        ctx.src_shape = src.shape
+        ctx.save_for_backward(x2, w1, w2, h, pre, mean, rstd, ln_weight, ln_bias)
+        return y.view(src.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        x2, w1, w2, h, pre, mean, rstd, ln_weight, ln_bias = ctx.saved_tensors
+        c, f = w1.shape[1], w1.shape[0]
+        gy = grad_y.reshape(-1, c).contiguous()
+        g, g_lnw, g_lnb = torch.ops.aten.native_layer_norm_backward(
+            gy, pre, [c], mean, rstd, ln_weight, ln_bias, [True, True, True])
+        gw2, gb2 = _wgrad(g, h, True)
+        # d(hidden) = (g @ W2) masked by the ReLU, straight out of the GEMM's epilogue
+        gh = _cabi.linear_forward(g, packed_weight(w2, transposed=True), f, gate=h)
+        gw1, gb1 = _wgrad(gh, x2, True)
+        # d(src) = gh @ W1 + g (the residual branch), the add fused as well
+        gx = _cabi.linear_forward(gh, packed_weight(w1, transposed=True), c, residual=g)
+        return gx.view(ctx.src_shape), gw1, gb1, gw2, gb2, g_lnw, g_lnb, None
+
+
+def ffn_block(src, linear1, linear2, norm):
+    """``norm(src + linear2(relu(linear1(src))))`` with no dropout in between; picks the fused
+    autograd Function, the fused inference kernels or the plain composition."""
+    ok = (eligible(src, linear1.weight) and eligible(src, linear2.weight)
+          and linear1.bias is not None and linear2.bias is not None and norm.elementwise_affine
+          and norm.bias is not None and linear2.weight.shape[0] <= 256
+          and tuple(norm.normalized_shape) == (linear2.weight.shape[0],))
+    needs_grad = torch.is_grad_enabled() and any(
+        t.requires_grad for t in (src, linear1.weight, linear1.bias, linear2.weight, linear2.bias,
+                                  norm.weight, norm.bias))
+    if ok and needs_grad:
+        return FFNFunction.apply(src, linear1.weight, linear1.bias, linear2.weight, linear2.bias,
+                                 norm.weight, norm.bias, norm.eps)
+    hidden = linear(src, linear1.weight, linear1.bias, relu=True)
+    return linear_residual_layernorm(hidden, linear2.weight, linear2.bias, src, norm)
+
+
 def linear(x, weight, bias=None, residual=None, relu: bool = False):
     """``[relu](F.linear(x, weight, bias) [+ residual])`` -- on the tensor cores when eligible."""
     if eligible(x, weight):

@@ -242,6 +242,43 @@ def test_encoder_inference_replays_from_a_cuda_graph():
     assert not torch.equal(captured, eager)
 
 
+def test_gated_epilogue_is_relu_backward():
+    from pctrans_b200 import _cabi
+    x, w, b, _ = _case(1000, 256, 1024, seed=7)
+    gate = torch.randn(1000, 1024).cuda()
+    y = _cabi.linear_forward(x, _cabi.linear_pack_weight(w), 1024, b, gate=gate)
+    ref = (x.double() @ w.double().t() + b.double()) * (gate > 0)
+    assert _rel(y, ref) < 1e-5
+    assert bool((y[gate <= 0] == 0).all())
+
+
+def test_ffn_block_autograd_matches_fp64():
+    """norm(src + linear2(relu(linear1(src)))) as FFNFunction: output and all seven gradients."""
+    from pctrans_b200.functions import linear_tc
+    torch.manual_seed(8)
+    lin1, lin2, norm = torch.nn.Linear(256, 1024).cuda(), torch.nn.Linear(1024, 256).cuda(), torch.nn.LayerNorm(256).cuda()
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.normal_()
+    src = torch.randn(3, 700, 256).cuda().requires_grad_(True)
+    gy = torch.randn(3, 700, 256).cuda()
+    y = linear_tc.ffn_block(src, lin1, lin2, norm)
+    assert type(y.grad_fn).__name__ == "FFNFunctionBackward"
+    y.backward(gy)
+    ours = [src.grad] + [p.grad for p in (lin1.weight, lin1.bias, lin2.weight, lin2.bias, norm.weight, norm.bias)]
+    d = [t.detach().double().clone().requires_grad_(True)
+         for t in (src, lin1.weight, lin1.bias, lin2.weight, lin2.bias, norm.weight, norm.bias)]
+    # ReLU's gradient is discontinuous at 0: a pre-activation within fp32 rounding of 0 (a handful
+    # of the 2.1 M here) may get the other sign in fp64, so the reference uses OUR activation mask
+    with torch.no_grad():
+        mask = (linear_tc.linear(src.detach(), lin1.weight, lin1.bias, relu=True) > 0).double()
+    yr = F.layer_norm(d[0] + F.linear(F.linear(d[0], d[1], d[2]) * mask, d[3], d[4]), (256,), d[5], d[6], norm.eps)
+    yr.backward(gy.double())
+    assert _rel(y.detach(), yr.detach()) < 1e-5
+    for a_, r_ in zip(ours, d):
+        assert _rel(a_, r_.grad) < 1e-4
+
+
 def test_packed_weight_cache_follows_in_place_updates():
     from pctrans_b200.functions import linear_tc
     lin = torch.nn.Linear(64, 32).cuda()
