@@ -53,6 +53,13 @@ namespace pct {
 #ifndef PCT_BWD_FUSED_THREADS
 #define PCT_BWD_FUSED_THREADS 640
 #endif
+// samples per branch-free block of the tap loops (tuning: 1 = test every sample)
+#ifndef PCT_TAP_BLOCK
+#define PCT_TAP_BLOCK 4
+#endif
+#ifndef PCT_TAP_BLOCK_BWD
+#define PCT_TAP_BLOCK_BWD 4
+#endif
 constexpr int kBwdFusedThreads = PCT_BWD_FUSED_THREADS;  // fused backward carries more state
 constexpr int kVecThreads = PCT_FWD_THREADS;     // forward: one persistent 32-warp CTA per SM
 constexpr int kBwdVecThreads = PCT_BWD_THREADS;  // backward needs ~80 registers per thread
@@ -392,7 +399,12 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     const long long pair = ((long long)b * Lq + (qvalid ? q : Lq - 1)) * M + m;
     const float2* lp = reinterpret_cast<const float2*>(loc) + pair * LP;
     const float* ap = attn + pair * LP;
-    const T* vimg = value + ((long long)b * S * M + m) * D + sub * VE;
+    // The lane's image base as an opaque 64-bit register pair: a corner address is then one
+    // IMAD.WIDE (base + 32-bit element offset) instead of a sign-extended 64-bit add + LEA pair.
+    unsigned long long vbase = reinterpret_cast<unsigned long long>(
+        value + ((long long)b * S * M + m) * D + sub * VE);
+    asm volatile("" : "+l"(vbase));
+    const T* vimg = reinterpret_cast<const T*>(vbase);
 
     float acc[VE];
 #pragma unroll
@@ -452,27 +464,40 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         w10 = tp.v10 ? tp.ly * hx * a : 0.f;
         w11 = tp.v11 ? tp.ly * tp.lx * a : 0.f;
       }
+      // one sample of the round: lane j of every pair broadcasts its taps, all lanes gather
+      auto tap = [&](const int j) {
+        const int o = __shfl_sync(0xffffffffu, off, j, LPP);
+        const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
+        const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
+        const float b00 = __shfl_sync(0xffffffffu, w00, j, LPP);
+        const float b01 = __shfl_sync(0xffffffffu, w01, j, LPP);
+        const float b10 = __shfl_sync(0xffffffffu, w10, j, LPP);
+        const float b11 = __shfl_sync(0xffffffffu, w11, j, LPP);
+        PCT_CHECK_TAP(o, ox, oy, (m * D + sub * VE), VE, (long long)S * MD);
+        // 32-bit corner offsets first: each address is then ONE wide multiply-add off the base
+        const int o01 = o + ox, o10 = o + oy, o11 = o10 + ox;
+        float v00[VE], v01[VE], v10[VE], v11[VE];
+        CV::load(vimg + o, v00);
+        CV::load(vimg + o01, v01);
+        CV::load(vimg + o10, v10);
+        CV::load(vimg + o11, v11);
 #pragma unroll
-      for (int j = 0; j < LPP; ++j) {
-        if (s0 + j < LP) {  // warp-uniform
-          const int o = __shfl_sync(0xffffffffu, off, j, LPP);
-          const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
-          const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
-          const float b00 = __shfl_sync(0xffffffffu, w00, j, LPP);
-          const float b01 = __shfl_sync(0xffffffffu, w01, j, LPP);
-          const float b10 = __shfl_sync(0xffffffffu, w10, j, LPP);
-          const float b11 = __shfl_sync(0xffffffffu, w11, j, LPP);
-          PCT_CHECK_TAP(o, ox, oy, (m * D + sub * VE), VE, (long long)S * MD);
-          const T* p00 = vimg + o;
-          const T* p10 = p00 + oy;
-          float v00[VE], v01[VE], v10[VE], v11[VE];
-          CV::load(p00, v00);
-          CV::load(p00 + ox, v01);
-          CV::load(p10, v10);
-          CV::load(p10 + ox, v11);
+        for (int i = 0; i < VE; ++i)
+          acc[i] = fmaf(b00, v00[i], fmaf(b01, v01[i], fmaf(b10, v10[i], fmaf(b11, v11[i], acc[i]))));
+      };
+      // Samples are taken in blocks of kBlk with ONE warp-uniform test per block: inside a block
+      // there are no branches, so the row loads of neighbouring samples are scheduled together
+      // (the kernel is partly latency-bound); only a ragged tail is tested per sample.
+      constexpr int kBlk = LPP < PCT_TAP_BLOCK ? LPP : PCT_TAP_BLOCK;
 #pragma unroll
-          for (int i = 0; i < VE; ++i)
-            acc[i] = fmaf(b00, v00[i], fmaf(b01, v01[i], fmaf(b10, v10[i], fmaf(b11, v11[i], acc[i]))));
+      for (int j0 = 0; j0 < LPP; j0 += kBlk) {
+        if (s0 + j0 + kBlk <= LP) {
+#pragma unroll
+          for (int j = 0; j < kBlk; ++j) tap(j0 + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kBlk; ++j)
+            if (s0 + j0 + j < LP) tap(j0 + j);
         }
       }
     }
@@ -533,8 +558,12 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     const float2* lp = reinterpret_cast<const float2*>(loc) + pair * LP;
     const float* ap = attn + pair * LP;
     const long long img_off = ((long long)b * S * M + m) * D + sub * VE;
-    const T* vimg = value + img_off;
-    ACC* gimg = gacc + img_off;
+    // opaque 64-bit bases: a corner address is one IMAD.WIDE off the base (see the forward)
+    unsigned long long vbase = reinterpret_cast<unsigned long long>(value + img_off);
+    unsigned long long gbase = reinterpret_cast<unsigned long long>(gacc + img_off);
+    asm volatile("" : "+l"(vbase), "+l"(gbase));
+    const T* vimg = reinterpret_cast<const T*>(vbase);
+    ACC* gimg = reinterpret_cast<ACC*>(gbase);
 
     float go[VE];
     CV::load_stream(grad_out + pair * D + sub * VE, go);
@@ -665,62 +694,71 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         }
       }
       float D00 = 0.f, D01 = 0.f, D10 = 0.f, D11 = 0.f;   // full dot products of MY sample
-#pragma unroll
-      for (int j = 0; j < LPP; ++j) {
-        if (s0 + j < LP) {  // warp-uniform
-          const int o = __shfl_sync(0xffffffffu, off, j, LPP);
-          const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
-          const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
-          const float b00 = __shfl_sync(0xffffffffu, rw0, j, LPP);
-          const float b01 = __shfl_sync(0xffffffffu, rw1, j, LPP);
-          const float b10 = __shfl_sync(0xffffffffu, rw2, j, LPP);
-          const float b11 = __shfl_sync(0xffffffffu, rw3, j, LPP);
-          PCT_CHECK_TAP(o, ox, oy, (m * D + sub * VE), VE, (long long)S * MD);
-          const T* p00 = vimg + o;
-          const T* p10 = p00 + oy;
-          float v00[VE], v01[VE], v10[VE], v11[VE];
-          CV::load(p00, v00);
-          CV::load(p00 + ox, v01);
-          CV::load(p10, v10);
-          CV::load(p10 + ox, v11);
-          // grad_value taps: w_k * attn * grad_out  (cuh:118,130,139,148,157)
-          ACC* g00 = gimg + o;
-          ACC* g10 = g00 + oy;
-          if (kDet) {
-            unsigned long long* r00 = reinterpret_cast<unsigned long long*>(grow + o);
-            unsigned long long* r10 = r00 + oy;
-#pragma unroll
-            for (int i = 0; i < VE; ++i) {
-              if (b00 != 0.f) atomicAdd(r00 + i * LPP, (unsigned long long)__float2ll_rn(b00 * gs[i]));
-              if (b01 != 0.f) atomicAdd(r00 + ox + i * LPP, (unsigned long long)__float2ll_rn(b01 * gs[i]));
-              if (b10 != 0.f) atomicAdd(r10 + i * LPP, (unsigned long long)__float2ll_rn(b10 * gs[i]));
-              if (b11 != 0.f) atomicAdd(r10 + ox + i * LPP, (unsigned long long)__float2ll_rn(b11 * gs[i]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < VE; i += 4) {
-              if (b00 != 0.f) red_add_v4(g00 + i, b00 * go[i], b00 * go[i + 1], b00 * go[i + 2], b00 * go[i + 3]);
-              if (b01 != 0.f) red_add_v4(g00 + ox + i, b01 * go[i], b01 * go[i + 1], b01 * go[i + 2], b01 * go[i + 3]);
-              if (b10 != 0.f) red_add_v4(g10 + i, b10 * go[i], b10 * go[i + 1], b10 * go[i + 2], b10 * go[i + 3]);
-              if (b11 != 0.f) red_add_v4(g10 + ox + i, b11 * go[i], b11 * go[i + 1], b11 * go[i + 2], b11 * go[i + 3]);
-            }
-          }
-          float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+      // one sample of the round: lane j of every pair broadcasts its taps; all lanes gather the
+      // four rows, scatter their grad_value share and reduce the four dot products
+      auto tap = [&](const int j) {
+        const int o = __shfl_sync(0xffffffffu, off, j, LPP);
+        const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
+        const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
+        const float b00 = __shfl_sync(0xffffffffu, rw0, j, LPP);
+        const float b01 = __shfl_sync(0xffffffffu, rw1, j, LPP);
+        const float b10 = __shfl_sync(0xffffffffu, rw2, j, LPP);
+        const float b11 = __shfl_sync(0xffffffffu, rw3, j, LPP);
+        PCT_CHECK_TAP(o, ox, oy, (m * D + sub * VE), VE, (long long)S * MD);
+        // 32-bit corner offsets first: each address is then ONE wide multiply-add off the base
+        const int o01 = o + ox, o10 = o + oy, o11 = o10 + ox;
+        float v00[VE], v01[VE], v10[VE], v11[VE];
+        CV::load(vimg + o, v00);
+        CV::load(vimg + o01, v01);
+        CV::load(vimg + o10, v10);
+        CV::load(vimg + o11, v11);
+        // grad_value taps: w_k * attn * grad_out  (cuh:118,130,139,148,157)
+        if (kDet) {
+          unsigned long long* r = reinterpret_cast<unsigned long long*>(grow);
 #pragma unroll
           for (int i = 0; i < VE; ++i) {
-            d00 = fmaf(go[i], v00[i], d00);
-            d01 = fmaf(go[i], v01[i], d01);
-            d10 = fmaf(go[i], v10[i], d10);
-            d11 = fmaf(go[i], v11[i], d11);
+            if (b00 != 0.f) atomicAdd(r + o + i * LPP, (unsigned long long)__float2ll_rn(b00 * gs[i]));
+            if (b01 != 0.f) atomicAdd(r + o01 + i * LPP, (unsigned long long)__float2ll_rn(b01 * gs[i]));
+            if (b10 != 0.f) atomicAdd(r + o10 + i * LPP, (unsigned long long)__float2ll_rn(b10 * gs[i]));
+            if (b11 != 0.f) atomicAdd(r + o11 + i * LPP, (unsigned long long)__float2ll_rn(b11 * gs[i]));
           }
+        } else {
 #pragma unroll
-          for (int w = LPP / 2; w > 0; w >>= 1) {
-            d00 += __shfl_xor_sync(0xffffffffu, d00, w);
-            d01 += __shfl_xor_sync(0xffffffffu, d01, w);
-            d10 += __shfl_xor_sync(0xffffffffu, d10, w);
-            d11 += __shfl_xor_sync(0xffffffffu, d11, w);
+          for (int i = 0; i < VE; i += 4) {
+            if (b00 != 0.f) red_add_v4(gimg + o + i, b00 * go[i], b00 * go[i + 1], b00 * go[i + 2], b00 * go[i + 3]);
+            if (b01 != 0.f) red_add_v4(gimg + o01 + i, b01 * go[i], b01 * go[i + 1], b01 * go[i + 2], b01 * go[i + 3]);
+            if (b10 != 0.f) red_add_v4(gimg + o10 + i, b10 * go[i], b10 * go[i + 1], b10 * go[i + 2], b10 * go[i + 3]);
+            if (b11 != 0.f) red_add_v4(gimg + o11 + i, b11 * go[i], b11 * go[i + 1], b11 * go[i + 2], b11 * go[i + 3]);
           }
-          if (sub == j) { D00 = d00; D01 = d01; D10 = d10; D11 = d11; }
+        }
+        float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VE; ++i) {
+          d00 = fmaf(go[i], v00[i], d00);
+          d01 = fmaf(go[i], v01[i], d01);
+          d10 = fmaf(go[i], v10[i], d10);
+          d11 = fmaf(go[i], v11[i], d11);
+        }
+#pragma unroll
+        for (int w = LPP / 2; w > 0; w >>= 1) {
+          d00 += __shfl_xor_sync(0xffffffffu, d00, w);
+          d01 += __shfl_xor_sync(0xffffffffu, d01, w);
+          d10 += __shfl_xor_sync(0xffffffffu, d10, w);
+          d11 += __shfl_xor_sync(0xffffffffu, d11, w);
+        }
+        if (sub == j) { D00 = d00; D01 = d01; D10 = d10; D11 = d11; }
+      };
+      // blocks of kBlk samples behind one warp-uniform test (see the forward kernel)
+      constexpr int kBlk = LPP < PCT_TAP_BLOCK_BWD ? LPP : PCT_TAP_BLOCK_BWD;
+#pragma unroll
+      for (int j0 = 0; j0 < LPP; j0 += kBlk) {
+        if (s0 + j0 + kBlk <= LP) {
+#pragma unroll
+          for (int j = 0; j < kBlk; ++j) tap(j0 + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kBlk; ++j)
+            if (s0 + j0 + j < LP) tap(j0 + j);
         }
       }
       if (s < LP && qvalid) {

@@ -8,7 +8,7 @@ for spec in "$@"; do
   name=${spec%%:*}; defs=${spec#*:}
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared \
        --cudart shared -ccbin /usr/bin/g++ $defs \
-       -o scripts/_build/libpctrans_msda_$name.so pctrans_b200/csrc/msda_capi.cu &
+       -o scripts/_build/libpctrans_msda_$name.so pctrans_b200/csrc/msda_capi.cu pctrans_b200/csrc/msda_host.cu pctrans_b200/csrc/linear_tc.cu &
 done
 wait
 ls scripts/_build/*.so
