@@ -57,6 +57,9 @@ namespace pct {
 #ifndef PCT_TAP_BLOCK
 #define PCT_TAP_BLOCK 4
 #endif
+#ifndef PCT_PACK_TAPS
+#define PCT_PACK_TAPS 1
+#endif
 #ifndef PCT_TAP_BLOCK_BWD
 #define PCT_TAP_BLOCK_BWD 4
 #endif
@@ -464,11 +467,25 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         w10 = tp.v10 ? tp.ly * hx * a : 0.f;
         w11 = tp.v11 ? tp.ly * tp.lx * a : 0.f;
       }
-      // one sample of the round: lane j of every pair broadcasts its taps, all lanes gather
-      auto tap = [&](const int j) {
+      // one sample of the round: lane j of every pair broadcasts its taps, all lanes gather.
+      // Shuffles cost one L1 data-pipe wavefront each (ncu: 31 % of this kernel's wavefronts are
+      // shuffles, and the pipe is what bounds it), so the three corner offsets travel as ONE word:
+      // off is a multiple of M*D (D >= 4), its two low bits say whether x+1 / y+1 is another pixel;
+      // the x step is M*D and the y step is the level's row pitch, read once per block.
+#if PCT_PACK_TAPS
+      const int word = off | (dx != 0 ? 1 : 0) | (dy != 0 ? 2 : 0);
+#endif
+      auto tap = [&](const int j, const int pitch) {
+#if PCT_PACK_TAPS
+        const int wd = __shfl_sync(0xffffffffu, word, j, LPP);
+        const int o = wd & ~3;
+        const int ox = (wd & 1) ? MD : 0;
+        const int oy = (wd & 2) ? pitch : 0;
+#else
         const int o = __shfl_sync(0xffffffffu, off, j, LPP);
         const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
         const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
+#endif
         const float b00 = __shfl_sync(0xffffffffu, w00, j, LPP);
         const float b01 = __shfl_sync(0xffffffffu, w01, j, LPP);
         const float b10 = __shfl_sync(0xffffffffu, w10, j, LPP);
@@ -492,12 +509,18 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 #pragma unroll
       for (int j0 = 0; j0 < LPP; j0 += kBlk) {
         if (s0 + j0 + kBlk <= LP) {
+          if (P % kBlk == 0) {   // the block lies inside one level (s0 + j0 is a multiple of kBlk)
+            const int pitch = PCT_PACK_TAPS ? s_tab[s0 + j0].y * MD : 0;
 #pragma unroll
-          for (int j = 0; j < kBlk; ++j) tap(j0 + j);
+            for (int j = 0; j < kBlk; ++j) tap(j0 + j, pitch);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlk; ++j) tap(j0 + j, PCT_PACK_TAPS ? s_tab[s0 + j0 + j].y * MD : 0);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < kBlk; ++j)
-            if (s0 + j0 + j < LP) tap(j0 + j);
+            if (s0 + j0 + j < LP) tap(j0 + j, PCT_PACK_TAPS ? s_tab[s0 + j0 + j].y * MD : 0);
         }
       }
     }
