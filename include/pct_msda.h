@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define PCT_MSDA_ABI_VERSION 3
+#define PCT_MSDA_ABI_VERSION 4
 
 /* value_dtype */
 #define PCT_MSDA_F32 0
@@ -75,8 +75,12 @@ extern "C" {
                                             integer reductions; needs pct_msda_backward_workspace_bytes_ex
                                             bytes of workspace; vector-path shapes only, else
                                             PCT_MSDA_E_UNSUPPORTED) */
+#define PCT_MSDA_FLAG_BWD_PER_TAP 0x20u   /* backward: use the per-tap scatter kernel (one L2 reduction per
+                                            bilinear corner) instead of the default cell-binned kernel */
 /* bits 8..15: threads/32 of the persistent CTA; bits 16..19: CTAs per SM; bits 20..24: 1 + static
- * share of the task list in sixteenths (tuning only) */
+ * share of the task list in sixteenths; bits 25..31: cap of the binned backward's chunk size in
+ * units of 8 queries; for the binned backward bits 16..19 are 1 + the cost of opening a cell in its
+ * segment balance (tuning only) */
 
 int pct_msda_abi_version(void);
 
@@ -90,6 +94,15 @@ uint64_t pct_msda_launch_count(void);
  * path.  `backward` selects the gradient kernels. */
 int pct_msda_kernel_family(int channels, int num_levels, int num_point, int value_dtype,
                            int backward);
+
+/* Which gradient kernel pct_msda_backward_ex runs for these dimensions and flags on the current
+ * device (buffers assumed 16-byte aligned): 0 = generic scalar, 1 = per-tap vector scatter,
+ * 2 = cell-binned (grad_value aggregated per bilinear cell on chip before any global reduction;
+ * the default whenever the head dim is 16/32/64/128 channels, L <= 8, L*P <= 64 and the level
+ * maps are small enough for shared memory).  Negative = error code negated. */
+int pct_msda_backward_plan(int batch, int spatial_size, int num_heads, int channels,
+                           int num_levels, int num_query, int num_point, int value_dtype,
+                           unsigned flags);
 
 /* out[b,q,m,:] = sum_{l,p} attn[b,q,m,l,p] * bilinear(value_l[b,:,m,:], loc[b,q,m,l,p]).
  * Replaces ms_deform_attn_cuda_forward (cu:25-85).  The reference's `im2col_step` has no

@@ -17,13 +17,13 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 # PCTRANS_MSDA_LIB selects another build of the SAME C ABI (the bounds-checking debug library in
 # tests); it is not a fallback: a missing file is still an ImportError.
 LIB_PATH = os.environ.get("PCTRANS_MSDA_LIB") or os.path.join(_PKG_DIR, "_build", "libpctrans_msda.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float64: 2}
 
 EXPORTS = (
     "pct_msda_abi_version", "pct_msda_error_string", "pct_msda_launch_count",
-    "pct_msda_kernel_family", "pct_msda_forward", "pct_msda_forward_ex",
+    "pct_msda_kernel_family", "pct_msda_backward_plan", "pct_msda_forward", "pct_msda_forward_ex",
     "pct_msda_backward_workspace_bytes", "pct_msda_backward_workspace_bytes_ex",
     "pct_msda_backward", "pct_msda_backward_ex",
     "pct_msda_fused_forward", "pct_msda_fused_backward",
@@ -37,6 +37,7 @@ E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
 FLAG_BF16_ACCUM = 0x8
 FLAG_DETERMINISTIC = 0x10
+FLAG_BWD_PER_TAP = 0x20
 
 _lib = None
 _lock = threading.Lock()
@@ -72,6 +73,8 @@ def load():
         lib.pct_msda_launch_count.argtypes = []
         lib.pct_msda_kernel_family.restype = i32
         lib.pct_msda_kernel_family.argtypes = [i32] * 5
+        lib.pct_msda_backward_plan.restype = i32
+        lib.pct_msda_backward_plan.argtypes = [i32] * 8 + [u32]
         fwd_args = [vp] * 6 + [i32] * 8 + [vp]
         lib.pct_msda_forward.restype = i32
         lib.pct_msda_forward.argtypes = fwd_args
@@ -122,6 +125,14 @@ def kernel_family(channels: int, num_levels: int, num_point: int, dtype: torch.d
                   backward: bool = False) -> int:
     return int(load().pct_msda_kernel_family(channels, num_levels, num_point, DTYPE_CODES[dtype],
                                              int(backward)))
+
+
+def backward_plan(N, S, M, D, L, Lq, P, dtype: torch.dtype, flags: int = 0) -> int:
+    """0 generic, 1 per-tap vector scatter, 2 cell-binned (needs a current CUDA device)."""
+    rc = int(load().pct_msda_backward_plan(N, S, M, D, L, Lq, P, DTYPE_CODES[dtype], flags))
+    if rc < 0:
+        check(-rc, "pct_msda_backward_plan")
+    return rc
 
 
 def _stream_ptr(device) -> int:

@@ -15,16 +15,30 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libpctrans_msda.so")
-SOURCES = ["msda_capi.cu", "msda_host.cu", "linear_tc.cu"]
-DEPS = ["msda_capi.cu", "msda_host.cu", "linear_tc.cu", "msda_kernels.cuh",
-        os.path.join("..", "..", "include", "pct_msda.h"), os.path.join("..", "..", "include", "pct_linear.h")]
-NVCC_FLAGS = [
+SOURCES = ["msda_capi.cu", "msda_inst_fwd.cu", "msda_inst_bwd.cu", "msda_inst_binned.cu",
+           "msda_host.cu", "linear_tc.cu"]
+HEADERS = ["msda_kernels.cuh", "msda_bwd_binned.cuh", "msda_launch.h",
+           os.path.join("..", "..", "include", "pct_msda.h"),
+           os.path.join("..", "..", "include", "pct_linear.h")]
+DEPS = SOURCES + HEADERS
+# headers a translation unit does NOT include (so editing them does not rebuild it)
+NOT_INCLUDED = {
+    "msda_inst_fwd.cu": ["msda_bwd_binned.cuh", "pct_linear.h"],
+    "msda_inst_bwd.cu": ["msda_bwd_binned.cuh", "pct_linear.h"],
+    "msda_inst_binned.cu": ["pct_linear.h"],
+    "msda_host.cu": ["msda_kernels.cuh", "msda_bwd_binned.cuh", "msda_launch.h", "pct_linear.h"],
+    "linear_tc.cu": ["msda_kernels.cuh", "msda_bwd_binned.cuh", "msda_launch.h"],
+}
+# every translation unit is compiled on its own (in parallel, objects cached by source hash) and
+# linked into one shared library
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-    "--cudart", "shared",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "--cudart", "shared"]
+NVCC_FLAGS = COMPILE_FLAGS + LINK_FLAGS
 
 
 def _nvcc() -> str:
@@ -66,39 +80,98 @@ def needs_build() -> bool:
 DEBUG_LIB_PATH = os.path.join(OUT_DIR, "libpctrans_msda_dbg.so")
 
 
+def _ccbin() -> list:
+    # the image exports CC/CXX wrappers that nvcc must not pick up as host compiler
+    return ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+
+
+def _compile_one(src: str, obj_dir: str, defines: list, force: bool):
+    """Compile one translation unit to an object file; skipped when the object was built from the
+    same bytes (sources + headers + flags).  Returns (object path, compiler output)."""
+    import hashlib
+    h = hashlib.sha256((" ".join(COMPILE_FLAGS + defines)).encode())
+    for d in [src] + [h_ for h_ in HEADERS if os.path.basename(h_) not in NOT_INCLUDED.get(src, [])]:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(f.read())
+    obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+    stamp = obj + ".srchash"
+    log = obj + ".log"
+    try:
+        with open(stamp) as f:
+            if not force and os.path.exists(obj) and f.read().strip() == h.hexdigest():
+                with open(log) as lf:
+                    return obj, lf.read()
+    except OSError:
+        pass
+    cmd = [_nvcc()] + COMPILE_FLAGS + defines + ["-c", "-o", obj, os.path.join(CSRC, src)] + _ccbin()
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    out = " ".join(cmd) + "\n" + proc.stdout
+    if proc.returncode != 0:
+        sys.stderr.write(out)
+        raise RuntimeError(f"nvcc failed on {src} (exit {proc.returncode})")
+    with open(log, "w") as f:
+        f.write(out)
+    with open(stamp, "w") as f:
+        f.write(h.hexdigest())
+    return obj, out
+
+
+def _build(lib_path: str, obj_dir: str, defines: list, force: bool, verbose: bool, log_name: str) -> str:
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(obj_dir, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(lambda s: _compile_one(s, obj_dir, defines, force), SOURCES))
+    cmd = [_nvcc()] + LINK_FLAGS + ["-o", lib_path] + [o for o, _ in results] + _ccbin()
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    text = "".join(out for _, out in results) + " ".join(cmd) + "\n" + proc.stdout
+    with open(os.path.join(OUT_DIR, log_name), "w") as f:
+        f.write(text)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(text)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc link failed (exit {proc.returncode}); see {log_name}")
+    return lib_path
+
+
 def build_library(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
     """Compile the CUDA sources for sm_100a.  Returns the path of the shared library.
     ``debug=True`` builds libpctrans_msda_dbg.so with -DPCT_MSDA_BOUNDS_CHECK (tap addresses
     checked in-kernel; used by tests/test_gpu_bounds.py through PCTRANS_MSDA_LIB)."""
+    os.makedirs(OUT_DIR, exist_ok=True)
     if debug:
-        os.makedirs(OUT_DIR, exist_ok=True)
         if not force and _is_current(DEBUG_LIB_PATH, "debug"):
             return DEBUG_LIB_PATH
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-DPCT_MSDA_BOUNDS_CHECK", "-o", DEBUG_LIB_PATH] + \
-            [os.path.join(CSRC, s) for s in SOURCES] + ["-ccbin", "/usr/bin/g++"]
-        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if proc.returncode != 0:
-            sys.stderr.write(proc.stdout)
-            raise RuntimeError("nvcc failed building the bounds-check library")
+        _build(DEBUG_LIB_PATH, os.path.join(OUT_DIR, "obj_dbg"), ["-DPCT_MSDA_BOUNDS_CHECK"], force,
+               verbose, "build_dbg.log")
         _stamp(DEBUG_LIB_PATH, "debug")
         return DEBUG_LIB_PATH
     if not force and not needs_build():
         return LIB_PATH
-    os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
-    # the image exports CC/CXX wrappers that nvcc must not pick up as host compiler
-    proc = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd,
-                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
-    log_path = os.path.join(OUT_DIR, "build.log")
-    with open(log_path, "w") as f:
-        f.write(" ".join(cmd) + "\n" + proc.stdout)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout)
-    if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed (exit {proc.returncode}); see {log_path}")
+    _build(LIB_PATH, os.path.join(OUT_DIR, "obj"), [], force, verbose, "build.log")
     _stamp(LIB_PATH)
     return LIB_PATH
+
+
+def build_variant(name: str, defines: list, sources=("msda_inst_binned.cu",)) -> str:
+    """Tuning builds: the listed translation units recompiled with extra -D flags and linked with the
+    release objects into _build/variants/libpctrans_msda_<name>.so (select with PCTRANS_MSDA_LIB)."""
+    build_library()
+    vdir = os.path.join(OUT_DIR, "variants")
+    odir = os.path.join(vdir, "obj_" + name)
+    os.makedirs(odir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        if src in sources:
+            objs.append(_compile_one(src, odir, list(defines), False)[0])
+        else:
+            objs.append(os.path.join(OUT_DIR, "obj", os.path.splitext(src)[0] + ".o"))
+    lib = os.path.join(vdir, f"libpctrans_msda_{name}.so")
+    cmd = [_nvcc()] + LINK_FLAGS + ["-o", lib] + objs + _ccbin()
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+        raise RuntimeError("variant link failed")
+    return lib
 
 
 if __name__ == "__main__":

@@ -1,0 +1,619 @@
+// msda_bwd_binned.cuh -- cell-binned backward of MSDeformAttn for sm_100a.
+//
+// Replaces the reference's seven col2im kernels (OPS/src/cuda/ms_deform_im2col_cuda.cuh:306-925)
+// and their scatter of 4 scalar atomics per tap and channel (cuh:124-158).  The arithmetic is the
+// reference's (cuh:93-164); the organisation is not:
+//
+// The per-tap backward (msda_bwd_vec_kernel) sends every bilinear corner of every sample to L2 as
+// its own 128-byte reduction and re-reads the four value rows of every sample: 8 row transfers
+// per sample through the SM's L1 data pipe and 16 L2 reduction sectors per sample, and the L2
+// reduction path (measured ceiling 199 sectors/ns) bounds the kernel.  But the samples of
+// neighbouring queries fall into the SAME bilinear cells -- a 16x16 level receives ~80 samples
+// per cell and (image, head) -- so here grad_value is aggregated per CELL on chip before any
+// global atomic:
+//
+//   task  = (image b, head m, chunk of QC consecutive queries); one persistent CTA per SM pulls
+//           tasks from a global counter.
+//   B1/B2/B3  counting sort of the chunk's QC*L*P samples by bilinear cell (level, y0, x0) in
+//           shared memory: one shared-memory integer atomic per sample (ATOMS.ADD is native for
+//           32-bit integers), a CTA-wide scan, and a 16-byte record {cell|query|level, lw, lh,
+//           attn} per in-range sample.  The chunk's grad_out rows are staged in shared memory
+//           with cp.async meanwhile.
+//   sweep  the sorted records are cut into segments of equal COST (records + cells opened), one
+//           per group of LPP lanes (a lane owns 4 channels).  A group keeps the four corner value
+//           rows of its current cell AND four fp32 accumulator rows in registers; per record it
+//           reads one grad_out row from shared memory, forms the four corner dot products
+//           (-> grad_attn, grad_loc, cuh:160-163) and adds w_k*attn*grad_out into the
+//           accumulators.  Only when the cell changes are the accumulators sent to L2
+//           (red.global.add.v4.f32) and four value rows loaded.
+//           Per-sample cost drops from 8 row transfers + 16 L2 sectors to 1 shared-memory row
+//           read, with 8 row transfers + 16 sectors per CELL.
+//   final  grad_sampling_loc / grad_attn_weight are written coalesced in sample order (the sweep
+//           left them in the records; out-of-range samples get exact zeros as in the reference).
+//
+// Everything is fp32 arithmetic with fp32 accumulation (bf16 values accumulate into the caller's
+// fp32 workspace exactly like the per-tap kernel).  Summation order differs from the reference
+// (as any atomic scatter does); tests hold the result to 1e-4.
+#pragma once
+
+#include "msda_kernels.cuh"
+
+namespace pct {
+
+#ifndef PCT_BIN_THREADS
+#define PCT_BIN_THREADS 768
+#endif
+#ifndef PCT_BIN_CTAS
+#define PCT_BIN_CTAS 1       // resident CTAs per SM (each gets 1/PCT_BIN_CTAS of the shared memory)
+#endif
+constexpr int kBinThreads = PCT_BIN_THREADS;
+constexpr int kBinCtasPerSm = PCT_BIN_CTAS;
+constexpr int kBinMaxLevels = 8;
+constexpr int kBinMaxSamples = 64;    // L*P
+constexpr int kBinMaxQc = 1024;       // queries per chunk: 10 bits of the record word
+constexpr int kBinMaxCells = 65535;   // 16 bits of the record word
+constexpr unsigned kBinNoPos = 0xffffu;
+
+struct __align__(16) BinLevel {   // read as two 16-byte words
+  int cell_base;                // cells of level l: cell_base + (y0+1)*(W+1) + (x0+1), y0 in [-1,H-1]
+  unsigned magic;               // ceil(2^32 / wp1): __umulhi(c, magic) == c / wp1 for c < 2^16
+  int wp1;                      // W + 1
+  int W;
+  int H, start;
+  float Hf, Wf;
+};
+
+struct BinLaunch {
+  int smem_bytes;   // dynamic shared memory of the launch
+  int qc_cap;       // upper limit for the chunk size (0 = whatever fits)
+  int slot;         // g_sched ring slot: [0] task counter, [1] CTA-exit counter
+  int cell_cost;    // cost of opening a cell in units of one record, for the segment balance
+};
+
+// Shared-memory bytes a chunk of one query needs: records + grad_out row + position of each sample.
+__host__ __device__ inline int bin_bytes_per_query(int LP, int row_bytes) {
+  return LP * 16 + row_bytes + LP * 2;
+}
+
+__device__ __forceinline__ float bin_coord(float loc, float size) {
+  // cuh:290-291: `loc * size - 0.5` -- float product (rounded), then the subtraction in double
+  // rounded once to float, which is exactly one fp32 subtraction of the rounded product.
+  return __fsub_rn(__fmul_rn(loc, size), 0.5f);
+}
+
+// transposed xor-shuffle reduction of three values over the LPP lanes of a group (LPP >= 4):
+// returns, in lane sub, the group sum of  a (sub&3 == 0),  y (== 1),  x (== 2),  0 (== 3).
+template <int LPP>
+__device__ __forceinline__ float bin_reduce3(float a, float x, float y, int sub) {
+  const bool b0 = sub & 1, b1 = sub & 2;
+  const float send0 = b0 ? a : y, send1 = b0 ? x : 0.f;
+  float keep0 = b0 ? y : a, keep1 = b0 ? 0.f : x;
+  keep0 += __shfl_xor_sync(0xffffffffu, send0, 1);
+  keep1 += __shfl_xor_sync(0xffffffffu, send1, 1);
+  const float send = b1 ? keep0 : keep1;
+  float k = b1 ? keep1 : keep0;
+  k += __shfl_xor_sync(0xffffffffu, send, 2);
+#pragma unroll
+  for (int w = 4; w < LPP; w <<= 1) k += __shfl_xor_sync(0xffffffffu, k, w);
+  return k;
+}
+
+template <typename T>
+struct BinRow;   // one lane's 4 channels of a staged grad_out row
+template <>
+struct BinRow<float> {
+  static __device__ __forceinline__ void load(const unsigned char* p, float (&g)[4]) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    g[0] = r.x; g[1] = r.y; g[2] = r.z; g[3] = r.w;
+  }
+};
+template <>
+struct BinRow<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const unsigned char* p, float (&g)[4]) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    g[0] = __uint_as_float(r.x << 16);
+    g[1] = __uint_as_float(r.x & 0xffff0000u);
+    g[2] = __uint_as_float(r.y << 16);
+    g[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+};
+
+// ---- packed fp32 pairs (fma.rn.f32x2 = FFMA2 on sm_100a) and raw shared-window accesses ----
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float sum2(u64 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return lo + hi;
+}
+#ifndef PCT_BIN_FMA2
+#define PCT_BIN_FMA2 1
+#endif
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+#if PCT_BIN_FMA2
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+#else
+  float a0, a1, b0, b1, c0, c1;
+  unpack2(a, a0, a1); unpack2(b, b0, b1); unpack2(c, c0, c1);
+  return pack2(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
+#endif
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+#if PCT_BIN_FMA2
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+#else
+  float a0, a1, b0, b1;
+  unpack2(a, a0, a1); unpack2(b, b0, b1);
+  return pack2(a0 * b0, a1 * b1);
+#endif
+}
+__device__ __forceinline__ uint4 lds_v4(unsigned addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint2 lds_v2(unsigned addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// one lane's 4 channels of a value row as two channel pairs; zeros when `keep` is false (the load
+// is predicated off, so nothing waits on it)
+template <typename T>
+struct BinVal;
+template <>
+struct BinVal<float> {
+  static __device__ __forceinline__ void load(const float* p, unsigned keep, u64& v01, u64& v23) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"
+        "@p ld.global.nc.v2.u64 {%0, %1}, [%3];\n\t}"
+        : "=&l"(v01), "=&l"(v23)
+        : "r"(keep), "l"(p));
+  }
+};
+template <>
+struct BinVal<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, unsigned keep, u64& v01, u64& v23) {
+    unsigned x, y;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\t"
+        "@p ld.global.nc.v2.u32 {%0, %1}, [%3];\n\t}"
+        : "=&r"(x), "=&r"(y)
+        : "r"(keep), "l"(p));
+    v01 = pack2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+    v23 = pack2(__uint_as_float(y << 16), __uint_as_float(y & 0xffff0000u));
+  }
+};
+
+// one lane's 4 channels of a staged grad_out row as two channel pairs
+template <typename T>
+struct BinRowS;
+template <>
+struct BinRowS<float> {
+  static __device__ __forceinline__ void load(unsigned addr, u64& g01, u64& g23) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(g01), "=l"(g23) : "r"(addr));
+  }
+};
+template <>
+struct BinRowS<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(unsigned addr, u64& g01, u64& g23) {
+    unsigned x, y;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(addr));
+    g01 = pack2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+    g23 = pack2(__uint_as_float(y << 16), __uint_as_float(y & 0xffff0000u));
+  }
+};
+
+
+#ifdef PCT_MSDA_BOUNDS_CHECK
+#define PCT_BIN_ASSERT(c) do { if (!(c)) __trap(); } while (0)
+#else
+#define PCT_BIN_ASSERT(c) do { } while (0)
+#endif
+
+template <typename T, int LPP>
+__global__ void __launch_bounds__(kBinThreads, kBinCtasPerSm)
+msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                       const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                       const float* __restrict__ attn, const T* __restrict__ grad_out,
+                       float* __restrict__ gacc, float* __restrict__ grad_loc,
+                       float* __restrict__ grad_attn, int N, int S, int M, int L, int Lq, int P,
+                       BinLaunch bl) {
+  constexpr int VE = 4;
+  constexpr int VB = VE * (int)sizeof(T);
+  using CV = ChanVec<T, VB>;
+  constexpr int D = LPP * VE;
+  constexpr int ROWB = D * (int)sizeof(T);     // bytes of one (query, head) grad_out row
+  constexpr int PPR = ROWB / 16;               // 16-byte pieces per row
+  constexpr int G = kBinThreads / LPP;         // lane groups per CTA
+  static_assert(LPP >= 4 && LPP <= 32 && ROWB % 16 == 0, "binned backward: 4..32 lanes of 4 channels");
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ BinLevel s_lvl[kBinMaxLevels];
+  __shared__ unsigned char s_slvl[kBinMaxSamples];   // level of sample s
+  __shared__ unsigned int s_wsum[32];
+  __shared__ unsigned short s_bound[G + 1];          // first record of every group's segment
+  __shared__ int s_nc, s_task;
+  __shared__ unsigned int s_total;                   // (non-empty cells << 16) | records
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARPS = kBinThreads / 32;
+  const int LP = L * P;
+  const int MD = M * D;
+
+  if (tid == 0) {
+    int cb = 0;
+    for (int l = 0; l < L; ++l) {
+      const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+      BinLevel lv;
+      lv.H = H; lv.W = W; lv.start = (int)lsi[l]; lv.cell_base = cb;
+      lv.wp1 = W + 1;
+      lv.magic = (unsigned)((0x100000000ull + (unsigned long long)W) / (unsigned long long)(W + 1));
+      lv.Hf = (float)H; lv.Wf = (float)W;
+      s_lvl[l] = lv;
+      cb += (H > 0 && W > 0) ? (H + 1) * (W + 1) : 0;
+    }
+    s_nc = cb;
+  }
+  for (int s = tid; s < LP; s += kBinThreads) s_slvl[s] = (unsigned char)(s / P);
+  __syncthreads();
+
+  // ---- chunk geometry (identical in every CTA: a function of the shapes only) ----
+  const int NC = s_nc;
+  const int cnt_words = (NC + 1 + 3) & ~3;
+  const int per_q = bin_bytes_per_query(LP, ROWB);
+  int qc_max = (bl.smem_bytes - cnt_words * 4 - 16) / per_q;
+  if (qc_max > kBinMaxQc) qc_max = kBinMaxQc;
+  if (qc_max > 65528 / LP) qc_max = 65528 / LP;   // 16-bit record positions, 0xffff = none
+  if (bl.qc_cap > 0 && qc_max > bl.qc_cap) qc_max = bl.qc_cap;
+  qc_max &= ~7;
+  if (qc_max < 8 || NC > kBinMaxCells) __trap();   // the launcher's bound guarantees the fit
+  const int nchunks = (Lq + qc_max - 1) / qc_max;
+  const int QC = (((Lq + nchunks - 1) / nchunks) + 7) & ~7;   // balanced chunks, <= qc_max
+  const int n_tasks = N * nchunks * M;
+
+  uint4* const rec = reinterpret_cast<uint4*>(smem);
+  unsigned char* const go_s = smem + (size_t)QC * LP * 16;
+  unsigned int* const cnt = reinterpret_cast<unsigned int*>(go_s + (size_t)QC * ROWB);
+  unsigned short* const posarr = reinterpret_cast<unsigned short*>(cnt + cnt_words);
+
+  const int grp = tid / LPP, sub = tid % LPP;
+  unsigned int* const ctr = g_sched + 2 * bl.slot;
+  const unsigned kappa = (unsigned)bl.cell_cost;
+
+  // one sample of the binning passes: cell index (or -1 when the reference skips it), fractions
+  auto locate = [&](float2 xy, int s, float& lw, float& lh, int& lvl) -> int {
+    lvl = s_slvl[s];
+    const int4 A = *reinterpret_cast<const int4*>(&s_lvl[lvl]);          // cell_base, magic, wp1, W
+    const float2 F = *reinterpret_cast<const float2*>(&s_lvl[lvl].Hf);   // Hf, Wf
+    const float y = bin_coord(xy.y, F.x), x = bin_coord(xy.x, F.y);
+    if (!(y > -1.f && x > -1.f && y < F.x && x < F.y)) return -1;       // cuh:293 (NaN: outside)
+    const float fy = floorf(y), fx = floorf(x);
+    lh = y - fy; lw = x - fx;
+    return A.x + ((int)fy + 1) * A.z + (int)fx + 1;
+  };
+
+  for (;;) {
+    if (tid == 0) s_task = (int)atomicAdd(ctr, 1u);
+    __syncthreads();
+    const int t = s_task;
+    if (t >= n_tasks) break;
+    const int m = t % M;
+    const int tc = t / M;
+    const int c = tc % nchunks, b = tc / nchunks;
+    const int q0 = c * QC;
+    const int nq = min(QC, Lq - q0);
+    const int ntaps = nq * LP;
+    // global index of sample (q0, m, 0); a query step is M*LP samples
+    const long long samp0 = ((long long)((long long)b * Lq + q0) * M + m) * LP;
+    const long long qstep = (long long)M * LP;
+    const float2* const loc2 = reinterpret_cast<const float2*>(loc) + samp0;
+    const float* const attn1 = attn + samp0;
+
+    // ---- P0: clear the cell counters, start staging the chunk's grad_out rows ----
+    for (int i = tid; i < cnt_words; i += kBinThreads) cnt[i] = 0u;
+    {
+      const T* gsrc = grad_out + ((long long)((long long)b * Lq + q0) * M + m) * D;
+      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(go_s);
+      for (int j = tid; j < nq * PPR; j += kBinThreads) {
+        const int row = j / PPR, part = j - row * PPR;
+        const T* src = gsrc + (long long)row * MD + part * (16 / (int)sizeof(T));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (unsigned)j * 16u), "l"(src)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- B1: count the samples of every cell (the loads of a batch first, then the atomics) ----
+    constexpr int UB = 4;
+    const int dq = kBinThreads / LP, ds = kBinThreads - dq * LP;
+    {
+      int ql = tid / LP, s = tid - ql * LP;
+      for (int k0 = tid; k0 < ntaps; k0 += UB * kBinThreads) {
+        float2 xy[UB];
+        int ss[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          ss[u] = s;
+          xy[u] = (k0 + u * kBinThreads < ntaps) ? __ldg(loc2 + ql * qstep + s)
+                                                : make_float2(-4.f, -4.f);   // outside every map
+          ql += dq; s += ds;
+          if (s >= LP) { s -= LP; ++ql; }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          float lw, lh;
+          int lvl;
+          const int cell = locate(xy[u], ss[u], lw, lh, lvl);
+          if (cell >= 0) {
+            PCT_BIN_ASSERT(cell < NC);
+            atomicAdd(cnt + cell, 1u);
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- B2: exclusive scan of (non-empty << 16 | count) over the cells, in place ----
+    {
+      const int per = (NC + kBinThreads - 1) / kBinThreads;
+      const int i0 = min(tid * per, NC), i1 = min(i0 + per, NC);
+      unsigned sum = 0;
+      for (int i = i0; i < i1; ++i) {
+        const unsigned cv = cnt[i];
+        sum += cv + (cv ? 0x10000u : 0u);
+      }
+      unsigned incl = sum;
+#pragma unroll
+      for (int w = 1; w < 32; w <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, w);
+        if (lane >= w) incl += o;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        const unsigned v = lane < NWARPS ? s_wsum[lane] : 0u;
+        unsigned inc2 = v;
+#pragma unroll
+        for (int w = 1; w < 32; w <<= 1) {
+          const unsigned o = __shfl_up_sync(0xffffffffu, inc2, w);
+          if (lane >= w) inc2 += o;
+        }
+        if (lane < NWARPS) s_wsum[lane] = inc2 - v;   // exclusive prefix of the warp totals
+        if (lane == 31) { s_total = inc2; cnt[NC] = inc2; }
+      }
+      __syncthreads();
+      unsigned base = s_wsum[warp] + incl - sum;
+      for (int i = i0; i < i1; ++i) {
+        const unsigned cv = cnt[i];
+        cnt[i] = base;
+        base += cv + (cv ? 0x10000u : 0u);
+      }
+    }
+    __syncthreads();
+
+    // ---- segment bounds: equal cost per lane group, cost = records + kappa * cells opened ----
+    if (tid <= G) {
+      const unsigned tot = s_total;
+      const unsigned r_tot = tot & 0xffffu, e_tot = tot >> 16;
+      const unsigned target =
+          (unsigned)(((unsigned long long)(r_tot + kappa * e_tot) * (unsigned)tid) / (unsigned)G);
+      int lo = 0, hi = NC;     // largest cell index whose cost-before is <= target
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        const unsigned pv = cnt[mid];
+        if ((pv & 0xffffu) + kappa * (pv >> 16) <= target) lo = mid; else hi = mid - 1;
+      }
+      unsigned bound = r_tot;
+      if (lo < NC) {
+        const unsigned pv = cnt[lo], nx = cnt[lo + 1];
+        const unsigned r0 = pv & 0xffffu, count = (nx & 0xffffu) - r0;
+        const unsigned rem = target - (r0 + kappa * (pv >> 16));
+        const unsigned off = rem > kappa ? rem - kappa : 0u;
+        bound = r0 + (off < count ? off : count);
+      }
+      s_bound[tid] = (unsigned short)bound;
+    }
+    __syncthreads();
+
+    // ---- B3: write the records into their bins ----
+    {
+      int ql = tid / LP, s = tid - ql * LP;
+      for (int k0 = tid; k0 < ntaps; k0 += UB * kBinThreads) {
+        float2 xy[UB];
+        float aw[UB];
+        int ss[UB], qq[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          ss[u] = s; qq[u] = ql;
+          const bool ok = k0 + u * kBinThreads < ntaps;
+          xy[u] = ok ? __ldg(loc2 + ql * qstep + s) : make_float2(-4.f, -4.f);
+          aw[u] = ok ? __ldg(attn1 + ql * qstep + s) : 0.f;
+          ql += dq; s += ds;
+          if (s >= LP) { s -= LP; ++ql; }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int k = k0 + u * kBinThreads;
+          if (k < ntaps) {
+            float lw = 0.f, lh = 0.f;
+            int lvl;
+            const int cell = locate(xy[u], ss[u], lw, lh, lvl);
+            unsigned pos = kBinNoPos;
+            if (cell >= 0) {
+              pos = atomicAdd(cnt + cell, 1u) & 0xffffu;
+              PCT_BIN_ASSERT(pos < (unsigned)ntaps);
+              rec[pos] = make_uint4(((unsigned)cell << 16) | ((unsigned)qq[u] << 6) | ((unsigned)lvl << 3),
+                                    __float_as_uint(lw), __float_as_uint(lh), __float_as_uint(aw[u]));
+            }
+            posarr[k] = (unsigned short)pos;
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- sweep: every lane group walks its segment of the cell-sorted records ----
+    {
+      const int beg = s_bound[grp], end = s_bound[grp + 1];
+      const long long img_off = ((long long)b * S * M + m) * D + sub * VE;
+      unsigned long long vbase = reinterpret_cast<unsigned long long>(value + img_off);
+      unsigned long long gbase = reinterpret_cast<unsigned long long>(gacc + img_off);
+      asm volatile("" : "+l"(vbase), "+l"(gbase));
+      const T* vimg = reinterpret_cast<const T*>(vbase);
+      float* gimg = reinterpret_cast<float*>(gbase);
+      // 32-bit shared-window addresses: record r at rec_sa + 16 r, this lane's part of grad_out
+      // row q at go_sa + ROWB q
+      const unsigned rec_sa = (unsigned)__cvta_generic_to_shared(rec);
+      const unsigned go_sa = (unsigned)__cvta_generic_to_shared(go_s) + (unsigned)(sub * VB);
+      const unsigned lvl_sa = (unsigned)__cvta_generic_to_shared(s_lvl);
+
+      int cur = -1;                      // current cell
+      int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+      unsigned vmask = 0;                // bit k: corner k exists in the map (cuh:61-83)
+      // value rows and accumulators as channel pairs (one 64-bit register pair each): the
+      // multiply-adds below are packed fma.rn.f32x2 (FFMA2 on sm_100a)
+      u64 v00[2], v01[2], v10[2], v11[2];
+      u64 a00[2], a01[2], a10[2], a11[2];
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        v00[k2] = v01[k2] = v10[k2] = v11[k2] = 0ull;
+        a00[k2] = a01[k2] = a10[k2] = a11[k2] = 0ull;
+      }
+      auto flush_row = [&](int off, const u64 (&acc)[2]) {
+        float x0, x1, x2, x3;
+        unpack2(acc[0], x0, x1);
+        unpack2(acc[1], x2, x3);
+        red_add_v4(gimg + off, x0, x1, x2, x3);
+      };
+
+      // the trip count is warp-uniform (shuffles inside); groups past their end idle
+      const int trips = (int)__reduce_max_sync(0xffffffffu, (unsigned)(end - beg));
+      for (int i = 0; i < trips; ++i) {
+        const int r = beg + i;
+        const bool active = r < end;
+        float pa = 0.f, px = 0.f, py = 0.f;
+        if (active) {
+          const uint4 rc = lds_v4(rec_sa + (unsigned)r * 16u);
+          u64 g01, g23;
+          BinRowS<T>::load(go_sa + ((rc.x >> 6) & 0x3ffu) * ROWB, g01, g23);
+          const int cell = (int)(rc.x >> 16);
+          if (cell != cur) {
+            if (vmask & 1u) flush_row(o00, a00);
+            if (vmask & 2u) flush_row(o01, a01);
+            if (vmask & 4u) flush_row(o10, a10);
+            if (vmask & 8u) flush_row(o11, a11);
+            cur = cell;
+            const unsigned lv = lvl_sa + ((rc.x >> 3) & 7u) * 32u;
+            const uint4 A = lds_v4(lv);          // cell_base, magic, wp1, W
+            const uint2 B = lds_v2(lv + 16u);    // H, start
+            const unsigned cl = (unsigned)cell - A.x;
+            const int yy = (int)__umulhi(cl, A.y);           // y0 + 1
+            const int xx = (int)cl - yy * (int)A.z;          // x0 + 1
+            const int Wl = (int)A.w, Hl = (int)B.x;
+            PCT_BIN_ASSERT(yy >= 0 && yy <= Hl && xx >= 0 && xx <= Wl);
+            const bool top = yy >= 1, bot = yy <= Hl - 1, lef = xx >= 1, rig = xx <= Wl - 1;
+            vmask = (top && lef ? 1u : 0u) | (top && rig ? 2u : 0u) | (bot && lef ? 4u : 0u) |
+                    (bot && rig ? 8u : 0u);
+            const int y0c = max(yy - 1, 0), x0c = max(xx - 1, 0);
+            const int y1c = min(yy, Hl - 1), x1c = min(xx, Wl - 1);
+            const int r0 = ((int)B.y + y0c * Wl) * MD, r1 = ((int)B.y + y1c * Wl) * MD;
+            o00 = r0 + x0c * MD;
+            o01 = r0 + x1c * MD;
+            o10 = r1 + x0c * MD;
+            o11 = r1 + x1c * MD;
+            PCT_CHECK_TAP(o00, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
+            PCT_CHECK_TAP(o11, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
+            // corners the reference skips read as 0 (cuh:61-83): zero-initialised, load predicated
+            BinVal<T>::load(vimg + o00, vmask & 1u, v00[0], v00[1]);
+            BinVal<T>::load(vimg + o01, vmask & 2u, v01[0], v01[1]);
+            BinVal<T>::load(vimg + o10, vmask & 4u, v10[0], v10[1]);
+            BinVal<T>::load(vimg + o11, vmask & 8u, v11[0], v11[1]);
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) a00[k2] = a01[k2] = a10[k2] = a11[k2] = 0ull;
+          }
+          const float lw = __uint_as_float(rc.y), lh = __uint_as_float(rc.z);
+          const float a = __uint_as_float(rc.w);
+          const float hw = 1.f - lw, hh = 1.f - lh;
+          const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;   // cuh:85
+          const float c00 = w00 * a, c01 = w01 * a, c10 = w10 * a, c11 = w11 * a;  // cuh:118,130-157
+          // four corner dot products <grad_out, value row>: two channel pairs each
+          const u64 e00 = fma2(g23, v00[1], mul2(g01, v00[0]));
+          const u64 e01 = fma2(g23, v01[1], mul2(g01, v01[0]));
+          const u64 e10 = fma2(g23, v10[1], mul2(g01, v10[0]));
+          const u64 e11 = fma2(g23, v11[1], mul2(g01, v11[0]));
+          // grad_value partial sums: acc_k += (w_k * attn) * grad_out
+          const u64 s00 = pack2(c00, c00), s01 = pack2(c01, c01), s10 = pack2(c10, c10), s11 = pack2(c11, c11);
+          a00[0] = fma2(s00, g01, a00[0]); a00[1] = fma2(s00, g23, a00[1]);
+          a01[0] = fma2(s01, g01, a01[0]); a01[1] = fma2(s01, g23, a01[1]);
+          a10[0] = fma2(s10, g01, a10[0]); a10[1] = fma2(s10, g23, a10[1]);
+          a11[0] = fma2(s11, g01, a11[0]); a11[1] = fma2(s11, g23, a11[1]);
+          const float d00 = sum2(e00), d01 = sum2(e01), d10 = sum2(e10), d11 = sum2(e11);
+          pa = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;          // cuh:161 (val . grad_out)
+          px = hh * (d01 - d00) + lh * (d11 - d10);                    // grad_w_weight (cuh:128-156)
+          py = hw * (d10 - d00) + lw * (d11 - d01);                    // grad_h_weight
+        }
+        // group sums: lane sub 0 holds pa, 1 px, 2 py; they replace words 0..2 of the record (its
+        // cell / lw / lh are used up; word 3 keeps attn for the scaling in the final pass)
+        const float red = bin_reduce3<LPP>(pa, py, px, sub);
+        if (active && sub < 3) sts_f32(rec_sa + (unsigned)r * 16u + (unsigned)sub * 4u, red);
+      }
+      if (vmask & 1u) flush_row(o00, a00);
+      if (vmask & 2u) flush_row(o01, a01);
+      if (vmask & 4u) flush_row(o10, a10);
+      if (vmask & 8u) flush_row(o11, a11);
+    }
+    __syncthreads();
+
+    // ---- final: coalesced grad_sampling_loc / grad_attn_weight in sample order ----
+    {
+      int ql = tid / LP, s = tid - ql * LP;
+      for (int k2 = tid; k2 < ntaps; k2 += kBinThreads) {
+        const unsigned pos = posarr[k2];
+        float ga = 0.f, gx = 0.f, gy = 0.f;    // out-of-range samples: exact zeros (cu:126-128)
+        if (pos != kBinNoPos) {
+          const uint4 rc = rec[pos];           // {val . grad_out, grad_w_weight, grad_h_weight, attn}
+          const float2 F = *reinterpret_cast<const float2*>(&s_lvl[s_slvl[s]].Hf);
+          const float a = __uint_as_float(rc.w);
+          ga = __uint_as_float(rc.x);                       // cuh:161
+          gx = F.y * __uint_as_float(rc.y) * a;             // cuh:162  W * grad_w_weight * attn
+          gy = F.x * __uint_as_float(rc.z) * a;             // cuh:163  H * grad_h_weight * attn
+        }
+        const long long si = samp0 + ql * qstep + s;
+        __stcs(grad_attn + si, ga);
+        __stcs(reinterpret_cast<float2*>(grad_loc) + si, make_float2(gx, gy));
+        ql += dq; s += ds;
+        if (s >= LP) { s -= LP; ++ql; }
+      }
+    }
+    __syncthreads();   // the next task reuses the shared arrays (and s_task)
+  }
+
+  // last CTA out resets the counters of this ring slot
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+      ctr[0] = 0u;
+      ctr[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace pct

@@ -7,7 +7,9 @@
 
 #include <atomic>
 
+#include "msda_bwd_binned.cuh"
 #include "msda_kernels.cuh"
+#include "msda_launch.h"
 
 namespace {
 
@@ -25,7 +27,12 @@ namespace pct {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace pct
 
-namespace {
+namespace pctl {
+
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+unsigned next_sched_slot() {
+  return g_sched_seq.fetch_add(1, std::memory_order_relaxed) % pct::kSchedSlots;
+}
 
 pct::SchedArgs make_sched(long long n_tasks, int grid, int warps, unsigned flags) {
   int sixteenths = kStaticSixteenths;
@@ -34,10 +41,33 @@ pct::SchedArgs make_sched(long long n_tasks, int grid, int warps, unsigned flags
   long long per_cta = n_tasks * sixteenths / 16 / grid;
   per_cta -= per_cta % warps;             // whole rounds of the CTA's warps
   pct::SchedArgs sa;
-  sa.slot = (int)(g_sched_seq.fetch_add(1, std::memory_order_relaxed) % pct::kSchedSlots);
+  sa.slot = (int)next_sched_slot();
   sa.static_per_cta = (int)(per_cta < 0 ? 0 : per_cta);
   return sa;
 }
+
+// Persistent launch: one CTA per SM (or fewer when there is little work).
+LaunchShape vec_launch_shape(long long n_tasks, int sm_count, unsigned flags, int default_block) {
+  int block = default_block;
+  int ctas_per_sm = 1;
+  const int fb = (int)((flags >> 8) & 0xffu);   // threads / 32
+  const int fc = (int)((flags >> 16) & 0xfu);
+  if (fb > 0 && fb * 32 <= default_block) block = fb * 32;
+  if (fc > 0) ctas_per_sm = fc;
+  const int warps = block / 32;
+  long long want = (n_tasks + warps - 1) / warps;
+  long long cap = (long long)sm_count * ctas_per_sm;
+  LaunchShape s;
+  s.grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+  s.block = block;
+  return s;
+}
+
+}  // namespace pctl
+
+namespace {
+
+using namespace pctl;
 
 int device_sm_count(int* out) {
   // Cached per device ordinal; racing initialisers write the same value.
@@ -62,12 +92,6 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 inline size_t elem_size(int dtype) {
   return dtype == PCT_MSDA_F32 ? 4 : dtype == PCT_MSDA_BF16 ? 2 : 8;
 }
-
-// How a (query, head) pair is spread over lanes on the vector path.
-struct VecPlan {
-  int lanes = 0;  // lanes per pair (0 = shape does not fit the vector path)
-  int vb = 0;     // bytes of channels per lane
-};
 
 inline bool pow2_le32(size_t x) { return x >= 1 && x <= 32 && (x & (x - 1)) == 0; }
 
@@ -94,10 +118,6 @@ inline VecPlan vec_plan(int channels, int num_levels, int num_point, int dtype, 
   return p;
 }
 
-struct Dims {
-  int N, S, M, D, L, Lq, P;
-};
-
 int check_dims(const Dims& d, int dtype) {
   if (dtype != PCT_MSDA_F32 && dtype != PCT_MSDA_BF16 && dtype != PCT_MSDA_F64) return PCT_MSDA_E_BAD_DTYPE;
   if (d.N < 0 || d.S < 0 || d.Lq < 0 || d.M <= 0 || d.D <= 0 || d.L <= 0 || d.P <= 0) return PCT_MSDA_E_BAD_SHAPE;
@@ -106,163 +126,6 @@ int check_dims(const Dims& d, int dtype) {
   if ((long double)d.N * d.S * d.M * d.D > lim || (long double)d.N * d.Lq * d.M * d.L * d.P * 2 > lim)
     return PCT_MSDA_E_TOO_LARGE;
   return 0;
-}
-
-struct LaunchShape {
-  int grid, block;
-};
-
-// Persistent launch: one CTA per SM (or fewer when there is little work).
-LaunchShape vec_launch_shape(long long n_tasks, int sm_count, unsigned flags, int default_block) {
-  int block = default_block;
-  int ctas_per_sm = 1;
-  const int fb = (int)((flags >> 8) & 0xffu);   // threads / 32
-  const int fc = (int)((flags >> 16) & 0xfu);
-  if (fb > 0 && fb * 32 <= default_block) block = fb * 32;
-  if (fc > 0) ctas_per_sm = fc;
-  const int warps = block / 32;
-  long long want = (n_tasks + warps - 1) / warps;
-  long long cap = (long long)sm_count * ctas_per_sm;
-  LaunchShape s;
-  s.grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
-  s.block = block;
-  return s;
-}
-
-template <typename T, int LPP, int VB, bool FUSED>
-int launch_fwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
-                   const void* attn, void* out, const Dims& d, int sm_count, cudaStream_t st,
-                   unsigned flags, pct::FusedRef fr) {
-  constexpr int PPW = 32 / LPP;
-  const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
-  const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kVecThreads);
-  pct::msda_fwd_vec_kernel<T, LPP, VB, FUSED><<<ls.grid, ls.block, 0, st>>>(
-      (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (T*)out, d.N, d.S, d.M,
-      d.L, d.Lq, d.P, fr, make_sched(n_tasks, ls.grid, ls.block / 32, flags));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
-}
-
-template <typename T, int LPP, int VB, bool FUSED, typename ACC = float>
-int launch_bwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
-                   const void* attn, const void* grad_out, void* gacc, void* grad_loc,
-                   void* grad_attn, const Dims& d, int sm_count, cudaStream_t st, unsigned flags,
-                   pct::FusedRef fr, const pct::DetScratch* det) {
-  constexpr int PPW = 32 / LPP;
-  const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
-  const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags,
-                                          FUSED ? pct::kBwdFusedThreads : pct::kBwdVecThreads);
-  pct::msda_bwd_vec_kernel<T, LPP, VB, FUSED, ACC><<<ls.grid, ls.block, 0, st>>>(
-      (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
-      (ACC*)gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, fr,
-      make_sched(n_tasks, ls.grid, ls.block / 32, flags), det);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
-}
-
-#define PCT_LANE_CASES(LAUNCH, T, VB, FUSED)                                             \
-  switch (plan.lanes) {                                                                 \
-    case 1: return LAUNCH<T, 1, VB, FUSED>;                                             \
-    case 2: return LAUNCH<T, 2, VB, FUSED>;                                             \
-    case 4: return LAUNCH<T, 4, VB, FUSED>;                                             \
-    case 8: return LAUNCH<T, 8, VB, FUSED>;                                             \
-    case 16: return LAUNCH<T, 16, VB, FUSED>;                                           \
-    case 32: return LAUNCH<T, 32, VB, FUSED>;                                           \
-  }                                                                                     \
-  return nullptr;
-
-using FwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
-                            void*, const Dims&, int, cudaStream_t, unsigned, pct::FusedRef);
-using BwdLauncher = int (*)(const void*, const int64_t*, const int64_t*, const void*, const void*,
-                            const void*, void*, void*, void*, const Dims&, int, cudaStream_t,
-                            unsigned, pct::FusedRef, const pct::DetScratch*);
-
-template <bool FUSED>
-FwdLauncher pick_fwd(const VecPlan& plan, int dtype) {
-  if (dtype == PCT_MSDA_F32) {
-    if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, float, 16, FUSED) }
-    if (plan.vb == 32 && plan.lanes == 32) return launch_fwd_vec<float, 32, 32, FUSED>;
-  } else {
-    if (plan.vb == 16) { PCT_LANE_CASES(launch_fwd_vec, __nv_bfloat16, 16, FUSED) }
-    if (plan.vb == 8 && plan.lanes == 1) return launch_fwd_vec<__nv_bfloat16, 1, 8, FUSED>;
-  }
-  return nullptr;
-}
-
-// deterministic fixed-point accumulator (opt-in): lanes of 4 channels only
-BwdLauncher pick_bwd_deterministic(const VecPlan& plan, int dtype) {
-#define PCT_DET_CASES(T, VB)                                                   \
-  switch (plan.lanes) {                                                        \
-    case 1: return launch_bwd_vec<T, 1, VB, false, long long>;                 \
-    case 2: return launch_bwd_vec<T, 2, VB, false, long long>;                 \
-    case 4: return launch_bwd_vec<T, 4, VB, false, long long>;                 \
-    case 8: return launch_bwd_vec<T, 8, VB, false, long long>;                 \
-    case 16: return launch_bwd_vec<T, 16, VB, false, long long>;               \
-    case 32: return launch_bwd_vec<T, 32, VB, false, long long>;               \
-  }
-  if (dtype == PCT_MSDA_F32 && plan.vb == 16) { PCT_DET_CASES(float, 16) }
-  if (dtype == PCT_MSDA_BF16 && plan.vb == 8) { PCT_DET_CASES(__nv_bfloat16, 8) }
-#undef PCT_DET_CASES
-  return nullptr;
-}
-
-// bf16 values, bf16 accumulator (opt-in): 8-byte lanes only
-BwdLauncher pick_bwd_bf16_accum(const VecPlan& plan) {
-  if (plan.vb != 8) return nullptr;
-  switch (plan.lanes) {
-    case 1: return launch_bwd_vec<__nv_bfloat16, 1, 8, false, __nv_bfloat16>;
-    case 2: return launch_bwd_vec<__nv_bfloat16, 2, 8, false, __nv_bfloat16>;
-    case 4: return launch_bwd_vec<__nv_bfloat16, 4, 8, false, __nv_bfloat16>;
-    case 8: return launch_bwd_vec<__nv_bfloat16, 8, 8, false, __nv_bfloat16>;
-    case 16: return launch_bwd_vec<__nv_bfloat16, 16, 8, false, __nv_bfloat16>;
-    case 32: return launch_bwd_vec<__nv_bfloat16, 32, 8, false, __nv_bfloat16>;
-  }
-  return nullptr;
-}
-
-template <bool FUSED>
-BwdLauncher pick_bwd(const VecPlan& plan, int dtype) {
-  if (dtype == PCT_MSDA_F32) {
-    if (plan.vb == 16) { PCT_LANE_CASES(launch_bwd_vec, float, 16, FUSED) }
-    if (plan.vb == 32 && plan.lanes == 32) return launch_bwd_vec<float, 32, 32, FUSED>;
-  } else {
-    if (plan.vb == 8) { PCT_LANE_CASES(launch_bwd_vec, __nv_bfloat16, 8, FUSED) }
-    if (plan.vb == 16 && plan.lanes == 32) return launch_bwd_vec<__nv_bfloat16, 32, 16, FUSED>;
-  }
-  return nullptr;
-}
-#undef PCT_LANE_CASES
-
-int generic_grid(long long n_tasks, int sm_count) {
-  const int warps = pct::kGenericThreads / 32;
-  long long want = (n_tasks + warps - 1) / warps;
-  long long cap = (long long)sm_count * 8;
-  return (int)(want < 1 ? 1 : (want < cap ? want : cap));
-}
-
-template <typename T, typename CT>
-int launch_fwd_generic(const void* value, const int64_t* shapes, const int64_t* lsi,
-                       const void* loc, const void* attn, void* out, const Dims& d, int sm_count,
-                       cudaStream_t st) {
-  const long long n_tasks = (long long)d.N * d.M * d.Lq;
-  pct::msda_fwd_generic_kernel<T, CT><<<generic_grid(n_tasks, sm_count), pct::kGenericThreads, 0, st>>>(
-      (const T*)value, shapes, lsi, (const CT*)loc, (const CT*)attn, (T*)out, d.N, d.S, d.M, d.D,
-      d.L, d.Lq, d.P);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
-}
-
-template <typename T, typename CT, typename AT>
-int launch_bwd_generic(const void* value, const int64_t* shapes, const int64_t* lsi,
-                       const void* loc, const void* attn, const void* grad_out, AT* gacc,
-                       void* grad_loc, void* grad_attn, const Dims& d, int sm_count,
-                       cudaStream_t st) {
-  const long long n_tasks = (long long)d.N * d.M * d.Lq;
-  pct::msda_bwd_generic_kernel<T, CT, AT><<<generic_grid(n_tasks, sm_count), pct::kGenericThreads, 0, st>>>(
-      (const T*)value, shapes, lsi, (const CT*)loc, (const CT*)attn, (const T*)grad_out, gacc,
-      (CT*)grad_loc, (CT*)grad_attn, d.N, d.S, d.M, d.D, d.L, d.Lq, d.P);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
 }
 
 // zero `bytes` at a 16-byte aligned address with a kernel (see msda_zero_kernel)
@@ -298,6 +161,54 @@ int round_workspace_to_bf16(const float* ws, void* grad_value, long long n, int 
     if (e != cudaSuccess) return (int)e;
   }
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cell-binned backward (msda_bwd_binned.cuh): the default gradient kernel whenever it fits.
+// The level shapes live in device memory, so the host sizes shared memory from an upper bound of
+// the number of bilinear cells,  sum_l (H_l+1)(W_l+1) <= 2*S + 2*L  (H + W <= H*W + 1), and the
+// kernel derives the chunk size from the real shapes.
+// ---------------------------------------------------------------------------------------------
+int device_smem_optin(int* out) {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev >= 0 && dev < 64) {
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v > 0) { *out = v; return 0; }
+  }
+  int n = 0;
+  e = cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+  *out = n;
+  return 0;
+}
+
+// 0 = not eligible, else lanes per (query, head) row
+int binned_plan(const Dims& d, int dtype, unsigned flags, int smem_optin, const void* value,
+                const void* grad_out, const void* acc, const void* loc, const void* attn,
+                const void* grad_loc) {
+  if (flags & (PCT_MSDA_FLAG_FORCE_GENERIC | PCT_MSDA_FLAG_BWD_PER_TAP)) return 0;
+  if (dtype != PCT_MSDA_F32 && dtype != PCT_MSDA_BF16) return 0;
+  if (d.D % 4 != 0) return 0;
+  const int lanes = d.D / 4;
+  if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return 0;
+  const long long LP = (long long)d.L * d.P;
+  if (d.L > pct::kBinMaxLevels || LP > pct::kBinMaxSamples) return 0;
+  if ((long long)d.S * d.M * d.D >= (1ll << 31) || d.S == 0) return 0;
+  if ((long long)d.N * d.M * ((long long)d.Lq / 8 + 1) >= (1ll << 31)) return 0;   // task index
+  const long long nc_bound = 2ll * d.S + 2ll * d.L;
+  if (nc_bound > pct::kBinMaxCells) return 0;
+  const int row_bytes = d.D * (int)elem_size(dtype);
+  const long long fixed = ((nc_bound + 1 + 3) & ~3ll) * 4 + 16 + 1024;   // + the kernel's static arrays
+  if (fixed + (long long)kBinMinChunk * pct::bin_bytes_per_query((int)LP, row_bytes) > smem_optin) return 0;
+  const size_t vb = 4 * elem_size(dtype);
+  if (!aligned(value, vb) || !aligned(grad_out, 16) || !aligned(acc, 16) || !aligned(loc, 8) ||
+      !aligned(attn, 4) || !aligned(grad_loc, 8))
+    return 0;
+  return lanes;
 }
 
 // `io` is output (forward) or grad_output (backward); `acc` the fp32 grad_value accumulator
@@ -377,23 +288,12 @@ int forward_impl(const void* value, const int64_t* spatial_shapes,
     return (int)cudaMemsetAsync(output, 0, (size_t)d.N * d.Lq * d.M * d.D * es, st);
   }
   const VecPlan vp = vec_eligible(d, value_dtype, flags, value, output, nullptr, sampling_loc, attn_weight);
-  if (FwdLauncher fn = vp.lanes == 0 ? nullptr
-                       : fused       ? pick_fwd<true>(vp, value_dtype)
-                                     : pick_fwd<false>(vp, value_dtype))
+  if (FwdLauncher fn = vp.lanes == 0 ? nullptr : pick_fwd(fused, vp, value_dtype))
     return fn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, sm_count,
               st, flags, fr);
   if (fused) return PCT_MSDA_E_UNSUPPORTED;  // the fused prologue exists on the vector path only
-  switch (value_dtype) {
-    case PCT_MSDA_F32:
-      return launch_fwd_generic<float, float>(value, spatial_shapes, level_start_index, sampling_loc,
-                                              attn_weight, output, d, sm_count, st);
-    case PCT_MSDA_BF16:
-      return launch_fwd_generic<__nv_bfloat16, float>(value, spatial_shapes, level_start_index,
-                                                      sampling_loc, attn_weight, output, d, sm_count, st);
-    default:
-      return launch_fwd_generic<double, double>(value, spatial_shapes, level_start_index,
-                                                sampling_loc, attn_weight, output, d, sm_count, st);
-  }
+  return launch_fwd_generic(value_dtype, value, spatial_shapes, level_start_index, sampling_loc,
+                            attn_weight, output, d, sm_count, st);
 }
 
 }  // namespace
@@ -554,36 +454,29 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
-  if (BwdLauncher fn = det_fn            ? det_fn
-                       : bf16_accum      ? bf16_accum
-                       : vp.lanes == 0 ? nullptr
-                       : fused         ? pick_bwd<true>(vp, value_dtype)
-                                       : pick_bwd<false>(vp, value_dtype)) {
+  int smem_optin = 0;
+  rc = device_smem_optin(&smem_optin);
+  if (rc) return rc;
+  const int bin_lanes = (det_fn || bf16_accum || fused)
+                            ? 0
+                            : binned_plan(d, value_dtype, flags, smem_optin, value, grad_output, acc_image,
+                                          sampling_loc, attn_weight, grad_sampling_loc);
+  if (bin_lanes) {
+    rc = dispatch_bwd_binned(bin_lanes, value_dtype, value, spatial_shapes, level_start_index,
+                             sampling_loc, attn_weight, grad_output, acc_image, grad_sampling_loc,
+                             grad_attn_weight, d, sm_count, smem_optin, st, flags);
+  } else if (BwdLauncher fn = det_fn          ? det_fn
+                              : bf16_accum    ? bf16_accum
+                              : vp.lanes == 0 ? nullptr
+                                              : pick_bwd(fused, vp, value_dtype)) {
     rc = fn(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
             acc_image, grad_sampling_loc, grad_attn_weight, d, sm_count, st, flags, fr, det);
   } else if (fused) {
     return PCT_MSDA_E_UNSUPPORTED;
   } else {
-    switch (value_dtype) {
-      case PCT_MSDA_F32:
-        rc = launch_bwd_generic<float, float, float>(value, spatial_shapes, level_start_index,
-                                                     sampling_loc, attn_weight, grad_output,
-                                                     (float*)acc_image, grad_sampling_loc,
-                                                     grad_attn_weight, d, sm_count, st);
-        break;
-      case PCT_MSDA_BF16:
-        rc = launch_bwd_generic<__nv_bfloat16, float, float>(value, spatial_shapes, level_start_index,
-                                                             sampling_loc, attn_weight, grad_output,
-                                                             (float*)acc_image, grad_sampling_loc,
-                                                             grad_attn_weight, d, sm_count, st);
-        break;
-      default:
-        rc = launch_bwd_generic<double, double, double>(value, spatial_shapes, level_start_index,
-                                                        sampling_loc, attn_weight, grad_output,
-                                                        (double*)acc_image, grad_sampling_loc,
-                                                        grad_attn_weight, d, sm_count, st);
-        break;
-    }
+    rc = launch_bwd_generic(value_dtype, value, spatial_shapes, level_start_index, sampling_loc,
+                            attn_weight, grad_output, acc_image, grad_sampling_loc, grad_attn_weight,
+                            d, sm_count, st);
   }
   if (rc) return rc;
   if (det_fn) {
@@ -604,6 +497,26 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
 }  // namespace
 
 extern "C" {
+
+int pct_msda_backward_plan(int batch, int spatial_size, int num_heads, int channels,
+                           int num_levels, int num_query, int num_point, int value_dtype,
+                           unsigned flags) {
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  int rc = check_dims(d, value_dtype);
+  if (rc) return -rc;
+  const bool special = flags & (PCT_MSDA_FLAG_DETERMINISTIC | PCT_MSDA_FLAG_BF16_ACCUM);
+  if (!special) {
+    int smem_optin = 0;
+    rc = device_smem_optin(&smem_optin);
+    if (rc) return -rc;
+    alignas(16) static const char dummy[16] = {0};
+    if (binned_plan(d, value_dtype, flags, smem_optin, dummy, dummy, dummy, dummy, dummy, dummy)) return 2;
+  }
+  if (flags & PCT_MSDA_FLAG_FORCE_GENERIC) return 0;
+  if ((long long)d.S * d.M * d.D >= (1ll << 31) || d.S == 0) return 0;
+  if ((long long)d.N * d.M * d.Lq >= (1ll << 31)) return 0;
+  return vec_plan(d.D, d.L, d.P, value_dtype, true).lanes > 0 ? 1 : 0;
+}
 
 int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
                          const int64_t* level_start_index, const void* sampling_loc,

@@ -1,0 +1,80 @@
+// msda_inst_binned.cu -- instantiations and launcher of the cell-binned backward (msda_bwd_binned.cuh).
+#include <atomic>
+
+#include "../../include/pct_msda.h"
+#include "msda_bwd_binned.cuh"
+#include "msda_launch.h"
+
+namespace pctl {
+namespace {
+
+constexpr int kDefaultCellCost = 2;
+
+template <typename T, int LPP>
+int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                      const void* attn, const void* grad_out, void* gacc, void* grad_loc,
+                      void* grad_attn, const Dims& d, int sm_count, int smem_optin, cudaStream_t st,
+                      unsigned flags) {
+  static std::atomic<int> configured[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  auto kern = pct::msda_bwd_binned_kernel<T, LPP>;
+  // dynamic shared memory = the opt-in maximum minus the kernel's static arrays
+  int dyn = (dev >= 0 && dev < 64) ? configured[dev].load(std::memory_order_acquire) : 0;
+  if (dyn == 0) {
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return (int)e;
+    // (per resident CTA: the SM's shared memory holds kBinCtasPerSm of them, each with 1 KB of
+    // system reserve)
+    dyn = ((smem_optin + 1024) / pct::kBinCtasPerSm - 1024 - (int)fa.sharedSizeBytes) & ~15;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) configured[dev].store(dyn, std::memory_order_release);
+  }
+  pct::BinLaunch bl;
+  bl.smem_bytes = dyn;
+  bl.qc_cap = (int)((flags >> 25) & 0x7fu) * 8;
+  bl.slot = (int)(next_sched_slot());
+  const int fk = (int)((flags >> 16) & 0xfu);   // tuning: 1 + cost of opening a cell, in records
+  bl.cell_cost = fk > 0 ? fk - 1 : kDefaultCellCost;
+  const long long want = (long long)d.N * d.M * ((d.Lq + kBinMinChunk - 1) / kBinMinChunk);
+  const long long cap = (long long)sm_count * pct::kBinCtasPerSm;
+  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  kern<<<grid, pct::kBinThreads, dyn, st>>>(
+      (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
+      (float*)gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, bl);
+  count_launches(1);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int dispatch_bwd_binned(int lanes, int dtype, const void* value, const int64_t* shapes,
+                        const int64_t* lsi, const void* loc, const void* attn, const void* grad_out,
+                        void* gacc, void* grad_loc, void* grad_attn, const Dims& d, int sm_count,
+                        int smem_optin, cudaStream_t st, unsigned flags) {
+#define PCT_BIN_CASE(T, LPP)                                                                       \
+  return launch_bwd_binned<T, LPP>(value, shapes, lsi, loc, attn, grad_out, gacc, grad_loc,        \
+                                   grad_attn, d, sm_count, smem_optin, st, flags)
+  if (dtype == PCT_MSDA_F32) {
+    switch (lanes) {
+      case 4: PCT_BIN_CASE(float, 4);
+      case 8: PCT_BIN_CASE(float, 8);
+      case 16: PCT_BIN_CASE(float, 16);
+      case 32: PCT_BIN_CASE(float, 32);
+    }
+  } else {
+    switch (lanes) {
+      case 4: PCT_BIN_CASE(__nv_bfloat16, 4);
+      case 8: PCT_BIN_CASE(__nv_bfloat16, 8);
+      case 16: PCT_BIN_CASE(__nv_bfloat16, 16);
+      case 32: PCT_BIN_CASE(__nv_bfloat16, 32);
+    }
+  }
+#undef PCT_BIN_CASE
+  return PCT_MSDA_E_UNSUPPORTED;
+}
+
+}  // namespace pctl

@@ -228,10 +228,11 @@ struct SampleTaps {
 __device__ __forceinline__ SampleTaps make_sample_taps(float loc_x, float loc_y, int H, int W,
                                                        int start, int MD) {
   SampleTaps t;
-  // The reference evaluates loc*size - 0.5 in double and rounds once (the literal 0.5 promotes,
-  // cuh:290-291): that is exactly one fused multiply-add in fp32.
-  const float y = fmaf(loc_y, (float)H, -0.5f);
-  const float x = fmaf(loc_x, (float)W, -0.5f);
+  // cuh:290-291 `loc * size - 0.5`: the product is rounded to float (float * int), the literal
+  // 0.5 promotes the subtraction to double and the assignment rounds once more -- bit for bit a
+  // float multiply followed by a float subtract (NOT a fused multiply-add).
+  const float y = __fsub_rn(__fmul_rn(loc_y, (float)H), 0.5f);
+  const float x = __fsub_rn(__fmul_rn(loc_x, (float)W), 0.5f);
   const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
   const float fy = floorf(y), fx = floorf(x);
   t.ly = y - fy;
@@ -276,7 +277,8 @@ constexpr int kSchedSlots = 512;
 #define PCT_MINI_CHUNK 2
 #endif
 constexpr int kMiniChunk = PCT_MINI_CHUNK;
-__device__ unsigned int g_sched[kSchedSlots * 2];
+// one ring per translation unit that launches persistent kernels (internal linkage)
+static __device__ unsigned int g_sched[kSchedSlots * 2];
 
 struct SchedArgs {
   int slot;            // ring slot of this launch
@@ -829,7 +831,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 // Zero-fill of the grad_value accumulator.  A kernel, not cudaMemsetAsync: a memset may be placed on
 // a copy engine, where it queues behind the host<->device copies of the end-to-end pipeline
 // (pctrans_b200/host_pipeline.py) and stalls the backward of every chunk.
-__global__ void msda_zero_kernel(uint4* __restrict__ dst, long long n16, unsigned char* tail,
+static __global__ void msda_zero_kernel(uint4* __restrict__ dst, long long n16, unsigned char* tail,
                                  int n_tail) {
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -865,7 +867,7 @@ __global__ void msda_absmax_kernel(const T* __restrict__ x, long long n, DetScra
   if ((threadIdx.x & 31) == 0 && m) atomicMax(&sc->max_bits, m);
 }
 
-__global__ void msda_det_scale_kernel(DetScratch* sc) {
+static __global__ void msda_det_scale_kernel(DetScratch* sc) {
   const float mx = __uint_as_float(sc->max_bits);
   // max*scale lands in [2^38, 2^39): bilinear weight * attention <= 1, so 2^24 contributions per
   // element still fit in 63 bits
@@ -882,7 +884,7 @@ __global__ void msda_fixed_to_value_kernel(const long long* __restrict__ acc, T*
 }
 
 // fp32 scratch image -> bf16 grad_value (bf16 path only)
-__global__ void msda_round_to_bf16_kernel(const float* __restrict__ src,
+static __global__ void msda_round_to_bf16_kernel(const float* __restrict__ src,
                                           __nv_bfloat16* __restrict__ dst, long long n8) {
   // n8 = number of 8-element groups
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
@@ -896,7 +898,7 @@ __global__ void msda_round_to_bf16_kernel(const float* __restrict__ src,
   }
 }
 
-__global__ void msda_round_to_bf16_tail_kernel(const float* __restrict__ src,
+static __global__ void msda_round_to_bf16_tail_kernel(const float* __restrict__ src,
                                                __nv_bfloat16* __restrict__ dst, long long begin,
                                                long long n) {
   const long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -919,7 +921,7 @@ struct TapsG {
 template <typename CT>
 __device__ __forceinline__ CT fma_coord(CT loc, int size);
 template <>
-__device__ __forceinline__ float fma_coord<float>(float loc, int size) { return fmaf(loc, (float)size, -0.5f); }
+__device__ __forceinline__ float fma_coord<float>(float loc, int size) { return __fsub_rn(__fmul_rn(loc, (float)size), 0.5f); }
 template <>
 __device__ __forceinline__ double fma_coord<double>(double loc, int size) { return loc * (double)size - 0.5; }
 

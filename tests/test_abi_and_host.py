@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_scalar_entry_points_without_gpu():
     from pctrans_b200 import _cabi
     lib = _cabi.load()
-    assert lib.pct_msda_abi_version() == 3
+    assert lib.pct_msda_abi_version() == 4
     assert lib.pct_msda_error_string(0) == b"success"
     assert b"null pointer" in lib.pct_msda_error_string(1001)
     assert b"unknown" in lib.pct_msda_error_string(-5)

@@ -72,7 +72,7 @@ def _golden(golden_dir):
 
 
 def test_library_loaded_and_fast_path_selected():
-    assert _cabi.load().pct_msda_abi_version() == 3
+    assert _cabi.load().pct_msda_abi_version() == 4
     assert _cabi.kernel_family(32, 3, 4, torch.float32) == 1
     assert _cabi.kernel_family(16, 3, 4, torch.float32) == 1
     assert _cabi.kernel_family(32, 3, 4, torch.bfloat16) == 1
