@@ -76,7 +76,10 @@ extern "C" {
                                             bytes of workspace; vector-path shapes only, else
                                             PCT_MSDA_E_UNSUPPORTED) */
 #define PCT_MSDA_FLAG_BWD_PER_TAP 0x20u   /* backward: use the per-tap scatter kernel (one L2 reduction per
-                                            bilinear corner) instead of the default cell-binned kernel */
+                                            bilinear corner) even where the cell-binned kernel is the default */
+#define PCT_MSDA_FLAG_BWD_BINNED 0x40u    /* backward: use the cell-binned kernel whenever the shape fits it
+                                            (default only for head rows of >= 256 bytes, where it measured
+                                            faster) */
 /* bits 8..15: threads/32 of the persistent CTA; bits 16..19: CTAs per SM; bits 20..24: 1 + static
  * share of the task list in sixteenths; bits 25..31: cap of the binned backward's chunk size in
  * units of 8 queries; for the binned backward bits 16..19 are 1 + the cost of opening a cell in its
@@ -98,8 +101,9 @@ int pct_msda_kernel_family(int channels, int num_levels, int num_point, int valu
 /* Which gradient kernel pct_msda_backward_ex runs for these dimensions and flags on the current
  * device (buffers assumed 16-byte aligned): 0 = generic scalar, 1 = per-tap vector scatter,
  * 2 = cell-binned (grad_value aggregated per bilinear cell on chip before any global reduction;
- * the default whenever the head dim is 16/32/64/128 channels, L <= 8, L*P <= 64 and the level
- * maps are small enough for shared memory).  Negative = error code negated. */
+ * available when the head dim is 16/32/64/128 channels, L <= 8, L*P <= 64 and the level maps are
+ * small enough for shared memory; the default for head rows of >= 256 bytes, otherwise selected
+ * with PCT_MSDA_FLAG_BWD_BINNED).  Negative = error code negated. */
 int pct_msda_backward_plan(int batch, int spatial_size, int num_heads, int channels,
                            int num_levels, int num_query, int num_point, int value_dtype,
                            unsigned flags);

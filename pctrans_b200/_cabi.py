@@ -38,6 +38,7 @@ FLAG_FORCE_GENERIC = 0x1
 FLAG_BF16_ACCUM = 0x8
 FLAG_DETERMINISTIC = 0x10
 FLAG_BWD_PER_TAP = 0x20
+FLAG_BWD_BINNED = 0x40
 
 _lib = None
 _lock = threading.Lock()

@@ -41,7 +41,7 @@
 namespace pct {
 
 #ifndef PCT_BIN_THREADS
-#define PCT_BIN_THREADS 768
+#define PCT_BIN_THREADS 1024
 #endif
 #ifndef PCT_BIN_CTAS
 #define PCT_BIN_CTAS 1       // resident CTAs per SM (each gets 1/PCT_BIN_CTAS of the shared memory)
@@ -171,6 +171,13 @@ __device__ __forceinline__ uint2 lds_v2(unsigned addr) {
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+#ifndef PCT_BIN_PREFETCH
+#define PCT_BIN_PREFETCH 0   // columns to the right of a newly opened cell pulled into L1 (measured: no gain)
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // one lane's 4 channels of a value row as two channel pairs; zeros when `keep` is false (the load
 // is predicated off, so nothing waits on it)
 template <typename T>
@@ -547,6 +554,18 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
             BinVal<T>::load(vimg + o11, vmask & 8u, v11[0], v11[1]);
 #pragma unroll
             for (int k2 = 0; k2 < 2; ++k2) a00[k2] = a01[k2] = a10[k2] = a11[k2] = 0ull;
+#if PCT_BIN_PREFETCH
+            // The records are sorted in raster order of the cells, so the next cell of this group
+            // is most often the right neighbour: pull its new column into L1 now (the other column
+            // is the one just loaded).  The kernel is bound by the latency of these row loads.
+            if (xx + PCT_BIN_PREFETCH <= Wl - 1) {
+#pragma unroll
+              for (int d = 1; d <= PCT_BIN_PREFETCH; ++d) {
+                prefetch_l1(vimg + o01 + d * MD);
+                prefetch_l1(vimg + o11 + d * MD);
+              }
+            }
+#endif
           }
           const float lw = __uint_as_float(rc.y), lh = __uint_as_float(rc.z);
           const float a = __uint_as_float(rc.w);

@@ -1,6 +1,7 @@
 """GPU parity of the cell-binned backward (pctrans_b200/csrc/msda_bwd_binned.cuh) through the C ABI.
 
-The binned kernel is the default gradient kernel; these cases pin it against (a) the CPU oracle
+The binned kernel is the default gradient kernel for wide head rows (>= 256 bytes) and selectable
+everywhere with ``PCT_MSDA_FLAG_BWD_BINNED``; these cases pin it against (a) the CPU oracle
 (fp64 closed form of cuh:93-164) and (b) the per-tap scatter kernel it replaces
 (``PCT_MSDA_FLAG_BWD_PER_TAP``), over the shapes that stress its bookkeeping: several chunks per
 (image, head), chunk sizes that do not divide Lq, L*P that does not divide the CTA size, one-pixel
@@ -41,6 +42,7 @@ def run_case(N, shapes, M, D, P, regime, seed, dtype=torch.float32, Lq=None, fla
     if dtype == torch.bfloat16:
         value, g = value.bfloat16().float(), g.bfloat16().float()
     S, L = value.shape[1], len(shapes)
+    flags |= _cabi.FLAG_BWD_BINNED
     assert _cabi.backward_plan(N, S, M, D, L, Lq, P, dtype, flags) == 2, "binned kernel not selected"
     assert _cabi.backward_plan(N, S, M, D, L, Lq, P, dtype, _cabi.FLAG_BWD_PER_TAP) == 1
     args = (value.to(DEV, dtype), sh.to(DEV), lsi.to(DEV), loc.to(DEV), attn.to(DEV), g.to(DEV, dtype))
@@ -96,7 +98,7 @@ def test_binned_on_grid_initial_offsets():
                                                   jitter_px=0.0)
     g = torch.randn(1, loc.shape[1], 256, generator=torch.Generator().manual_seed(9))
     args = (value.to(DEV), sh.to(DEV), lsi.to(DEV), loc.to(DEV), attn.to(DEV), g.to(DEV))
-    gv, gl, ga = _cabi.backward(*args)
+    gv, gl, ga = _cabi.backward(*args, flags=_cabi.FLAG_BWD_BINNED)
     pv, pl, pa = _cabi.backward(*args, flags=_cabi.FLAG_BWD_PER_TAP)
     rv, rl, ra = oracle.backward_c(value, sh, lsi, loc, attn, g, dtype=np.float32)
     for name, a, p, r in (("gv", gv, pv, rv), ("gl", gl, pl, rl), ("ga", ga, pa, ra)):
@@ -123,7 +125,8 @@ def test_binned_zero_weights_and_nan_free():
     attn[:, ::2] = 0.0
     loc = synth.nudge_off_grid(loc, shapes)
     g = torch.randn(1, 30, 64, generator=torch.Generator().manual_seed(3))
-    gv, gl, ga = _cabi.backward(value.to(DEV), sh.to(DEV), lsi.to(DEV), loc.to(DEV), attn.to(DEV), g.to(DEV))
+    gv, gl, ga = _cabi.backward(value.to(DEV), sh.to(DEV), lsi.to(DEV), loc.to(DEV), attn.to(DEV), g.to(DEV),
+                                flags=_cabi.FLAG_BWD_BINNED)
     rv, rl, ra = oracle.backward_c(value, sh, lsi, loc, attn, g)
     assert rel(gv, rv) <= 1e-4 and rel(gl, rl) <= 1e-4 and rel(ga, ra) <= 1e-4
     assert torch.isfinite(gv).all() and torch.isfinite(gl).all() and torch.isfinite(ga).all()
@@ -135,11 +138,18 @@ def test_binned_back_to_back_launches_share_nothing():
     value, sh, lsi, loc, attn = synth.make_inputs(2, synth.CVPPP_448, M=8, D=16, P=4, regime="R", seed=6)
     g = torch.randn(2, loc.shape[1], 128, generator=torch.Generator().manual_seed(6))
     args = (value.to(DEV), sh.to(DEV), lsi.to(DEV), loc.to(DEV), attn.to(DEV), g.to(DEV))
-    first = _cabi.backward(*args)
+    first = _cabi.backward(*args, flags=_cabi.FLAG_BWD_BINNED)
     for _ in range(20):
-        last = _cabi.backward(*args)
+        last = _cabi.backward(*args, flags=_cabi.FLAG_BWD_BINNED)
     torch.cuda.synchronize()
     assert torch.allclose(first[0], last[0], rtol=0, atol=1e-5 * float(first[0].abs().max()))
     # grad_loc / grad_attn depend on the order of the records inside a cell only through the
     # group that processes them -- each record is reduced on its own, so they are reproducible
     assert torch.equal(first[1], last[1]) and torch.equal(first[2], last[2])
+
+
+def test_binned_is_the_default_for_wide_rows():
+    assert _cabi.backward_plan(2, 5376, 8, 64, 3, 5376, 4, torch.float32, 0) == 2
+    assert _cabi.backward_plan(2, 5376, 8, 32, 3, 5376, 4, torch.float32, 0) == 1
+    assert _cabi.backward_plan(2, 5376, 8, 32, 3, 5376, 4, torch.float32, _cabi.FLAG_BWD_BINNED) == 2
+    assert _cabi.backward_plan(2, 5376, 8, 30, 3, 5376, 4, torch.float32, _cabi.FLAG_BWD_BINNED) == 0
