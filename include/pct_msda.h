@@ -34,8 +34,10 @@
  * re-entrant and may be called from any host thread (cu:70,140 use the current stream too).
  *
  * The persistent kernels balance their tail through a ring of 512 module-scope counter slots, one
- * per launch; launches may overlap freely, but a CUDA graph that captured a call must not be
- * replayed concurrently with itself (both replays would share the captured slot).
+ * per launch (the slot index is chosen on the host at launch time and is baked into a captured
+ * CUDA graph).  Eager launches may overlap freely.  A captured graph must not run concurrently
+ * with itself, nor with more than ~500 other pct_msda launches issued after its capture (the ring
+ * would wrap onto its slot): serialise graph replays of this library on one stream, or re-capture.
  *
  * Errors: 0 on success; 1..999 = the cudaError_t of the failing runtime call or launch
  * (the reference only printf()s launch errors, cuh:953-957); >= 1000 = PCT_MSDA_E_* below.
@@ -189,7 +191,10 @@ int pct_msda_fused_backward(const void* value, const int64_t* spatial_shapes,
  * overlaps H2D copies, kernels and D2H copies, and returns when the results are in host memory.
  * Pinned (page-locked) host buffers give full-duplex copies; pageable buffers work but serialise.
  * spatial_shapes / level_start_index are HOST arrays here.  One call at a time per context;
- * contexts are independent (one per device / thread).
+ * contexts are independent (one per device / thread).  Every entry point below works on the
+ * context's device and restores the calling thread's current device before it returns; when a
+ * call fails, its streams are drained first, so the caller's host buffers are no longer in use,
+ * and a failed growth of the staging buffers leaves the context empty but reusable.
  */
 typedef struct pct_msda_host_ctx pct_msda_host_ctx;
 

@@ -9,12 +9,15 @@ Two independent restatements of the reference's result live here
 * ``forward_c`` / ``backward_c`` -- ctypes bindings of ``msda_oracle.c`` (closed form of
   OPS/src/cuda/ms_deform_im2col_cuda.cuh:38-164,258-303).  Fast, fp64 or literal fp32,
   analytic gradients, deterministic summation order.
+* ``reference_core`` -- the reference's own ``ms_deform_attn_core_pytorch`` run from the bytecode
+  in ``oracle/_ref/`` (built by ``oracle/build_ref.py`` from ``/root/reference``; git-ignored).
 * ``core_grid_sample`` -- the algorithm of OPS/functions/ms_deform_attn_func.py:52-72
   (``ms_deform_attn_core_pytorch``): per-level ``F.grid_sample(bilinear, zeros,
   align_corners=False)`` on ``2*loc-1`` followed by the attention-weighted sum.  This is what
   the reference executes on a CPU (the reference has no native CPU kernel,
   OPS/src/cpu/ms_deform_attn_cpu.cpp:22-45), so it is the leg timed as ``cpu_baseline`` and by
-  ``bench.py --impl reference`` (kind "port").
+  ``bench.py --impl reference`` when ``oracle/_ref/`` is absent (kind "port"; with it the
+  reference's own function is timed, kind "reference").
 
 Parity status: pinned.  ``tests/test_oracle.py`` checks both against golden vectors produced
 by the reference's own function (``tests/golden/make_golden.py``).
@@ -38,6 +41,37 @@ def build(force: bool = False) -> str:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return _LIB_PATH
+
+
+_REF_PYC = os.path.join(_HERE, "_ref", "ms_deform_attn_func.pyc")
+_ref_core = False   # False = not tried yet, None = unavailable
+
+
+def reference_core():
+    """The reference's OWN ``ms_deform_attn_core_pytorch`` (func.py:52-72), executed from the
+    bytecode ``oracle/build_ref.py`` compiled out of ``/root/reference`` -- or None when
+    ``oracle/_ref/`` was not built (then callers use ``core_grid_sample``, the in-repo port).
+    The file imports the reference's CUDA extension at module level (func.py:20-29); an empty
+    stand-in module satisfies that import, the CPU function never touches it."""
+    global _ref_core
+    if _ref_core is not False:
+        return _ref_core
+    _ref_core = None
+    if os.path.exists(_REF_PYC):
+        import importlib.machinery
+        import importlib.util
+        import sys
+        import types
+        sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+        try:
+            loader = importlib.machinery.SourcelessFileLoader("pctrans_reference_ms_deform_attn_func", _REF_PYC)
+            spec = importlib.util.spec_from_loader(loader.name, loader)
+            mod = importlib.util.module_from_spec(spec)
+            loader.exec_module(mod)
+            _ref_core = mod.ms_deform_attn_core_pytorch
+        except Exception:   # bytecode of another interpreter version: treat as not built
+            _ref_core = None
+    return _ref_core
 
 
 def _load():

@@ -63,8 +63,23 @@ int realloc_dev(void** p, size_t bytes) {
   return 0;
 }
 
+void free_slots(pct_msda_host_ctx* c) {
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& s = c->slots[i];
+    void** bufs[] = {&s.value, &s.loc, &s.attn, &s.gout, &s.out, &s.gvalue, &s.gloc, &s.gattn, &s.ws};
+    for (void** b : bufs) {
+      if (*b) cudaFree(*b);
+      *b = nullptr;
+    }
+  }
+  c->cap_value = c->cap_loc = c->cap_attn = c->cap_io = c->cap_ws = 0;
+  c->has_bwd = false;
+}
+
 // Staging buffers only ever grow; when any of them is too small every slot is reallocated at the
-// new sizes (after draining the streams -- nothing is in flight between calls anyway).
+// new sizes (after draining the streams -- nothing is in flight between calls anyway).  The new
+// capacities are committed only when EVERY allocation succeeded; a failure half way frees all
+// slots and resets the capacities, so the next call starts from a clean context.
 int ensure_capacity(pct_msda_host_ctx* c, size_t b_value, size_t b_loc, size_t b_attn, size_t b_io,
                     size_t b_ws, bool backward) {
   const bool fits = b_value <= c->cap_value && b_loc <= c->cap_loc && b_attn <= c->cap_attn &&
@@ -74,29 +89,59 @@ int ensure_capacity(pct_msda_host_ctx* c, size_t b_value, size_t b_loc, size_t b
   PCT_CUDA(cudaStreamSynchronize(c->s_run));
   PCT_CUDA(cudaStreamSynchronize(c->s_out));
   auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
-  c->cap_value = mx(c->cap_value, b_value);
-  c->cap_loc = mx(c->cap_loc, b_loc);
-  c->cap_attn = mx(c->cap_attn, b_attn);
-  c->cap_io = mx(c->cap_io, b_io);
-  c->cap_ws = mx(c->cap_ws, backward ? b_ws : 0);
-  c->has_bwd = c->has_bwd || backward;
-  for (int i = 0; i < kSlots; ++i) {
+  const size_t n_value = mx(c->cap_value, b_value), n_loc = mx(c->cap_loc, b_loc);
+  const size_t n_attn = mx(c->cap_attn, b_attn), n_io = mx(c->cap_io, b_io);
+  const size_t n_ws = mx(c->cap_ws, backward ? b_ws : 0);
+  const bool n_bwd = c->has_bwd || backward;
+  int rc = 0;
+  for (int i = 0; i < kSlots && !rc; ++i) {
     Slot& s = c->slots[i];
-    int rc;
-    if ((rc = realloc_dev(&s.value, c->cap_value))) return rc;
-    if ((rc = realloc_dev(&s.loc, c->cap_loc))) return rc;
-    if ((rc = realloc_dev(&s.attn, c->cap_attn))) return rc;
-    if ((rc = realloc_dev(&s.out, c->cap_io))) return rc;
-    if (c->has_bwd) {
-      if ((rc = realloc_dev(&s.gout, c->cap_io))) return rc;
-      if ((rc = realloc_dev(&s.gvalue, c->cap_value))) return rc;
-      if ((rc = realloc_dev(&s.gloc, c->cap_loc))) return rc;
-      if ((rc = realloc_dev(&s.gattn, c->cap_attn))) return rc;
-      if ((rc = realloc_dev(&s.ws, c->cap_ws))) return rc;
+    if (!rc) rc = realloc_dev(&s.value, n_value);
+    if (!rc) rc = realloc_dev(&s.loc, n_loc);
+    if (!rc) rc = realloc_dev(&s.attn, n_attn);
+    if (!rc) rc = realloc_dev(&s.out, n_io);
+    if (n_bwd) {
+      if (!rc) rc = realloc_dev(&s.gout, n_io);
+      if (!rc) rc = realloc_dev(&s.gvalue, n_value);
+      if (!rc) rc = realloc_dev(&s.gloc, n_loc);
+      if (!rc) rc = realloc_dev(&s.gattn, n_attn);
+      if (!rc) rc = realloc_dev(&s.ws, n_ws);
     }
   }
+  if (rc) {
+    free_slots(c);
+    cudaGetLastError();   // clear the sticky allocation error for the caller's next call
+    return rc;
+  }
+  c->cap_value = n_value; c->cap_loc = n_loc; c->cap_attn = n_attn; c->cap_io = n_io; c->cap_ws = n_ws;
+  c->has_bwd = n_bwd;
   return 0;
 }
+
+// Every entry point works on the context's device and puts the caller's current device back on
+// every exit path (the Python wrapper may be destroyed by the garbage collector at any time).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return (int)e;
+    if (prev != device) {
+      e = cudaSetDevice(device);
+      if (e != cudaSuccess) return (int)e;
+      switched = true;
+    }
+    return 0;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+int pipeline_body(pct_msda_host_ctx* c, const void* value, const int64_t* shapes, const int64_t* lsi,
+                  const void* loc, const void* attn, const void* grad_out, void* out,
+                  void* grad_value, void* grad_loc, void* grad_attn, int N, int S, int M, int D,
+                  int L, int Lq, int P, int dtype);
 
 int run_pipeline(pct_msda_host_ctx* c, const void* value, const int64_t* shapes, const int64_t* lsi,
                  const void* loc, const void* attn, const void* grad_out, void* out,
@@ -109,7 +154,26 @@ int run_pipeline(pct_msda_host_ctx* c, const void* value, const int64_t* shapes,
   if (N == 0) return 0;
   if (!shapes || !lsi || !out || (S && !value) || (Lq && (!loc || !attn))) return PCT_MSDA_E_NULL_POINTER;
   if (backward && (!grad_value || !grad_loc || !grad_attn)) return PCT_MSDA_E_NULL_POINTER;
-  PCT_CUDA(cudaSetDevice(c->device));
+  DeviceGuard guard;
+  int rc = guard.enter(c->device);
+  if (rc) return rc;
+  rc = pipeline_body(c, value, shapes, lsi, loc, attn, grad_out, out, grad_value, grad_loc, grad_attn,
+                     N, S, M, D, L, Lq, P, dtype);
+  if (rc) {
+    // an error in the middle of the loop: copies to / from the caller's host buffers may still be
+    // in flight -- drain the three streams before the caller gets its buffers back
+    cudaStreamSynchronize(c->s_in);
+    cudaStreamSynchronize(c->s_run);
+    cudaStreamSynchronize(c->s_out);
+  }
+  return rc;
+}
+
+int pipeline_body(pct_msda_host_ctx* c, const void* value, const int64_t* shapes, const int64_t* lsi,
+                  const void* loc, const void* attn, const void* grad_out, void* out,
+                  void* grad_value, void* grad_loc, void* grad_attn, int N, int S, int M, int D,
+                  int L, int Lq, int P, int dtype) {
+  const bool backward = grad_out != nullptr;
 
   const size_t es = esize(dtype), ls = lsize(dtype);
   const size_t img_value = (size_t)S * M * D * es;
@@ -190,7 +254,8 @@ extern "C" {
 int pct_msda_host_ctx_create(pct_msda_host_ctx** ctx, int device, int chunk_images) {
   if (!ctx) return PCT_MSDA_E_NULL_POINTER;
   *ctx = nullptr;
-  PCT_CUDA(cudaSetDevice(device));
+  DeviceGuard guard;
+  if (int rc = guard.enter(device)) return rc;
   pct_msda_host_ctx* c = new (std::nothrow) pct_msda_host_ctx();
   if (!c) return (int)cudaErrorMemoryAllocation;
   c->device = device;
@@ -213,13 +278,12 @@ int pct_msda_host_ctx_create(pct_msda_host_ctx** ctx, int device, int chunk_imag
 
 void pct_msda_host_ctx_destroy(pct_msda_host_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard guard;
+  guard.enter(c->device);
   if (c->s_out) cudaStreamSynchronize(c->s_out);
+  free_slots(c);
   for (int i = 0; i < kSlots; ++i) {
     Slot& s = c->slots[i];
-    void* bufs[] = {s.value, s.loc, s.attn, s.gout, s.out, s.gvalue, s.gloc, s.gattn, s.ws};
-    for (void* b : bufs)
-      if (b) cudaFree(b);
     if (s.loaded) cudaEventDestroy(s.loaded);
     if (s.done) cudaEventDestroy(s.done);
     if (s.free_ev) cudaEventDestroy(s.free_ev);

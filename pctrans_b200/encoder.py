@@ -77,6 +77,7 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         self.linear2 = nn.Linear(d_ffn, d_model)
         self.dropout3 = nn.Dropout(dropout)
         self.norm2 = nn.LayerNorm(d_model)
+        linear_tc.install_invalidation_hooks(self)
 
     @staticmethod
     def with_pos_embed(tensor, pos):
@@ -140,7 +141,11 @@ class MSDeformAttnTransformerEncoder(nn.Module):
             cache = self.__dict__.setdefault("_ref_cache", {})
             key = (tuple(shapes_hint), src.shape[0], str(src.device))
             if key not in cache:
-                cache[key] = self.get_reference_points(shapes_hint, valid_ratios, device=src.device)
+                # built outside inference mode: a cached inference tensor could not be saved for
+                # backward by a later training step
+                with torch.inference_mode(False):
+                    cache[key] = self.get_reference_points(
+                        shapes_hint, torch.ones_like(valid_ratios), device=src.device)
             ref = cache[key]
         else:
             ref = self.get_reference_points(spatial_shapes if shapes_hint is None else shapes_hint,
@@ -163,6 +168,7 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         self._reset_parameters()
 
     def _reset_parameters(self):
+        linear_tc.invalidate()   # the initialisers below may write through .data
         for p in self.parameters():
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
@@ -178,9 +184,10 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         cache = self.__dict__.setdefault("_level_cache", {})
         key = (shapes, str(device))
         if key not in cache:
-            spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=device)
-            level_start_index = torch.cat(
-                (spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+            with torch.inference_mode(False):   # see _ref_cache: never cache inference tensors
+                spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=device)
+                level_start_index = torch.cat(
+                    (spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
             cache[key] = (spatial_shapes, level_start_index)
         return cache[key]
 

@@ -24,13 +24,32 @@ from torch.autograd.function import once_differentiable
 from .. import _cabi
 
 ENABLED = True            # process-wide switch (tests flip it to compare against torch)
+_EPOCH = 0                # bumped by invalidate(): every cached packed weight becomes stale
+
+
+def invalidate() -> None:
+    """Drop every cached packed weight (they are re-packed lazily on next use).
+
+    The cache below notices in-place updates through autograd's version counter (optimizer
+    steps, ``copy_`` under ``no_grad``) and reallocation -- but a write through ``.data``
+    (``p.data.mul_()``, EMA swaps, hand-written checkpoint loaders) changes neither.  The modules
+    of this package call ``invalidate()`` from ``_reset_parameters``, after ``load_state_dict`` and
+    on every ``train()`` / ``eval()`` switch; code that writes weights through ``.data`` outside of
+    those must call it too."""
+    global _EPOCH
+    _EPOCH += 1
+
+
+def install_invalidation_hooks(module: torch.nn.Module) -> None:
+    """``load_state_dict`` into ``module`` drops the cached packed weights."""
+    module.register_load_state_dict_post_hook(lambda mod, incompatible_keys: invalidate())
 
 
 def packed_weight(weight: torch.Tensor, transposed: bool = False) -> torch.Tensor:
     """Packed 3xTF32 operand of ``weight`` (or of ``weight.T`` for the input gradient), cached
-    until the weight changes in place (optimizer step) or is reallocated."""
+    until the weight changes in place (optimizer step), is reallocated, or ``invalidate()`` runs."""
     slot = weight.__dict__.setdefault("_pct_packed", {})
-    tag = (weight._version, weight.data_ptr(), weight.device)
+    tag = (weight._version if not weight.is_inference() else -1, weight.data_ptr(), weight.device, _EPOCH)
     hit = slot.get(transposed)
     if hit is not None and hit[0] == tag:
         return hit[1]

@@ -24,6 +24,8 @@ from __future__ import annotations
 import math
 import warnings
 
+import weakref
+
 import torch
 from torch import nn
 
@@ -65,9 +67,15 @@ class MSDeformAttn(nn.Module):
         self.attention_weights = nn.Linear(d_model, samples)
         self.value_proj = nn.Linear(d_model, d_model)
         self.output_proj = nn.Linear(d_model, d_model)
+        linear_tc.install_invalidation_hooks(self)
         self._reset_parameters()
 
+    def train(self, mode: bool = True):
+        linear_tc.invalidate()   # weights may have been swapped (EMA, .data writes) between phases
+        return super().train(mode)
+
     def _reset_parameters(self):
+        linear_tc.invalidate()
         with torch.no_grad():
             self.sampling_offsets.weight.zero_()
             self.sampling_offsets.bias = nn.Parameter(
@@ -98,10 +106,16 @@ class MSDeformAttn(nn.Module):
     def _check_lengths(self, spatial_shapes, len_in):
         """``sum_l H_l*W_l == Len_in`` (mod.py:96).  Reading the shapes back is a device sync, so a
         given shapes tensor is checked once, not in every layer of every step."""
-        key = (spatial_shapes.data_ptr(), spatial_shapes._version, len_in)
-        if self.__dict__.get("_lengths_ok") != key:
-            assert int(spatial_shapes.prod(1).sum()) == len_in
-            self.__dict__["_lengths_ok"] = key
+        seen = self.__dict__.get("_lengths_ok")
+        # keyed on the tensor OBJECT (weak reference), not on its address or version counter: an
+        # address can be reused by another tensor, and inference tensors have no version counter
+        if seen is not None and seen[0]() is spatial_shapes and seen[1] == len_in:
+            return
+        total = int(spatial_shapes.prod(1).sum())
+        if total != len_in:
+            raise ValueError(f"input_spatial_shapes describe {total} positions but input_flatten has "
+                             f"{len_in} (mod.py:96)")
+        self.__dict__["_lengths_ok"] = (weakref.ref(spatial_shapes), len_in)
 
     def _proj(self, layer, x):
         if self.tensor_core_linears:
