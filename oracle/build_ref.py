@@ -28,7 +28,8 @@ REF_ROOT = os.environ.get("PCTRANS_REFERENCE", "/root/reference")
 REF_FILE = os.path.join(REF_ROOT, "connectomics", "model", "maskformer_block", "pixel_decoder", "ops",
                         "functions", "ms_deform_attn_func.py")
 OUT_DIR = os.path.join(HERE, "_ref")
-PYC = os.path.join(OUT_DIR, "ms_deform_attn_func.pyc")
+# not named *.pyc: snapshot tools treat that suffix as interpreter junk and drop it
+PYC = os.path.join(OUT_DIR, "ms_deform_attn_func.bytecode")
 META = os.path.join(OUT_DIR, "provenance.json")
 
 

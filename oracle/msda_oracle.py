@@ -43,7 +43,7 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
-_REF_PYC = os.path.join(_HERE, "_ref", "ms_deform_attn_func.pyc")
+_REF_PYC = os.path.join(_HERE, "_ref", "ms_deform_attn_func.bytecode")
 _ref_core = False   # False = not tried yet, None = unavailable
 
 
@@ -58,18 +58,20 @@ def reference_core():
         return _ref_core
     _ref_core = None
     if os.path.exists(_REF_PYC):
-        import importlib.machinery
         import importlib.util
+        import marshal
         import sys
         import types
         sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
         try:
-            loader = importlib.machinery.SourcelessFileLoader("pctrans_reference_ms_deform_attn_func", _REF_PYC)
-            spec = importlib.util.spec_from_loader(loader.name, loader)
-            mod = importlib.util.module_from_spec(spec)
-            loader.exec_module(mod)
+            with open(_REF_PYC, "rb") as f:
+                data = f.read()
+            if data[:4] != importlib.util.MAGIC_NUMBER:
+                raise ImportError("bytecode of another interpreter version")
+            mod = types.ModuleType("pctrans_reference_ms_deform_attn_func")
+            exec(marshal.loads(data[16:]), mod.__dict__)   # 16-byte .pyc header, then the code object
             _ref_core = mod.ms_deform_attn_core_pytorch
-        except Exception:   # bytecode of another interpreter version: treat as not built
+        except Exception:   # treat as not built
             _ref_core = None
     return _ref_core
 

@@ -18,6 +18,30 @@ class _OracleFunction:
         return oracle.core_grid_sample(value, shapes, loc, attn)
 
 
+class _OracleFp32Function(torch.autograd.Function):
+    """MSDeformAttnFunction with the C oracle as arithmetic, in the dtype of ``value``: the literal
+    fp32 instantiation rounds the pixel coordinate exactly like the kernels (cuh:290-291), so both
+    legs sample the SAME bilinear cells even for points within rounding distance of a grid line --
+    which a grid_sample formulation (different coordinate arithmetic) does not guarantee; with
+    fp64 tensors it is the ground truth both fp32 evaluations are measured against."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, lsi, loc, attn, im2col_step):
+        import numpy as np
+        ctx.save_for_backward(value, shapes, lsi, loc, attn)
+        ctx.np_dtype = np.float64 if value.dtype == torch.float64 else np.float32
+        out = oracle.forward_c(value, shapes, lsi, loc, attn, dtype=ctx.np_dtype)
+        return torch.from_numpy(out).to(value.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        value, shapes, lsi, loc, attn = ctx.saved_tensors
+        gv, gl, ga = oracle.backward_c(value, shapes, lsi, loc, attn, grad_out.contiguous(), dtype=ctx.np_dtype)
+        dev = value.device
+        return (torch.from_numpy(gv).to(dev), None, None, torch.from_numpy(gl).to(dev),
+                torch.from_numpy(ga).to(dev), None)
+
+
 def _set_fused(model, on):
     """CUDA leg: fused-prologue kernels; oracle leg: the module composes softmax / locations in
     PyTorch and calls the (monkeypatched) Function."""
@@ -135,23 +159,43 @@ def test_config4_bbbc_encoder_forward_backward(monkeypatch):
         mem.square().mean().backward()
         return mem.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
 
-    mem, grads = run()
-    monkeypatch.setattr(mod_file, "MSDeformAttnFunction", _OracleFunction)
+    mem_fused, grads_fused = run()          # product path: fused-prologue kernels
     _set_fused(model, False)
-    mem_ref, grads_ref = run()
+    mem, grads = run()                      # the unfused Function (locations / weights from PyTorch)
+    monkeypatch.setattr(mod_file, "MSDeformAttnFunction", _OracleFp32Function)
+    mem_ref, grads_ref = run()              # same module code, op = literal-fp32 C oracle (same cells)
     assert mem.shape == (2, 7481, 256)
     assert float((mem - mem_ref).abs().max() / mem_ref.abs().max()) <= 1e-5
-    for k in grads:
-        scale = float(grads_ref[k].abs().max())
-        if scale == 0.0:
-            assert float(grads[k].abs().max()) == 0.0
-            continue
-        # two fp32 formulations through 6 layers: a handful of samples that sit within rounding
-        # distance of a pixel-grid line take different one-sided location derivatives, and summed
-        # parameter gradients with heavy cancellation (level_embed) show it; the op-level gradient
-        # parity is pinned tightly in test_gpu_parity.py
-        err = float((grads[k] - grads_ref[k]).norm() / grads_ref[k].norm())
-        assert err <= 3e-2, (k, err)
+    assert float((mem_fused - mem_ref).abs().max() / mem_ref.abs().max()) <= 1e-5
+
+    # Ground truth: the same encoder in fp64 (fp64 GEMMs, fp64 C oracle as the op).  Parameter
+    # gradients are sums over ~15 000 positions with heavy cancellation, so two fp32 evaluations
+    # differ from each other by far more than 1e-4 on some tensors (sampling_offsets.weight of the
+    # late layers: ~1e-2) -- the honest bar is that the CUDA path is as close to the truth as a
+    # literal fp32 evaluation of the reference's own formulas, tensor by tensor.
+    model.double()
+    srcs, pos = [s.double() for s in srcs], [p.double() for p in pos]
+    _, grads64 = run()
+
+    def errors(got):
+        out = {}
+        for k, ref in grads64.items():
+            scale = float(ref.abs().max())
+            if scale == 0.0:
+                assert float(got[k].abs().max()) == 0.0, k
+                continue
+            out[k] = float((got[k].double() - ref).norm() / ref.norm())
+        return out
+
+    e_ref32, e_cuda, e_fused = errors(grads_ref), errors(grads), errors(grads_fused)
+    for k in e_ref32:
+        bar = max(1e-3, 4.0 * e_ref32[k])
+        assert e_cuda[k] <= bar, ("unfused", k, e_cuda[k], e_ref32[k])
+        assert e_fused[k] <= bar, ("fused", k, e_fused[k], e_ref32[k])
+    worst = max(e_cuda, key=e_cuda.get)
+    print(f"config 4 parameter gradients vs fp64: worst CUDA {worst} {e_cuda[worst]:.2e} "
+          f"(literal fp32 oracle on the same tensor {e_ref32[worst]:.2e}); "
+          f"median CUDA {sorted(e_cuda.values())[len(e_cuda) // 2]:.2e}")
 
 
 def test_linear_helpers_on_cpu_are_plain_torch():
@@ -167,3 +211,59 @@ def test_linear_helpers_on_cpu_are_plain_torch():
                        torch.relu(lin(x) + res))
     assert torch.equal(linear_tc.linear_residual_layernorm(x, lin.weight, lin.bias, res, norm),
                        norm(res + lin(x)))
+
+
+@pytest.mark.gpu
+def test_inference_mode_then_training():
+    """The reference's module works under torch.inference_mode(); ours caches level / reference
+    tensors across calls, and those caches must not hold inference tensors (they could not be
+    saved for backward by a later training step)."""
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    model = enc.MSDeformAttnTransformerEncoderOnly(d_model=128, nhead=8, num_encoder_layers=2,
+                                                   dim_feedforward=256, dropout=0.0,
+                                                   num_feature_levels=3).to(dev)
+    g = torch.Generator().manual_seed(1)
+    srcs = [torch.randn(2, 128, h, w, generator=g).to(dev) for h, w in ((4, 5), (8, 10), (16, 20))]
+    pe = enc.PositionEmbeddingSine(64, normalize=True)
+    pos = [pe(s) for s in srcs]
+    with torch.inference_mode():
+        a = model(srcs, pos)[0]
+    with torch.no_grad():
+        b = model(srcs, pos)[0]
+    assert torch.equal(a, b)
+    out = model(srcs, pos)[0]                 # training step after the inference-mode call
+    out.square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.gpu
+def test_packed_weight_cache_sees_data_writes_after_invalidate():
+    """functions/linear_tc.py caches the packed 3xTF32 weights.  In-place updates under autograd
+    are seen through the version counter; writes through ``.data`` are not -- the documented
+    contract is ``linear_tc.invalidate()``, which the modules call from load_state_dict, train() /
+    eval() and _reset_parameters."""
+    from pctrans_b200.functions import linear_tc
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    layer = enc.MSDeformAttnTransformerEncoderLayer(d_model=64, d_ffn=128, dropout=0.0, n_levels=2,
+                                                    n_heads=4, n_points=2).to(dev).eval()
+    x = torch.randn(3, 40, 64, device=dev)
+    with torch.no_grad():
+        y0 = layer.forward_ffn(x)
+        layer.linear1.weight.mul_(2.0)                    # version counter: seen
+        y1 = layer.forward_ffn(x)
+        assert not torch.allclose(y0, y1)
+        ref = layer.norm2(x + layer.linear2(torch.relu(torch.nn.functional.linear(x, layer.linear1.weight, layer.linear1.bias))))
+        assert torch.allclose(y1, ref, atol=1e-4)
+        layer.linear1.weight.data.mul_(0.5)               # .data write: invisible to the cache ...
+        linear_tc.invalidate()                            # ... until the documented call
+        assert torch.allclose(layer.forward_ffn(x), y0, atol=1e-4)
+        state = {k: v.clone() for k, v in layer.state_dict().items()}
+        state["linear2.weight"] = state["linear2.weight"] * 3.0
+        layer.load_state_dict(state)                      # hook invalidates
+        ref = layer.norm2(x + layer.linear2(torch.relu(layer.linear1(x))))
+        assert torch.allclose(layer.forward_ffn(x), ref, atol=1e-4)
+        layer.linear2.weight.data.div_(3.0)
+        layer.train().eval()                              # phase switch invalidates
+        assert torch.allclose(layer.forward_ffn(x), y0, atol=1e-4)
