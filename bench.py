@@ -399,21 +399,19 @@ def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dis
     pos = [pe(x) for x in srcs]
     params = list(model.parameters())
     n_params = sum(p.numel() for p in params)
-    side = torch.cuda.Stream() if dist is not None else None
-    flat = torch.empty(n_params, device=dev) if dist is not None else None
+    reducer = None
+    if dist is not None:
+        # DDP-style exchange (model/build.py:89): buckets all-reduced on a side stream as soon as
+        # backward has produced them (pctrans_b200/dist.py)
+        from pctrans_b200.dist import BucketedGradReducer
+        reducer = BucketedGradReducer(params, bucket_bytes=3 << 20)
 
     def step():
         model.zero_grad(set_to_none=True)
         mem = model(srcs, pos)[0]
         mem.float().square().mean().backward()
-        if dist is not None:
-            # DDP-style exchange (model/build.py:89): one flat bucket, on a side stream
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                torch.cat([p.grad.reshape(-1) for p in params], out=flat)
-                dist.all_reduce(flat)
-                flat.div_(world)
-            torch.cuda.current_stream().wait_stream(side)   # the optimizer step would start here
+        if reducer is not None:
+            reducer.finish()        # the optimizer step would start here
         return mem
 
     def barrier():
@@ -435,12 +433,16 @@ def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dis
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     lq = sum(h * w for h, w in pyramid)
+    n_buckets = len(reducer.buckets) if reducer is not None else 0
+    if reducer is not None:
+        reducer.remove()
     del model, srcs, pos
     torch.cuda.empty_cache()
     return {
         "workload": f"{ENCODER_LAYERS}-layer MSDeformAttn encoder training step (fwd+bwd), {pyr_name} pyramid, "
                     f"{batch} images/GPU, d_model {d_model}, fp32 (tensor-core 3xTF32 Linears, fused-prologue op)"
-                    + (f", NCCL all-reduce of {n_params} param grads on a side stream" if dist is not None else ""),
+                    + (f", NCCL all-reduce of {n_params} param grads in {n_buckets} buckets on a side "
+                       "stream, overlapped with the backward" if dist is not None else ""),
         "n_gpus": world, "batch_per_gpu": batch, "global_batch": batch * world, "ms_per_step": ms,
         "images_per_s": world * batch / (ms * 1e-3),
         "queries_per_s": world * batch * lq * ENCODER_LAYERS / (ms * 1e-3),

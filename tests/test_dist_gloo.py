@@ -57,6 +57,24 @@ def _worker(rank, world, port, out_dir):
     assert torch.allclose(grads[1], torch.arange(4, dtype=torch.float32) * 1.5)
     fin = allreduce_mean_([torch.ones(5) * rank], async_op=True)
     fin()
+    # bucketed, overlapped exchange (DDP-style hooks): equals the plain mean of the per-rank grads
+    from pctrans_b200.dist import BucketedGradReducer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 4),
+                              torch.nn.ReLU(), torch.nn.Linear(4, 3))
+    red = BucketedGradReducer(net.parameters(), bucket_bytes=64)
+    assert len(red.buckets) >= 3
+    for step in range(2):            # re-armed after finish()
+        net.zero_grad(set_to_none=True)
+        x = torch.randn(7, 6, generator=torch.Generator().manual_seed(10 * step + rank))
+        net(x).square().sum().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        red.finish()
+        for p, g in zip(net.parameters(), local):
+            both = [torch.zeros_like(g) for _ in range(world)]
+            dist.all_gather(both, g)
+            assert torch.allclose(p.grad, sum(both) / world, atol=1e-6)
+    red.remove()
     dist.barrier()
     dist.destroy_process_group()
 
