@@ -60,6 +60,13 @@ namespace pct {
 #ifndef PCT_PACK_TAPS
 #define PCT_PACK_TAPS 1
 #endif
+// forward: taps travel from the lane that computed them to the lanes of its pair through a small
+// per-warp shared-memory patch (2 broadcast loads per sample) instead of 5 warp shuffles -- used
+// when a pair has 8 or more lanes (fp32 D >= 32: 223 -> 213 us; with 4-lane pairs the shuffles
+// are as fast or faster, profiles/r02_fwd_smem_taps.log)
+#ifndef PCT_FWD_SMEM_TAPS
+#define PCT_FWD_SMEM_TAPS 1
+#endif
 #ifndef PCT_TAP_BLOCK_BWD
 #define PCT_TAP_BLOCK_BWD 4
 #endif
@@ -383,6 +390,15 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   constexpr int D = LPP * VE;
   constexpr int PPW = 32 / LPP;  // pairs per warp
   __shared__ int4 s_tab[kMaxFastSamples];
+  constexpr bool kSmemTaps = PCT_FWD_SMEM_TAPS && PCT_PACK_TAPS && LPP >= 8;
+#if PCT_FWD_SMEM_TAPS
+  // Tap exchange patch of this warp: slot (pair, sample-of-round) holds {w00,w01,w10,w11} and the
+  // packed corner word.  A pair's slots are padded to LPP+1 so that the PPW pairs of a warp read
+  // different banks (the LPP lanes of a pair read the same slot: a broadcast).
+  constexpr int kSlots = kSmemTaps ? PPW * (LPP + 1) : 1;
+  __shared__ float4 s_tapw[kSmemTaps ? kVecThreads / 32 : 1][kSlots];
+  __shared__ int s_tapo[kSmemTaps ? kVecThreads / 32 : 1][kSlots];
+#endif
   fill_level_table(s_tab, shapes, lsi, L, P);
   __syncthreads();
 
@@ -394,6 +410,10 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   // the launcher guarantees n_tasks < 2^31, so the per-task index math stays 32-bit
   const int n_tasks = N * M * tasks_per_stream;
   TaskIter iter(sched, n_tasks, warp, nwarps, lane);
+#if PCT_FWD_SMEM_TAPS
+  float4* const my_w = &s_tapw[kSmemTaps ? warp : 0][kSmemTaps ? grp * (LPP + 1) : 0];
+  int* const my_o = &s_tapo[kSmemTaps ? warp : 0][kSmemTaps ? grp * (LPP + 1) : 0];
+#endif
 
   for (int t = iter.next(); t >= 0; t = iter.next()) {
     const int stream = t / tasks_per_stream;
@@ -477,8 +497,33 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 #if PCT_PACK_TAPS
       const int word = off | (dx != 0 ? 1 : 0) | (dy != 0 ? 2 : 0);
 #endif
+#if PCT_FWD_SMEM_TAPS && PCT_PACK_TAPS
+      if (kSmemTaps) {
+        __syncwarp();                                 // the previous round's reads are done
+        my_w[sub] = make_float4(w00, w01, w10, w11);
+        my_o[sub] = word;
+        __syncwarp();
+      }
+#endif
       auto tap = [&](const int j, const int pitch) {
-#if PCT_PACK_TAPS
+#if PCT_FWD_SMEM_TAPS && PCT_PACK_TAPS
+        int wd;
+        float b00, b01, b10, b11;
+        if (kSmemTaps) {
+          wd = my_o[j];
+          const float4 wv = my_w[j];
+          b00 = wv.x; b01 = wv.y; b10 = wv.z; b11 = wv.w;
+        } else {
+          wd = __shfl_sync(0xffffffffu, word, j, LPP);
+          b00 = __shfl_sync(0xffffffffu, w00, j, LPP);
+          b01 = __shfl_sync(0xffffffffu, w01, j, LPP);
+          b10 = __shfl_sync(0xffffffffu, w10, j, LPP);
+          b11 = __shfl_sync(0xffffffffu, w11, j, LPP);
+        }
+        const int o = wd & ~3;
+        const int ox = (wd & 1) ? MD : 0;
+        const int oy = (wd & 2) ? pitch : 0;
+#elif PCT_PACK_TAPS
         const int wd = __shfl_sync(0xffffffffu, word, j, LPP);
         const int o = wd & ~3;
         const int ox = (wd & 1) ? MD : 0;
@@ -488,10 +533,12 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         const int ox = __shfl_sync(0xffffffffu, dx, j, LPP);
         const int oy = __shfl_sync(0xffffffffu, dy, j, LPP);
 #endif
+#if !(PCT_FWD_SMEM_TAPS && PCT_PACK_TAPS)
         const float b00 = __shfl_sync(0xffffffffu, w00, j, LPP);
         const float b01 = __shfl_sync(0xffffffffu, w01, j, LPP);
         const float b10 = __shfl_sync(0xffffffffu, w10, j, LPP);
         const float b11 = __shfl_sync(0xffffffffu, w11, j, LPP);
+#endif
         PCT_CHECK_TAP(o, ox, oy, (m * D + sub * VE), VE, (long long)S * MD);
         // 32-bit corner offsets first: each address is then ONE wide multiply-add off the base
         const int o01 = o + ox, o10 = o + oy, o11 = o10 + ox;
