@@ -1,9 +1,10 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fused.py -q -x 2>&1 | tail -4
-echo "== smem taps (release)"
-timeout 300 python scripts/tune.py --only fwd --flags 0 --dtypes f32,bf16 --regimes R,U
-timeout 300 python scripts/tune.py --only fwd --flags 0 --dtypes f32,bf16 --regimes R --d-model 128
-echo "== shuffles (variant)"
-export PCTRANS_MSDA_LIB=pctrans_b200/_build/variants/libpctrans_msda_fwd_shfl.so
-timeout 300 python scripts/tune.py --only fwd --flags 0 --dtypes f32,bf16 --regimes R,U
-timeout 300 python scripts/tune.py --only fwd --flags 0 --dtypes f32,bf16 --regimes R --d-model 128
+timeout 300 python scripts/bench_legacy.py > gpurun_out/r02_legacy_vs_new_f32_d32.json 2>gpurun_out/legacy.err; tail -1 gpurun_out/r02_legacy_vs_new_f32_d32.json | cut -c1-600
+timeout 300 python scripts/bench_legacy.py --d-model 128 > gpurun_out/r02_legacy_vs_new_f32_d16.json 2>>gpurun_out/legacy.err; tail -1 gpurun_out/r02_legacy_vs_new_f32_d16.json | cut -c1-600
+timeout 300 python scripts/bench_legacy.py --regime U > gpurun_out/r02_legacy_vs_new_f32_d32_uniform.json 2>>gpurun_out/legacy.err; tail -1 gpurun_out/r02_legacy_vs_new_f32_d32_uniform.json | cut -c1-600
+tail -3 gpurun_out/legacy.err
+timeout 600 python bench.py > gpurun_out/bench_r02_f32.json 2> gpurun_out/bench_r02_f32.err; echo bench rc=$?
+timeout 300 python bench.py --dtype bf16 --no-sub-records > gpurun_out/bench_r02_bf16.json 2>> gpurun_out/bench_r02_f32.err; echo bench bf16 rc=$?
+timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_r02_reference.json 2>> gpurun_out/bench_r02_f32.err; echo ref rc=$?
+timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-sub-records > gpurun_out/plain2.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_ncu_launch_list.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-sub-records > gpurun_out/ncu2.log 2>&1; echo ncu rc=$?
