@@ -39,6 +39,12 @@
  * with itself, nor with more than ~500 other pct_msda launches issued after its capture (the ring
  * would wrap onto its slot): serialise graph replays of this library on one stream, or re-capture.
  *
+ * Numerics: fp32 arithmetic with fp32 accumulation for F32 and BF16 values, fp64 for F64.  grad_value
+ * is accumulated with fp32 global reductions (red.global.add.v4.f32; the reference uses atomicAdd,
+ * cuh:130-157): the summation order varies from run to run unless PCT_MSDA_FLAG_DETERMINISTIC is
+ * set, and -- a property of the hardware instruction, REDG.E.ADD.F32x4.FTZ -- subnormal addends and
+ * sums are flushed to zero (|x| < 1.18e-38; the reference's atomicAdd flushes them too).
+ *
  * Errors: 0 on success; 1..999 = the cudaError_t of the failing runtime call or launch
  * (the reference only printf()s launch errors, cuh:953-957); >= 1000 = PCT_MSDA_E_* below.
  * There is no CPU fallback of any kind.

@@ -294,6 +294,31 @@ class MSDeformAttnPixelDecoder(nn.Module):
         self.lateral_convs = lateral[::-1]
         self.output_convs = output[::-1]
 
+    @classmethod
+    def from_config(cls, cfg, input_shape):
+        """Constructor arguments from a PCTrans / Mask2Former config node (PD:288-304), without
+        detectron2's ``configurable`` plumbing: ``MSDeformAttnPixelDecoder(**from_config(cfg, shapes))``.
+        ``cfg`` is any object with the ``MODEL.SEM_SEG_HEAD.*`` / ``MODEL.MASK_FORMER.*`` attributes
+        (a yacs / detectron2 CfgNode, a namespace); ``input_shape`` maps feature name to either a
+        ``(channels, stride)`` pair or an object with ``.channels`` / ``.stride`` (ShapeSpec)."""
+        head, mf = cfg.MODEL.SEM_SEG_HEAD, cfg.MODEL.MASK_FORMER
+
+        def pair(v):
+            return (int(v.channels), int(v.stride)) if hasattr(v, "channels") else (int(v[0]), int(v[1]))
+
+        return {
+            "input_shape": {k: pair(v) for k, v in input_shape.items() if k in head.IN_FEATURES},
+            "conv_dim": head.CONVS_DIM,
+            "mask_dim": head.MASK_DIM,
+            "norm": head.NORM,
+            "transformer_dropout": mf.DROPOUT,
+            "transformer_nheads": mf.NHEADS,
+            "transformer_dim_feedforward": 1024,   # fixed for the deformable encoder (PD:298-299)
+            "transformer_enc_layers": head.TRANSFORMER_ENC_LAYERS,
+            "transformer_in_features": head.DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES,
+            "common_stride": head.COMMON_STRIDE,
+        }
+
     def forward_features(self, features: Dict[str, torch.Tensor]):
         """Returns (mask_features, lowest-resolution encoder map, multi_scale_features[:3]) as
         PD:314-360; always fp32 (PD:314,320)."""

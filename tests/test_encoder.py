@@ -79,6 +79,23 @@ def test_state_dict_keys_match_reference_layout():
     assert sum(p.numel() for p in _decoder(256).transformer.parameters()) == 4_393_920
 
 
+def test_from_config_reads_the_pctrans_config_node():
+    """PD:288-304 with the values of configs/CVPPP/CVPPP-PCTrans.yaml (CONVS_DIM 128 etc.)."""
+    from types import SimpleNamespace as NS
+    cfg = NS(MODEL=NS(
+        SEM_SEG_HEAD=NS(IN_FEATURES=["res2", "res3", "res4", "res5"], CONVS_DIM=128, MASK_DIM=128, NORM="GN",
+                        TRANSFORMER_ENC_LAYERS=6, COMMON_STRIDE=4,
+                        DEFORMABLE_TRANSFORMER_ENCODER_IN_FEATURES=["res3", "res4", "res5"]),
+        MASK_FORMER=NS(DROPOUT=0.0, NHEADS=8, DIM_FEEDFORWARD=2048)))
+    shapes = {"res2": NS(channels=256, stride=4), "res3": (512, 8), "res4": (1024, 16),
+              "res5": NS(channels=2048, stride=32), "stem": (64, 2)}
+    kw = enc.MSDeformAttnPixelDecoder.from_config(cfg, shapes)
+    assert kw["transformer_dim_feedforward"] == 1024 and "stem" not in kw["input_shape"]
+    dec = enc.MSDeformAttnPixelDecoder(**kw)
+    assert dec.transformer.d_model == 128 and len(dec.transformer.encoder.layers) == 6
+    assert dec.transformer_in_features == ["res3", "res4", "res5"] and dec.num_fpn_levels == 1
+
+
 def test_decoder_runs_on_cpu_through_oracle(monkeypatch):
     """Host logic only (no GPU): shapes, level order low->high resolution, FPN output grid."""
     monkeypatch.setattr(mod_file, "MSDeformAttnFunction", _OracleFunction)
