@@ -32,7 +32,7 @@ for case in range(n_cases):
     N, Lq = rng.randint(1, 4), rng.randint(1, 300)
     dtype = rng.choice([torch.float32, torch.float32, torch.bfloat16, torch.float64])
     regime = rng.choice(["U", "O", "O"])
-    mode = rng.choice(["plain", "plain", "det", "fused2", "fused4"])
+    mode = rng.choice(["plain", "plain", "det", "fused2", "fused4", "binned", "binned"])
     value, sh, lsi, loc, attn = synth.make_inputs(N, shapes, M=M, D=D, P=P, regime=regime, seed=case, Lq=Lq)
     loc = synth.nudge_off_grid(loc, shapes, eps=2e-3)
     g = torch.randn(N, Lq, M * D, generator=torch.Generator().manual_seed(case + 7)) * rng.choice([1e-3, 1.0, 1e3])
@@ -71,6 +71,8 @@ for case in range(n_cases):
         else:
             det_ok = vec and D <= 128   # deterministic kernels exist for 4-channel lanes (<= 32 lanes) only
             flags = _cabi.FLAG_DETERMINISTIC if (mode == "det" and det_ok) else 0
+            if mode == "binned":   # the cell-binned backward wherever the shape fits it
+                flags = _cabi.FLAG_BWD_BINNED
             lo, at = d(loc, ldt), d(attn, ldt)
             out = _cabi.forward(v, d(sh), d(lsi), lo, at)
             gv, gl, ga = _cabi.backward(v, d(sh), d(lsi), lo, at, go, flags=flags)

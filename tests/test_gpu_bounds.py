@@ -22,7 +22,7 @@ from pctrans_b200 import _cabi, synth
 assert _cabi.LIB_PATH.endswith("_dbg.so"), _cabi.LIB_PATH
 dev = "cuda:0"
 cases = [(((1, 1), (1, 3), (2, 1)), 3), (((7, 9), (4, 5), (2, 3)), 4), (((17, 22), (33, 44)), 2)]
-n = 0
+n = nb = 0
 for shapes, P in cases:
     for D, dt in ((4, torch.float32), (16, torch.float32), (32, torch.float32), (128, torch.float32),
                   (256, torch.float32), (4, torch.bfloat16), (32, torch.bfloat16), (256, torch.bfloat16)):
@@ -40,7 +40,16 @@ for shapes, P in cases:
             assert torch.isfinite(out.float()).all() and torch.isfinite(gv.float()).all()
             assert torch.isfinite(gl).all() and torch.isfinite(ga).all()
             n += 1
+            # the cell-binned backward (its index arithmetic carries device-side asserts in this build)
+            S, L = v.shape[1], len(shapes)
+            if _cabi.backward_plan(3, S, 4, D, L, lq, P, dt, _cabi.FLAG_BWD_BINNED) == 2:
+                bv, bl, ba = _cabi.backward(v, sh.to(dev), lsi.to(dev), lo, at, g, flags=_cabi.FLAG_BWD_BINNED)
+                torch.cuda.synchronize()
+                assert torch.isfinite(bv.float()).all() and torch.isfinite(bl).all() and torch.isfinite(ba).all()
+                assert torch.allclose(bl, gl, rtol=1e-3, atol=1e-3 * float(gl.abs().max()) + 1e-30)
+                nb += 1
 print("bounds-checked cases:", n)
+print("binned cases:", nb)
 """
 
 
@@ -52,6 +61,7 @@ def test_vector_kernels_under_bounds_checking_build():
                           text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
     assert "bounds-checked cases: 72" in proc.stdout, proc.stdout
+    assert "binned cases: 36" in proc.stdout, proc.stdout     # D in {16, 32, 128} fp32, 32 bf16
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
