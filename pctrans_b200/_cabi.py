@@ -39,6 +39,7 @@ FLAG_BF16_ACCUM = 0x8
 FLAG_DETERMINISTIC = 0x10
 FLAG_BWD_PER_TAP = 0x20
 FLAG_BWD_BINNED = 0x40
+FLAG_BF16_F16_ACCUM = 0x80
 
 _lib = None
 _lock = threading.Lock()

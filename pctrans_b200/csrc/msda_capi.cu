@@ -404,6 +404,22 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
     if (!det_fn) return PCT_MSDA_E_UNSUPPORTED;
     bf16_accum = nullptr;
   }
+  int smem_optin = 0;
+  rc = device_smem_optin(&smem_optin);
+  if (rc) return rc;
+  // opt-in for bf16 values on the per-tap vector path: accumulate in a SCALED FP16 image inside the
+  // workspace (half the L2 reduction sectors of the fp32 scratch image, msda_kernels.cuh)
+  BwdLauncher half_fn = nullptr;
+  if ((flags & PCT_MSDA_FLAG_BF16_F16_ACCUM) && value_dtype == PCT_MSDA_BF16 && !det_fn && !bf16_accum &&
+      n_value >= 64 && n_pairs > 0 && !(flags & PCT_MSDA_FLAG_FORCE_GENERIC) &&
+      aligned(grad_sampling_loc, 8) && workspace && aligned(workspace, 16) &&
+      !binned_plan(d, value_dtype, fused ? (flags | PCT_MSDA_FLAG_BWD_PER_TAP) : flags, smem_optin, value,
+                   grad_output, workspace, sampling_loc, attn_weight, grad_sampling_loc)) {
+    const VecPlan p = vec_eligible(d, value_dtype, flags, value, grad_output, workspace, sampling_loc,
+                                   attn_weight);
+    if (p.lanes > 0) half_fn = pick_bwd_half_accum(fused, p);
+  }
+  const size_t half_image = (((size_t)n_value * 2 + 15) / 16) * 16;   // DetScratch follows, 16-aligned
   const size_t need = det_fn ? pct_msda_backward_workspace_bytes_ex(batch, spatial_size, num_heads, channels,
                                                                     value_dtype, flags)
                       : bf16_accum ? 0
@@ -419,9 +435,12 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
   // grad_value accumulates through reductions: clear the accumulator image first.
   const bool ws_accum = det_fn || (value_dtype == PCT_MSDA_BF16 && !bf16_accum);
   void* acc_image = ws_accum ? workspace : grad_value;
-  const size_t acc_bytes = ws_accum ? need : (size_t)n_value * es;
-  pct::DetScratch* det = det_fn ? reinterpret_cast<pct::DetScratch*>((char*)workspace + (size_t)n_value * 8)
-                                : nullptr;
+  const size_t acc_bytes = half_fn    ? half_image + sizeof(pct::DetScratch)
+                           : ws_accum ? need
+                                      : (size_t)n_value * es;
+  pct::DetScratch* det = det_fn    ? reinterpret_cast<pct::DetScratch*>((char*)workspace + (size_t)n_value * 8)
+                         : half_fn ? reinterpret_cast<pct::DetScratch*>((char*)workspace + half_image)
+                                   : nullptr;
   if (acc_bytes > 0) {
     rc = zero_fill(acc_image, acc_bytes, sm_count, st);
     if (rc) return rc;
@@ -459,10 +478,29 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
-  int smem_optin = 0;
-  rc = device_smem_optin(&smem_optin);
-  if (rc) return rc;
-  const int bin_lanes = (det_fn || bf16_accum || fused)
+  if (half_fn) {
+    // scale from max|grad_out|, max sum|attn| and Lq (accumulator and DetScratch were just zeroed)
+    const long long n_go = n_pairs * d.D;
+    const long long cap = (long long)sm_count * 8;
+    long long want = (n_go + 1023) / 1024;
+    pct::msda_absmax_kernel<__nv_bfloat16><<<(int)(want < 1 ? 1 : (want < cap ? want : cap)), 256, 0, st>>>(
+        (const __nv_bfloat16*)grad_output, n_go, det);
+    if (fused) {
+      // the kernel's own softmax produces the weights: every row sums to exactly one
+      const unsigned one = 0x3f800000u;
+      cudaError_t e = cudaMemcpyAsync(&det->rowsum_bits, &one, sizeof(one), cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return (int)e;
+    } else {
+      want = (n_pairs + 255) / 256;
+      pct::msda_attn_rowsum_max_kernel<<<(int)(want < 1 ? 1 : (want < cap ? want : cap)), 256, 0, st>>>(
+          (const float*)attn_weight, n_pairs, d.L * d.P, det);
+    }
+    pct::msda_half_scale_kernel<<<1, 1, 0, st>>>(det, d.Lq);
+    g_launches.fetch_add(fused ? 2 : 3, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int bin_lanes = (det_fn || bf16_accum || half_fn || fused)
                             ? 0
                             : binned_plan(d, value_dtype, flags, smem_optin, value, grad_output, acc_image,
                                           sampling_loc, attn_weight, grad_sampling_loc);
@@ -471,6 +509,7 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
                              sampling_loc, attn_weight, grad_output, acc_image, grad_sampling_loc,
                              grad_attn_weight, d, sm_count, smem_optin, st, flags);
   } else if (BwdLauncher fn = det_fn          ? det_fn
+                              : half_fn       ? half_fn
                               : bf16_accum    ? bf16_accum
                               : vp.lanes == 0 ? nullptr
                                               : pick_bwd(fused, vp, value_dtype)) {
@@ -491,6 +530,14 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
       pct::msda_fixed_to_value_kernel<float><<<grid, 256, 0, st>>>((const long long*)workspace, (float*)grad_value, n_value, det);
     else
       pct::msda_fixed_to_value_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const long long*)workspace, (__nv_bfloat16*)grad_value, n_value, det);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+  }
+  if (half_fn) {
+    long long want = (n_value / 8 + 255) / 256;
+    const long long cap = (long long)sm_count * 16;
+    pct::msda_half_to_bf16_kernel<<<(int)(want < 1 ? 1 : (want < cap ? want : cap)), 256, 0, st>>>(
+        (const __half*)workspace, (__nv_bfloat16*)grad_value, n_value, det);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
   }

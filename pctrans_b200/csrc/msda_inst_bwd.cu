@@ -99,6 +99,22 @@ BwdLauncher pick_bwd_bf16_accum(const VecPlan& plan) {
 }
 
 
+// bf16 values, scaled fp16 accumulator in the workspace (opt-in): 8-byte lanes only
+BwdLauncher pick_bwd_half_accum(bool fused, const VecPlan& plan) {
+  if (plan.vb != 8) return nullptr;
+#define PCT_HALF_CASES(FUSED)                                                               \
+  switch (plan.lanes) {                                                                     \
+    case 2: return launch_bwd_vec<__nv_bfloat16, 2, 8, FUSED, __half>;                      \
+    case 4: return launch_bwd_vec<__nv_bfloat16, 4, 8, FUSED, __half>;                      \
+    case 8: return launch_bwd_vec<__nv_bfloat16, 8, 8, FUSED, __half>;                      \
+    case 16: return launch_bwd_vec<__nv_bfloat16, 16, 8, FUSED, __half>;                    \
+    case 32: return launch_bwd_vec<__nv_bfloat16, 32, 8, FUSED, __half>;                    \
+  }
+  if (fused) { PCT_HALF_CASES(true) } else { PCT_HALF_CASES(false) }
+#undef PCT_HALF_CASES
+  return nullptr;
+}
+
 BwdLauncher pick_bwd(bool fused, const VecPlan& plan, int dtype) {
   return fused ? pick_bwd_t<true>(plan, dtype) : pick_bwd_t<false>(plan, dtype);
 }

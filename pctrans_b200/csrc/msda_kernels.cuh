@@ -24,6 +24,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -190,9 +191,11 @@ struct Scalar<__nv_bfloat16> {
   static __device__ __forceinline__ void store(__nv_bfloat16* p, CT v) { *p = __float2bfloat16_rn((float)v); }
 };
 
-struct DetScratch {       // tail of the deterministic workspace
+struct DetScratch {       // tail of the deterministic / scaled-fp16 workspace
   unsigned int max_bits;  // bit pattern of max |grad_out| (non-negative floats order like ints)
-  float scale;            // 2^(38 - exponent(max))
+  float scale;            // power of two the scattered products are multiplied with
+  unsigned int rowsum_bits;   // scaled-fp16 path: bit pattern of max over (b,q,m) of sum_{l,p} |attn|
+  unsigned int pad;
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -212,7 +215,23 @@ __device__ __forceinline__ void red_add_v4(__nv_bfloat16* p, float a, float b, f
                : "memory");
 }
 
+// Scaled fp16 accumulator (bf16 values, opt-in PCT_MSDA_FLAG_BF16_F16_ACCUM): four channels as one 8-byte packed reduction --
+// half the L2 sector operations of the fp32 scratch image, which is what bounds the per-tap
+// backward.  The products arrive pre-multiplied by a power-of-two scale chosen from max|grad_out|,
+// max sum|attn| and Lq so that no sum can overflow fp16 (msda_half_scale_kernel); fp16 keeps 11
+// significand bits in the running sum where the bf16 accumulator keeps 8.
+__device__ __forceinline__ void red_add_v4(__half* p, float a, float b, float c, float d) {
+  const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+  asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(p),
+               "r"(*reinterpret_cast<const unsigned*>(&lo)),
+               "r"(*reinterpret_cast<const unsigned*>(&hi))
+               : "memory");
+}
+
 __device__ __forceinline__ void red_add_v4(long long*, float, float, float, float) {}  // unused (kDet path scatters itself)
+
+template <typename ACC> struct AccScaled { static constexpr bool value = false; };
+template <> struct AccScaled<__half> { static constexpr bool value = true; };
 
 // ---------------------------------------------------------------------------------------------
 // Bilinear taps (cuh:45-58 geometry, cuh:61-83 per-corner bounds, cuh:293 in-range predicate).
@@ -642,8 +661,17 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     // deterministic mode: this lane scatters channels {i*LPP + sub} so that the LPP lanes of a
     // pair cover contiguous 8-byte accumulators (whole sectors) with each integer reduction
     constexpr bool kDet = sizeof(ACC) == 8;
+    constexpr bool kScaled = AccScaled<ACC>::value;   // fp16 accumulator: scatter scale * grad_out
     float gs[VE];
     ACC* grow = gacc;
+    float gsc[VE];
+#pragma unroll
+    for (int i = 0; i < VE; ++i) gsc[i] = go[i];
+    if (kScaled) {
+      const float scale = det->scale;
+#pragma unroll
+      for (int i = 0; i < VE; ++i) gsc[i] = go[i] * scale;
+    }
     if (kDet) {
       const float scale = det->scale;
 #pragma unroll
@@ -797,10 +825,10 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         } else {
 #pragma unroll
           for (int i = 0; i < VE; i += 4) {
-            if (b00 != 0.f) red_add_v4(gimg + o + i, b00 * go[i], b00 * go[i + 1], b00 * go[i + 2], b00 * go[i + 3]);
-            if (b01 != 0.f) red_add_v4(gimg + o01 + i, b01 * go[i], b01 * go[i + 1], b01 * go[i + 2], b01 * go[i + 3]);
-            if (b10 != 0.f) red_add_v4(gimg + o10 + i, b10 * go[i], b10 * go[i + 1], b10 * go[i + 2], b10 * go[i + 3]);
-            if (b11 != 0.f) red_add_v4(gimg + o11 + i, b11 * go[i], b11 * go[i + 1], b11 * go[i + 2], b11 * go[i + 3]);
+            if (b00 != 0.f) red_add_v4(gimg + o + i, b00 * gsc[i], b00 * gsc[i + 1], b00 * gsc[i + 2], b00 * gsc[i + 3]);
+            if (b01 != 0.f) red_add_v4(gimg + o01 + i, b01 * gsc[i], b01 * gsc[i + 1], b01 * gsc[i + 2], b01 * gsc[i + 3]);
+            if (b10 != 0.f) red_add_v4(gimg + o10 + i, b10 * gsc[i], b10 * gsc[i + 1], b10 * gsc[i + 2], b10 * gsc[i + 3]);
+            if (b11 != 0.f) red_add_v4(gimg + o11 + i, b11 * gsc[i], b11 * gsc[i + 1], b11 * gsc[i + 2], b11 * gsc[i + 3]);
           }
         }
         float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
@@ -928,6 +956,57 @@ __global__ void msda_fixed_to_value_kernel(const long long* __restrict__ acc, T*
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     Scalar<T>::template store<float>(dst + i, __ll2float_rn(acc[i]) * inv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scaled fp16 accumulator (bf16 values): bound, scale, and the conversion back.
+// Any element of grad_value is  sum over (q, l, p) of  w * attn * grad_out  with bilinear weights
+// w <= 1, so  |element| <= max|grad_out| * Lq * max_{b,q,m} sum_{l,p} |attn|.  The scale is the
+// largest power of two that keeps that bound below the fp16 maximum.
+// ---------------------------------------------------------------------------------------------
+static __global__ void msda_attn_rowsum_max_kernel(const float* __restrict__ attn, long long n_pairs,
+                                                   int LP, DetScratch* sc) {
+  unsigned int m = 0u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < LP; ++k) s += fabsf(__ldg(attn + i * LP + k));
+    if (s == s && s <= 3.4e38f) m = max(m, __float_as_uint(s));
+  }
+#pragma unroll
+  for (int w = 16; w > 0; w >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, w));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(&sc->rowsum_bits, m);
+}
+
+static __global__ void msda_half_scale_kernel(DetScratch* sc, int Lq) {
+  const float mx = __uint_as_float(sc->max_bits);
+  const float rows = fmaxf(__uint_as_float(sc->rowsum_bits), 1e-30f);
+  const float bound = mx * (float)Lq * rows;          // no accumulated element can exceed this
+  // bound * scale < 2^15 (fp16 max is 65504): scale = 2^(14 - exponent(bound))
+  sc->scale = (bound > 0.f && bound < 3.0e38f) ? ldexpf(1.f, 14 - ilogbf(bound)) : 1.f;
+}
+
+static __global__ void msda_half_to_bf16_kernel(const __half* __restrict__ acc,
+                                                __nv_bfloat16* __restrict__ dst, long long n,
+                                                const DetScratch* sc) {
+  const float inv = 1.f / sc->scale;   // exact: power of two
+  const long long n8 = n / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = __ldcs(reinterpret_cast<const uint4*>(acc) + i);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(h[k]);
+      v[2 * k] = f.x * inv;
+      v[2 * k + 1] = f.y * inv;
+    }
+    ChanVec<__nv_bfloat16, 16>::store_stream(dst + 8 * i, v);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x)
+      dst[i] = __float2bfloat16_rn(__half2float(acc[i]) * inv);
 }
 
 // fp32 scratch image -> bf16 grad_value (bf16 path only)

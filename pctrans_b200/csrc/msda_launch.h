@@ -47,6 +47,7 @@ int launch_fwd_generic(int dtype, const void* value, const int64_t* shapes, cons
 BwdLauncher pick_bwd(bool fused, const VecPlan& plan, int dtype);
 BwdLauncher pick_bwd_deterministic(const VecPlan& plan, int dtype);
 BwdLauncher pick_bwd_bf16_accum(const VecPlan& plan);
+BwdLauncher pick_bwd_half_accum(bool fused, const VecPlan& plan);   // bf16 values, scaled fp16 accumulator
 int launch_bwd_generic(int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
                        const void* loc, const void* attn, const void* grad_out, void* gacc,
                        void* grad_loc, void* grad_attn, const Dims& d, int sm_count, cudaStream_t st);

@@ -1,0 +1,82 @@
+"""bf16 values: PCT_MSDA_FLAG_BF16_F16_ACCUM accumulates grad_value in a scaled fp16 image (half the
+L2 reduction traffic of the default fp32 scratch image); these cases pin its accuracy, its overflow
+guard and its documented limit (it is opt-in because of that limit)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import msda_oracle as oracle
+from pctrans_b200 import _cabi, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a = a.detach().double().cpu().numpy()
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a.reshape(b.shape) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def run(value, sh, lsi, loc, attn, g, flags=0):
+    return _cabi.backward(value.to(DEV, torch.bfloat16), sh.to(DEV), lsi.to(DEV), loc.to(DEV),
+                          attn.to(DEV), g.to(DEV, torch.bfloat16), flags=flags)
+
+
+@pytest.mark.parametrize("gscale", [1e-4, 1.0, 1e4])
+@pytest.mark.parametrize("shapes,D,regime", [(synth.CVPPP_512, 32, "R"), (synth.BBBC_520x696, 16, "R"),
+                                             (((9, 7), (5, 4)), 64, "O")])
+def test_fp16_accumulator_accuracy(shapes, D, regime, gscale):
+    value, sh, lsi, loc, attn = synth.make_inputs(2, shapes, M=8, D=D, P=4, regime=regime, seed=1,
+                                                  Lq=None if regime == "R" else 300)
+    loc = synth.nudge_off_grid(loc, shapes)
+    g = torch.randn(2, loc.shape[1], 8 * D, generator=torch.Generator().manual_seed(2)) * gscale
+    value, g = value.bfloat16().float(), g.bfloat16().float()
+    gv, gl, ga = run(value, sh, lsi, loc, attn, g, flags=_cabi.FLAG_BF16_F16_ACCUM)
+    fv, fl, fa = run(value, sh, lsi, loc, attn, g)
+    rv, rl, ra = oracle.backward_c(value, sh, lsi, loc, attn, g)
+    e_half, e_f32 = rel(gv, rv), rel(fv, rv)
+    print(f"grad_value error vs fp64 oracle: fp16 accumulator {e_half:.2e}, fp32 scratch {e_f32:.2e}")
+    assert e_half <= 1e-2 and e_f32 <= 1e-2          # BASELINE tolerance for bf16 is 2e-2
+    assert torch.equal(gl, fl) and torch.equal(ga, fa)   # the other gradients do not depend on it
+    assert rel(gl, rl) <= 2e-2 and rel(ga, ra) <= 2e-2
+
+
+@pytest.mark.parametrize("Lq", [1000, 4000])
+def test_fp16_accumulator_cannot_overflow(Lq):
+    """Worst case for the bound: every query puts all of its weight on the same pixel and grad_out
+    is constant and large -> one element receives Lq * max|grad_out| (x a row sum above one).  The
+    scale keeps it finite; up to ~2000 same-signed addends the 11-bit running sum is also accurate,
+    beyond that it stops growing -- the documented reason the mode is opt-in."""
+    shapes = ((8, 8), (4, 4))
+    N, M, D, L, P = 1, 2, 32, 2, 2
+    sh, lsi, S = synth.level_tensors(shapes)
+    value = torch.randn(N, S, M, D).bfloat16().float()
+    loc = torch.full((N, Lq, M, L, P, 2), (3 + 0.5) / 8)        # pixel centre (3, 3) of level 0
+    attn = torch.zeros(N, Lq, M, L, P)
+    attn[..., 0, 0] = 1.75                                        # un-normalised on purpose
+    g = torch.full((N, Lq, M * D), 3.0e4).bfloat16().float()
+    gv, gl, ga = run(value, sh, lsi, loc, attn, g, flags=_cabi.FLAG_BF16_F16_ACCUM)
+    rv, rl, ra = oracle.backward_c(value, sh, lsi, loc, attn, g)
+    assert torch.isfinite(gv.float()).all()
+    assert abs(float(rv.max()) / (1.75 * 3.0e4 * Lq) - 1) < 0.01   # the bound is attained
+    if Lq <= 2000:
+        assert rel(gv, rv) <= 1e-2
+    else:
+        assert rel(gv, rv) > 1e-2      # stagnation; the default fp32 scratch image has no such limit
+        fv, _, _ = run(value, sh, lsi, loc, attn, g)
+        assert rel(fv, rv) <= 1e-2
+
+
+def test_fp16_accumulator_zero_and_negative_weights():
+    shapes = ((6, 5), (3, 4))
+    value, sh, lsi, loc, attn = synth.make_inputs(2, shapes, M=4, D=32, P=3, regime="U", seed=3, Lq=77)
+    attn = (attn - attn.mean()) * 3.0                            # signed, rows do not sum to one
+    loc = synth.nudge_off_grid(loc, shapes)
+    g = torch.randn(2, 77, 128, generator=torch.Generator().manual_seed(4)).bfloat16().float()
+    value = value.bfloat16().float()
+    gv, _, _ = run(value, sh, lsi, loc, attn, g, flags=_cabi.FLAG_BF16_F16_ACCUM)
+    rv, _, _ = oracle.backward_c(value, sh, lsi, loc, attn, g)
+    assert rel(gv, rv) <= 1e-2
+    gz, _, _ = run(value, sh, lsi, loc, attn, torch.zeros_like(g), flags=_cabi.FLAG_BF16_F16_ACCUM)    # max|grad_out| == 0
+    assert not gz.float().any()
