@@ -158,6 +158,21 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
   return pack2(a0 * b0, a1 * b1);
 #endif
 }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 pack2u(unsigned lo, unsigned hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+  unsigned r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
 __device__ __forceinline__ uint4 lds_v4(unsigned addr) {
   uint4 r;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -171,12 +186,9 @@ __device__ __forceinline__ uint2 lds_v2(unsigned addr) {
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-#ifndef PCT_BIN_PREFETCH
-#define PCT_BIN_PREFETCH 0   // columns to the right of a newly opened cell pulled into L1 (measured: no gain)
+#ifndef PCT_BIN_EXPERIMENT
+#define PCT_BIN_EXPERIMENT 0   // timing experiments only (wrong results): 1 = never change cell, 2 = no sweep
 #endif
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
 
 // one lane's 4 channels of a value row as two channel pairs; zeros when `keep` is false (the load
 // is predicated off, so nothing waits on it)
@@ -191,6 +203,9 @@ struct BinVal<float> {
         : "=&l"(v01), "=&l"(v23)
         : "r"(keep), "l"(p));
   }
+  static __device__ __forceinline__ void load_all(const float* p, u64& v01, u64& v23) {
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(v01), "=l"(v23) : "l"(p));
+  }
 };
 template <>
 struct BinVal<__nv_bfloat16> {
@@ -201,6 +216,12 @@ struct BinVal<__nv_bfloat16> {
         "@p ld.global.nc.v2.u32 {%0, %1}, [%3];\n\t}"
         : "=&r"(x), "=&r"(y)
         : "r"(keep), "l"(p));
+    v01 = pack2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+    v23 = pack2(__uint_as_float(y << 16), __uint_as_float(y & 0xffff0000u));
+  }
+  static __device__ __forceinline__ void load_all(const __nv_bfloat16* p, u64& v01, u64& v23) {
+    unsigned x, y;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(p));
     v01 = pack2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
     v23 = pack2(__uint_as_float(y << 16), __uint_as_float(y & 0xffff0000u));
   }
@@ -256,6 +277,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   __shared__ unsigned short s_bound[G + 1];          // first record of every group's segment
   __shared__ int s_nc, s_task;
   __shared__ unsigned int s_total;                   // (non-empty cells << 16) | records
+  __shared__ __align__(16) unsigned int s_zero[16];   // zeros the compiler cannot see through
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARPS = kBinThreads / 32;
@@ -277,6 +299,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     s_nc = cb;
   }
   for (int s = tid; s < LP; s += kBinThreads) s_slvl[s] = (unsigned char)(s / P);
+  if (tid < 16) s_zero[tid] = 0u;
   __syncthreads();
 
   // ---- chunk geometry (identical in every CTA: a function of the shapes only) ----
@@ -293,9 +316,10 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   const int QC = (((Lq + nchunks - 1) / nchunks) + 7) & ~7;   // balanced chunks, <= qc_max
   const int n_tasks = N * nchunks * M;
 
-  uint4* const rec = reinterpret_cast<uint4*>(smem);
-  unsigned char* const go_s = smem + (size_t)QC * LP * 16;
-  unsigned int* const cnt = reinterpret_cast<unsigned int*>(go_s + (size_t)QC * ROWB);
+  // staged grad_out rows first (a compile-time shared address in the sweep), then the records
+  unsigned char* const go_s = smem;
+  uint4* const rec = reinterpret_cast<uint4*>(smem + (size_t)QC * ROWB);
+  unsigned int* const cnt = reinterpret_cast<unsigned int*>(smem + (size_t)QC * ROWB + (size_t)QC * LP * 16);
   unsigned short* const posarr = reinterpret_cast<unsigned short*>(cnt + cnt_words);
 
   const int grp = tid / LPP, sub = tid % LPP;
@@ -465,7 +489,20 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
             if (cell >= 0) {
               pos = atomicAdd(cnt + cell, 1u) & 0xffffu;
               PCT_BIN_ASSERT(pos < (unsigned)ntaps);
-              rec[pos] = make_uint4(((unsigned)cell << 16) | ((unsigned)qq[u] << 6) | ((unsigned)lvl << 3),
+              // the record's first word carries the geometry of its cell, worked out here by ONE
+              // thread per sample: first pixel of the cell clamped into the map (15 bits), which
+              // of its four corners exist (cuh:61-83), level, query
+              const int4 A = *reinterpret_cast<const int4*>(&s_lvl[lvl]);     // cell_base, magic, wp1, W
+              const int2 B = *reinterpret_cast<const int2*>(&s_lvl[lvl].H);   // H, start
+              const int cl = cell - A.x;
+              const int yy = (int)__umulhi((unsigned)cl, (unsigned)A.y);     // y0 + 1
+              const int xx = cl - yy * A.z;                                   // x0 + 1
+              const bool top = yy >= 1, bot = yy <= B.x - 1, lef = xx >= 1, rig = xx <= A.w - 1;
+              const unsigned vm = (top && lef ? 1u : 0u) | (top && rig ? 2u : 0u) |
+                                  (bot && lef ? 4u : 0u) | (bot && rig ? 8u : 0u);
+              const unsigned pix = (unsigned)(B.y + max(yy - 1, 0) * A.w + max(xx - 1, 0));
+              PCT_BIN_ASSERT(pix < 32768u && vm != 0u);
+              rec[pos] = make_uint4((pix << 17) | (vm << 13) | ((unsigned)lvl << 10) | (unsigned)qq[u],
                                     __float_as_uint(lw), __float_as_uint(lh), __float_as_uint(aw[u]));
             }
             posarr[k] = (unsigned short)pos;
@@ -477,126 +514,151 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     __syncthreads();
 
     // ---- sweep: every lane group walks its segment of the cell-sorted records ----
+    // Bilinear-basis form.  With value(lw, lh) = u0 + lw u1 + lh u2 + lw lh u3  (u0 = v00,
+    // u1 = v01 - v00, u2 = v10 - v00, u3 = v11 - v10 - v01 + v00) the three per-sample results are
+    //   val . grad_out = e0 + lw e1 + lh e2 + lw lh e3,   grad_w_weight = e1 + lh e3,
+    //   grad_h_weight  = e2 + lw e3                        (e_k = <grad_out, u_k>; cuh:128-161)
+    // and the four corner sums of grad_value are differences of the four running sums
+    //   A0 = sum a g, A1 = sum a lw g, A2 = sum a lh g, A3 = sum a lw lh g   (cuh:118-158),
+    // so the per-record work needs no corner weights at all; the change of basis is paid once per
+    // CELL (when its rows are loaded / its sums are flushed), and the cell's geometry comes
+    // ready-made in the record's first word.
     {
-      const int beg = s_bound[grp], end = s_bound[grp + 1];
-      const long long img_off = ((long long)b * S * M + m) * D + sub * VE;
-      unsigned long long vbase = reinterpret_cast<unsigned long long>(value + img_off);
-      unsigned long long gbase = reinterpret_cast<unsigned long long>(gacc + img_off);
-      asm volatile("" : "+l"(vbase), "+l"(gbase));
-      const T* vimg = reinterpret_cast<const T*>(vbase);
-      float* gimg = reinterpret_cast<float*>(gbase);
-      // 32-bit shared-window addresses: record r at rec_sa + 16 r, this lane's part of grad_out
-      // row q at go_sa + ROWB q
-      const unsigned rec_sa = (unsigned)__cvta_generic_to_shared(rec);
-      const unsigned go_sa = (unsigned)__cvta_generic_to_shared(go_s) + (unsigned)(sub * VB);
+      // (the launcher guarantees N*S*M*D < 2^31: one 32-bit element offset serves value and gacc)
+      const int img_off = (b * S * M + m) * D + sub * VE;
+      unsigned go_sa = (unsigned)__cvta_generic_to_shared(go_s) + (unsigned)(sub * VB);
+      unsigned sub4 = (unsigned)sub * 4u;
+      asm volatile("" : "+r"(go_sa), "+r"(sub4));   // kept in registers, not re-derived per record
       const unsigned lvl_sa = (unsigned)__cvta_generic_to_shared(s_lvl);
+      const unsigned zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
+      unsigned rp = (unsigned)__cvta_generic_to_shared(rec) + (unsigned)s_bound[grp] * 16u;   // next record
+      const unsigned rend = (unsigned)__cvta_generic_to_shared(rec) + (unsigned)s_bound[grp + 1] * 16u;
 
-      int cur = -1;                      // current cell
-      int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-      unsigned vmask = 0;                // bit k: corner k exists in the map (cuh:61-83)
-      // value rows and accumulators as channel pairs (one 64-bit register pair each): the
-      // multiply-adds below are packed fma.rn.f32x2 (FFMA2 on sm_100a)
-      u64 v00[2], v01[2], v10[2], v11[2];
-      u64 a00[2], a01[2], a10[2], a11[2];
+      unsigned cur = 0u;                 // (pixel, corner mask, level) of the open cell; 0 = none
+      u64 u0[2], u1[2], u2[2], u3[2];    // value rows of the cell in the bilinear basis
+      u64 A0[2], A1[2], A2[2], A3[2];    // running sums of grad_value in the same basis
 #pragma unroll
       for (int k2 = 0; k2 < 2; ++k2) {
-        v00[k2] = v01[k2] = v10[k2] = v11[k2] = 0ull;
-        a00[k2] = a01[k2] = a10[k2] = a11[k2] = 0ull;
+        u0[k2] = u1[k2] = u2[k2] = u3[k2] = 0ull;
+        A0[k2] = A1[k2] = A2[k2] = A3[k2] = 0ull;
       }
-      auto flush_row = [&](int off, const u64 (&acc)[2]) {
+      // element offsets of the four corner rows of cell `key`, clamped into the map (a corner the
+      // map does not have shares the row of its neighbour and is never touched)
+      auto geometry = [&](unsigned key, int& o00, int& o01, int& o10, int& o11) {
+        const unsigned vm = key >> 3;
+        const int Wl = (int)lds_u32(lvl_sa + (key & 7u) * 32u + 12u);
+        const int xs = ((vm & (vm >> 1)) & 5u) ? MD : 0;          // left and right column both in the map
+        const int ys = ((vm & (vm >> 2)) & 3u) ? Wl * MD : 0;     // top and bottom row both in the map
+        o00 = img_off + (int)(key >> 7) * MD;
+        o01 = o00 + xs;
+        o10 = o00 + ys;
+        o11 = o10 + xs;
+      };
+      auto red_row = [&](int off, u64 lo, u64 hi) {
         float x0, x1, x2, x3;
-        unpack2(acc[0], x0, x1);
-        unpack2(acc[1], x2, x3);
-        red_add_v4(gimg + off, x0, x1, x2, x3);
+        unpack2(lo, x0, x1);
+        unpack2(hi, x2, x3);
+        red_add_v4(gacc + off, x0, x1, x2, x3);
+      };
+      auto flush = [&]() {
+        if (cur == 0u) return;
+        int o00, o01, o10, o11;
+        geometry(cur, o00, o01, o10, o11);
+        const unsigned vm = (cur >> 3) & 15u;   // bit k: corner 00, 01, 10, 11 exists
+        const u64 c01a = sub2(A1[0], A3[0]), c01b = sub2(A1[1], A3[1]);
+        const u64 c10a = sub2(A2[0], A3[0]), c10b = sub2(A2[1], A3[1]);
+        const u64 c00a = sub2(sub2(A0[0], A1[0]), c10a), c00b = sub2(sub2(A0[1], A1[1]), c10b);
+        if (vm == 15u) {                   // interior cell: no tests
+          red_row(o00, c00a, c00b);
+          red_row(o01, c01a, c01b);
+          red_row(o10, c10a, c10b);
+          red_row(o11, A3[0], A3[1]);
+        } else {
+          if (vm & 1u) red_row(o00, c00a, c00b);
+          if (vm & 2u) red_row(o01, c01a, c01b);
+          if (vm & 4u) red_row(o10, c10a, c10b);
+          if (vm & 8u) red_row(o11, A3[0], A3[1]);
+        }
       };
 
-      // the trip count is warp-uniform (shuffles inside); groups past their end idle
-      const int trips = (int)__reduce_max_sync(0xffffffffu, (unsigned)(end - beg));
-      for (int i = 0; i < trips; ++i) {
-        const int r = beg + i;
-        const bool active = r < end;
+      // warp-uniform loop (shuffles inside): groups past their end idle
+#if PCT_BIN_EXPERIMENT == 2
+      rp = rend;
+#endif
+      while (__any_sync(0xffffffffu, rp < rend)) {
+        const bool active = rp < rend;
         float pa = 0.f, px = 0.f, py = 0.f;
         if (active) {
-          const uint4 rc = lds_v4(rec_sa + (unsigned)r * 16u);
+          const uint4 rc = lds_v4(rp);
           u64 g01, g23;
-          BinRowS<T>::load(go_sa + ((rc.x >> 6) & 0x3ffu) * ROWB, g01, g23);
-          const int cell = (int)(rc.x >> 16);
-          if (cell != cur) {
-            if (vmask & 1u) flush_row(o00, a00);
-            if (vmask & 2u) flush_row(o01, a01);
-            if (vmask & 4u) flush_row(o10, a10);
-            if (vmask & 8u) flush_row(o11, a11);
-            cur = cell;
-            const unsigned lv = lvl_sa + ((rc.x >> 3) & 7u) * 32u;
-            const uint4 A = lds_v4(lv);          // cell_base, magic, wp1, W
-            const uint2 B = lds_v2(lv + 16u);    // H, start
-            const unsigned cl = (unsigned)cell - A.x;
-            const int yy = (int)__umulhi(cl, A.y);           // y0 + 1
-            const int xx = (int)cl - yy * (int)A.z;          // x0 + 1
-            const int Wl = (int)A.w, Hl = (int)B.x;
-            PCT_BIN_ASSERT(yy >= 0 && yy <= Hl && xx >= 0 && xx <= Wl);
-            const bool top = yy >= 1, bot = yy <= Hl - 1, lef = xx >= 1, rig = xx <= Wl - 1;
-            vmask = (top && lef ? 1u : 0u) | (top && rig ? 2u : 0u) | (bot && lef ? 4u : 0u) |
-                    (bot && rig ? 8u : 0u);
-            const int y0c = max(yy - 1, 0), x0c = max(xx - 1, 0);
-            const int y1c = min(yy, Hl - 1), x1c = min(xx, Wl - 1);
-            const int r0 = ((int)B.y + y0c * Wl) * MD, r1 = ((int)B.y + y1c * Wl) * MD;
-            o00 = r0 + x0c * MD;
-            o01 = r0 + x1c * MD;
-            o10 = r1 + x0c * MD;
-            o11 = r1 + x1c * MD;
-            PCT_CHECK_TAP(o00, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
-            PCT_CHECK_TAP(o11, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
-            // corners the reference skips read as 0 (cuh:61-83): zero-initialised, load predicated
-            BinVal<T>::load(vimg + o00, vmask & 1u, v00[0], v00[1]);
-            BinVal<T>::load(vimg + o01, vmask & 2u, v01[0], v01[1]);
-            BinVal<T>::load(vimg + o10, vmask & 4u, v10[0], v10[1]);
-            BinVal<T>::load(vimg + o11, vmask & 8u, v11[0], v11[1]);
-#pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2) a00[k2] = a01[k2] = a10[k2] = a11[k2] = 0ull;
-#if PCT_BIN_PREFETCH
-            // The records are sorted in raster order of the cells, so the next cell of this group
-            // is most often the right neighbour: pull its new column into L1 now (the other column
-            // is the one just loaded).  The kernel is bound by the latency of these row loads.
-            if (xx + PCT_BIN_PREFETCH <= Wl - 1) {
-#pragma unroll
-              for (int d = 1; d <= PCT_BIN_PREFETCH; ++d) {
-                prefetch_l1(vimg + o01 + d * MD);
-                prefetch_l1(vimg + o11 + d * MD);
-              }
-            }
+          BinRowS<T>::load(go_sa + (rc.x & 0x3ffu) * ROWB, g01, g23);
+          const unsigned key = rc.x >> 10;
+#if PCT_BIN_EXPERIMENT == 1
+          if (cur == 0u) {
+#else
+          if (key != cur) {
 #endif
+            // the new cell's rows are requested FIRST; the old cell is flushed while they travel
+            int o00, o01, o10, o11;
+            geometry(key, o00, o01, o10, o11);
+            const unsigned vm = (key >> 3) & 15u;
+            PCT_CHECK_TAP(o00 - img_off, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
+            PCT_CHECK_TAP(o11 - img_off, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
+            u64 v01[2], v10[2], v11[2];
+            if (vm == 15u) {
+              BinVal<T>::load_all(value + o00, u0[0], u0[1]);
+              BinVal<T>::load_all(value + o01, v01[0], v01[1]);
+              BinVal<T>::load_all(value + o10, v10[0], v10[1]);
+              BinVal<T>::load_all(value + o11, v11[0], v11[1]);
+            } else {
+              // corners the reference skips read as 0 (cuh:61-83): zero-initialised, load predicated
+              BinVal<T>::load(value + o00, vm & 1u, u0[0], u0[1]);
+              BinVal<T>::load(value + o01, vm & 2u, v01[0], v01[1]);
+              BinVal<T>::load(value + o10, vm & 4u, v10[0], v10[1]);
+              BinVal<T>::load(value + o11, vm & 8u, v11[0], v11[1]);
+            }
+            flush();
+            cur = key;
+            // the running sums restart from zeros READ from shared memory: as constants ptxas
+            // routes them through 32 uniform-register moves at the end of this block
+            {
+              const uint4 z0 = lds_v4(zero_sa), z1 = lds_v4(zero_sa + 16u), z2 = lds_v4(zero_sa + 32u), z3 = lds_v4(zero_sa + 48u);
+              A0[0] = pack2u(z0.x, z0.y); A0[1] = pack2u(z0.z, z0.w);
+              A1[0] = pack2u(z1.x, z1.y); A1[1] = pack2u(z1.z, z1.w);
+              A2[0] = pack2u(z2.x, z2.y); A2[1] = pack2u(z2.z, z2.w);
+              A3[0] = pack2u(z3.x, z3.y); A3[1] = pack2u(z3.z, z3.w);
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+              u1[k2] = sub2(v01[k2], u0[k2]);
+              u2[k2] = sub2(v10[k2], u0[k2]);
+              u3[k2] = sub2(sub2(v11[k2], v10[k2]), u1[k2]);
+            }
           }
           const float lw = __uint_as_float(rc.y), lh = __uint_as_float(rc.z);
           const float a = __uint_as_float(rc.w);
-          const float hw = 1.f - lw, hh = 1.f - lh;
-          const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;   // cuh:85
-          const float c00 = w00 * a, c01 = w01 * a, c10 = w10 * a, c11 = w11 * a;  // cuh:118,130-157
-          // four corner dot products <grad_out, value row>: two channel pairs each
-          const u64 e00 = fma2(g23, v00[1], mul2(g01, v00[0]));
-          const u64 e01 = fma2(g23, v01[1], mul2(g01, v01[0]));
-          const u64 e10 = fma2(g23, v10[1], mul2(g01, v10[0]));
-          const u64 e11 = fma2(g23, v11[1], mul2(g01, v11[0]));
-          // grad_value partial sums: acc_k += (w_k * attn) * grad_out
-          const u64 s00 = pack2(c00, c00), s01 = pack2(c01, c01), s10 = pack2(c10, c10), s11 = pack2(c11, c11);
-          a00[0] = fma2(s00, g01, a00[0]); a00[1] = fma2(s00, g23, a00[1]);
-          a01[0] = fma2(s01, g01, a01[0]); a01[1] = fma2(s01, g23, a01[1]);
-          a10[0] = fma2(s10, g01, a10[0]); a10[1] = fma2(s10, g23, a10[1]);
-          a11[0] = fma2(s11, g01, a11[0]); a11[1] = fma2(s11, g23, a11[1]);
-          const float d00 = sum2(e00), d01 = sum2(e01), d10 = sum2(e10), d11 = sum2(e11);
-          pa = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;          // cuh:161 (val . grad_out)
-          px = hh * (d01 - d00) + lh * (d11 - d10);                    // grad_w_weight (cuh:128-156)
-          py = hw * (d10 - d00) + lw * (d11 - d01);                    // grad_h_weight
+          const u64 LW = pack2(lw, lw), LH = pack2(lh, lh), AA = pack2(a, a);
+          const u64 T1 = mul2(AA, LW), T2 = mul2(AA, LH), T3 = mul2(T1, LH);
+          A0[0] = fma2(AA, g01, A0[0]); A0[1] = fma2(AA, g23, A0[1]);
+          A1[0] = fma2(T1, g01, A1[0]); A1[1] = fma2(T1, g23, A1[1]);
+          A2[0] = fma2(T2, g01, A2[0]); A2[1] = fma2(T2, g23, A2[1]);
+          A3[0] = fma2(T3, g01, A3[0]); A3[1] = fma2(T3, g23, A3[1]);
+          const u64 e3 = fma2(g23, u3[1], mul2(g01, u3[0]));
+          const u64 X = fma2(LH, e3, fma2(g23, u1[1], mul2(g01, u1[0])));   // e1 + lh e3
+          const u64 e2 = fma2(g23, u2[1], mul2(g01, u2[0]));
+          const u64 Y = fma2(LW, e3, e2);                                   // e2 + lw e3
+          const u64 e0 = fma2(g23, u0[1], mul2(g01, u0[0]));
+          px = sum2(X);                                     // grad_w_weight (cuh:128-156)
+          py = sum2(Y);                                     // grad_h_weight
+          pa = sum2(fma2(LW, X, fma2(LH, e2, e0)));         // cuh:161: e0 + lw e1 + lh e2 + lw lh e3
         }
         // group sums: lane sub 0 holds pa, 1 px, 2 py; they replace words 0..2 of the record (its
-        // cell / lw / lh are used up; word 3 keeps attn for the scaling in the final pass)
+        // header / lw / lh are used up; word 3 keeps attn for the scaling in the final pass)
         const float red = bin_reduce3<LPP>(pa, py, px, sub);
-        if (active && sub < 3) sts_f32(rec_sa + (unsigned)r * 16u + (unsigned)sub * 4u, red);
+        if (active && sub4 < 12u) sts_f32(rp + sub4, red);
+        rp += 16u;
       }
-      if (vmask & 1u) flush_row(o00, a00);
-      if (vmask & 2u) flush_row(o01, a01);
-      if (vmask & 4u) flush_row(o10, a10);
-      if (vmask & 8u) flush_row(o11, a11);
+      flush();
     }
     __syncthreads();
 

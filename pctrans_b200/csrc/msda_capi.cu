@@ -202,7 +202,7 @@ int binned_plan(const Dims& d, int dtype, unsigned flags, int smem_optin, const 
   if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return 0;
   const long long LP = (long long)d.L * d.P;
   if (d.L > pct::kBinMaxLevels || LP > pct::kBinMaxSamples) return 0;
-  if ((long long)d.S * d.M * d.D >= (1ll << 31) || d.S == 0) return 0;
+  if ((long long)d.N * d.S * d.M * d.D >= (1ll << 31) || d.S == 0) return 0;   // 32-bit element offsets
   if ((long long)d.N * d.M * ((long long)d.Lq / 8 + 1) >= (1ll << 31)) return 0;   // task index
   const long long nc_bound = 2ll * d.S + 2ll * d.L;
   if (nc_bound > pct::kBinMaxCells) return 0;
