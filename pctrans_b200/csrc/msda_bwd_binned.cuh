@@ -74,6 +74,11 @@ struct BinLaunch {
 __host__ __device__ inline int bin_bytes_per_query(int LP, int row_bytes) {
   return LP * 16 + row_bytes + LP * 2;
 }
+// Shared-memory bytes that depend on the number of cells NC only: the counters / bin offsets and
+// the list of non-empty cells in the order of the sweep.
+__host__ __device__ inline long long bin_bytes_fixed(long long NC) {
+  return ((NC + 1 + 3) & ~3ll) * 4 + ((NC * 2 + 15) & ~15ll) + 16;
+}
 
 __device__ __forceinline__ float bin_coord(float loc, float size) {
   // cuh:290-291: `loc * size - 0.5` -- float product (rounded), then the subtraction in double
@@ -186,6 +191,9 @@ __device__ __forceinline__ uint2 lds_v2(unsigned addr) {
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+#ifndef PCT_BIN_ROUNDS
+#define PCT_BIN_ROUNDS 1      // sweep in lock-step rounds over cells sorted by their record count
+#endif
 #ifndef PCT_BIN_EXPERIMENT
 #define PCT_BIN_EXPERIMENT 0   // timing experiments only (wrong results): 1 = never change cell, 2 = no sweep
 #endif
@@ -277,6 +285,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   __shared__ unsigned short s_bound[G + 1];          // first record of every group's segment
   __shared__ int s_nc, s_task;
   __shared__ unsigned int s_total;                   // (non-empty cells << 16) | records
+  __shared__ unsigned int s_hist[64];                // non-empty cells per record count (descending)
   __shared__ __align__(16) unsigned int s_zero[16];   // zeros the compiler cannot see through
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -306,7 +315,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   const int NC = s_nc;
   const int cnt_words = (NC + 1 + 3) & ~3;
   const int per_q = bin_bytes_per_query(LP, ROWB);
-  int qc_max = (bl.smem_bytes - cnt_words * 4 - 16) / per_q;
+  int qc_max = (bl.smem_bytes - (int)bin_bytes_fixed(NC)) / per_q;
   if (qc_max > kBinMaxQc) qc_max = kBinMaxQc;
   if (qc_max > 65528 / LP) qc_max = 65528 / LP;   // 16-bit record positions, 0xffff = none
   if (bl.qc_cap > 0 && qc_max > bl.qc_cap) qc_max = bl.qc_cap;
@@ -321,6 +330,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   uint4* const rec = reinterpret_cast<uint4*>(smem + (size_t)QC * ROWB);
   unsigned int* const cnt = reinterpret_cast<unsigned int*>(smem + (size_t)QC * ROWB + (size_t)QC * LP * 16);
   unsigned short* const posarr = reinterpret_cast<unsigned short*>(cnt + cnt_words);
+  unsigned short* const klist = posarr + (size_t)QC * LP;   // (QC*LP*2 is a multiple of 16)
 
   const int grp = tid / LPP, sub = tid % LPP;
   unsigned int* const ctr = g_sched + 2 * bl.slot;
@@ -357,6 +367,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
 
     // ---- P0: clear the cell counters, start staging the chunk's grad_out rows ----
     for (int i = tid; i < cnt_words; i += kBinThreads) cnt[i] = 0u;
+    if (tid < 64) s_hist[tid] = 0u;
     {
       const T* gsrc = grad_out + ((long long)((long long)b * Lq + q0) * M + m) * D;
       const unsigned dst0 = (unsigned)__cvta_generic_to_shared(go_s);
@@ -408,6 +419,9 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
       for (int i = i0; i < i1; ++i) {
         const unsigned cv = cnt[i];
         sum += cv + (cv ? 0x10000u : 0u);
+#if PCT_BIN_ROUNDS
+        if (cv) atomicAdd(&s_hist[63u - min(cv, 63u)], 1u);     // bin 0 = the fullest cells
+#endif
       }
       unsigned incl = sum;
 #pragma unroll
@@ -428,16 +442,34 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
         if (lane < NWARPS) s_wsum[lane] = inc2 - v;   // exclusive prefix of the warp totals
         if (lane == 31) { s_total = inc2; cnt[NC] = inc2; }
       }
+#if PCT_BIN_ROUNDS
+      if (warp == 1) {   // exclusive scan of the 64 histogram bins (two per lane)
+        const unsigned h0 = s_hist[2 * lane], h1 = s_hist[2 * lane + 1];
+        unsigned inc2 = h0 + h1;
+#pragma unroll
+        for (int w = 1; w < 32; w <<= 1) {
+          const unsigned o = __shfl_up_sync(0xffffffffu, inc2, w);
+          if (lane >= w) inc2 += o;
+        }
+        s_hist[2 * lane] = inc2 - h0 - h1;
+        s_hist[2 * lane + 1] = inc2 - h1;
+      }
+#endif
       __syncthreads();
       unsigned base = s_wsum[warp] + incl - sum;
       for (int i = i0; i < i1; ++i) {
         const unsigned cv = cnt[i];
         cnt[i] = base;
         base += cv + (cv ? 0x10000u : 0u);
+#if PCT_BIN_ROUNDS
+        // the sweep visits the non-empty cells in the order of their record counts
+        if (cv) klist[atomicAdd(&s_hist[63u - min(cv, 63u)], 1u)] = (unsigned short)i;
+#endif
       }
     }
     __syncthreads();
 
+#if !PCT_BIN_ROUNDS
     // ---- segment bounds: equal cost per lane group, cost = records + kappa * cells opened ----
     if (tid <= G) {
       const unsigned tot = s_total;
@@ -461,6 +493,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
       s_bound[tid] = (unsigned short)bound;
     }
     __syncthreads();
+#endif
 
     // ---- B3: write the records into their bins ----
     {
@@ -513,6 +546,143 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
+#if PCT_BIN_ROUNDS
+    // ---- sweep: lock-step rounds over the non-empty cells, fullest cells first ----
+    // Bilinear-basis form.  With value(lw, lh) = u0 + lw u1 + lh u2 + lw lh u3  (u0 = v00,
+    // u1 = v01 - v00, u2 = v10 - v00, u3 = v11 - v10 - v01 + v00) the three per-sample results are
+    //   val . grad_out = e0 + lw e1 + lh e2 + lw lh e3,   grad_w_weight = e1 + lh e3,
+    //   grad_h_weight  = e2 + lw e3                        (e_k = <grad_out, u_k>; cuh:128-161)
+    // and the four corner sums of grad_value are differences of the four running sums
+    //   A0 = sum a g, A1 = sum a lw g, A2 = sum a lh g, A3 = sum a lw lh g   (cuh:118-158),
+    // so the per-record work needs no corner weights at all; the change of basis is paid once per
+    // CELL, and the cell's geometry comes ready-made in the record's first word.
+    // A round gives each of the warp's 32/LPP lane groups ONE cell: all groups load their four
+    // value rows together, walk their records together (cells of a round hold the same number of
+    // records up to the 63-record histogram limit, so hardly a lane idles) and flush together --
+    // no branch inside the record loop.
+    {
+      constexpr int GPW = 32 / LPP;                  // lane groups (cells) per warp and round
+      // (the launcher guarantees N*S*M*D < 2^31: one 32-bit element offset serves value and gacc)
+      const int img_off = (b * S * M + m) * D + sub * VE;
+      unsigned go_sa = (unsigned)__cvta_generic_to_shared(go_s) + (unsigned)(sub * VB);
+      unsigned sub4 = (unsigned)sub * 4u;
+      asm volatile("" : "+r"(go_sa), "+r"(sub4));   // kept in registers, not re-derived per record
+      const unsigned rec_sa = (unsigned)__cvta_generic_to_shared(rec);
+      const unsigned lvl_sa = (unsigned)__cvta_generic_to_shared(s_lvl);
+      const unsigned zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
+      const int ncell = (int)(s_total >> 16);
+      const int nrounds = (ncell + GPW - 1) / GPW;
+#if PCT_BIN_EXPERIMENT == 2
+      if (false)
+#endif
+      for (int rd = warp; rd < nrounds; rd += NWARPS) {
+        const int ci = rd * GPW + (lane / LPP);
+        unsigned rp = 0u, rend = 0u;                 // shared addresses of this group's records
+        if (ci < ncell) {
+          const unsigned c = klist[ci];
+          rp = rec_sa + (c ? (cnt[c - 1] & 0xffffu) : 0u) * 16u;   // B3 left the END of every bin in cnt
+          rend = rec_sa + (cnt[c] & 0xffffu) * 16u;
+          PCT_BIN_ASSERT(rp < rend);
+        }
+        const bool have = rp < rend;
+        // ---- open ----
+        // element offsets of the four corner rows of cell `key`, clamped into the map (a corner the
+        // map does not have shares the row of its neighbour and is never touched); key 0 = no cell
+        auto geometry = [&](unsigned key, int& o00, int& o01, int& o10, int& o11) {
+          const unsigned vm = key >> 3;
+          const int Wl = (int)lds_u32(lvl_sa + (key & 7u) * 32u + 12u);
+          const int xs = ((vm & (vm >> 1)) & 5u) ? MD : 0;          // left and right column both in the map
+          const int ys = ((vm & (vm >> 2)) & 3u) ? Wl * MD : 0;     // top and bottom row both in the map
+          o00 = img_off + (int)(key >> 7) * MD;
+          o01 = o00 + xs;
+          o10 = o00 + ys;
+          o11 = o10 + xs;
+        };
+        const unsigned key = have ? lds_u32(rp) >> 10 : 0u;    // (pixel, corner mask, level)
+        u64 u0[2], u1[2], u2[2], u3[2];    // value rows of the cell in the bilinear basis
+        u64 A0[2], A1[2], A2[2], A3[2];    // running sums of grad_value in the same basis
+        {
+          u64 v01[2], v10[2], v11[2];
+          const unsigned vm = (key >> 3) & 15u;                // bit k: corner 00, 01, 10, 11 exists
+          int o00, o01, o10, o11;
+          geometry(key, o00, o01, o10, o11);
+          PCT_CHECK_TAP(o00 - img_off, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
+          PCT_CHECK_TAP(o11 - img_off, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
+          // corners the reference skips read as 0 (cuh:61-83): zero-initialised, load predicated
+          BinVal<T>::load(value + o00, vm & 1u, u0[0], u0[1]);
+          BinVal<T>::load(value + o01, vm & 2u, v01[0], v01[1]);
+          BinVal<T>::load(value + o10, vm & 4u, v10[0], v10[1]);
+          BinVal<T>::load(value + o11, vm & 8u, v11[0], v11[1]);
+          // the running sums start from zeros READ from shared memory: as constants ptxas routes
+          // them through 32 uniform-register moves
+          const uint4 z0 = lds_v4(zero_sa), z1 = lds_v4(zero_sa + 16u), z2 = lds_v4(zero_sa + 32u), z3 = lds_v4(zero_sa + 48u);
+          A0[0] = pack2u(z0.x, z0.y); A0[1] = pack2u(z0.z, z0.w);
+          A1[0] = pack2u(z1.x, z1.y); A1[1] = pack2u(z1.z, z1.w);
+          A2[0] = pack2u(z2.x, z2.y); A2[1] = pack2u(z2.z, z2.w);
+          A3[0] = pack2u(z3.x, z3.y); A3[1] = pack2u(z3.z, z3.w);
+#pragma unroll
+          for (int k2 = 0; k2 < 2; ++k2) {
+            u1[k2] = sub2(v01[k2], u0[k2]);
+            u2[k2] = sub2(v10[k2], u0[k2]);
+            u3[k2] = sub2(sub2(v11[k2], v10[k2]), u1[k2]);
+          }
+        }
+        // ---- the records of the round (warp-uniform trip count: shuffles inside) ----
+#if PCT_BIN_EXPERIMENT == 1
+        for (int i = 0; i > 0; --i, rp += 16u) {
+#else
+        for (int i = (int)__reduce_max_sync(0xffffffffu, (rend - rp) >> 4); i > 0; --i, rp += 16u) {
+#endif
+          float pa = 0.f, px = 0.f, py = 0.f;
+          const bool active = rp < rend;
+          if (active) {
+            const uint4 rc = lds_v4(rp);
+            u64 g01, g23;
+            BinRowS<T>::load(go_sa + (rc.x & 0x3ffu) * ROWB, g01, g23);
+            const float lw = __uint_as_float(rc.y), lh = __uint_as_float(rc.z);
+            const float a = __uint_as_float(rc.w);
+            const u64 LW = pack2(lw, lw), LH = pack2(lh, lh), AA = pack2(a, a);
+            const u64 T1 = mul2(AA, LW), T2 = mul2(AA, LH), T3 = mul2(T1, LH);
+            A0[0] = fma2(AA, g01, A0[0]); A0[1] = fma2(AA, g23, A0[1]);
+            A1[0] = fma2(T1, g01, A1[0]); A1[1] = fma2(T1, g23, A1[1]);
+            A2[0] = fma2(T2, g01, A2[0]); A2[1] = fma2(T2, g23, A2[1]);
+            A3[0] = fma2(T3, g01, A3[0]); A3[1] = fma2(T3, g23, A3[1]);
+            const u64 e3 = fma2(g23, u3[1], mul2(g01, u3[0]));
+            const u64 X = fma2(LH, e3, fma2(g23, u1[1], mul2(g01, u1[0])));   // e1 + lh e3
+            const u64 e2 = fma2(g23, u2[1], mul2(g01, u2[0]));
+            const u64 Y = fma2(LW, e3, e2);                                   // e2 + lw e3
+            const u64 e0 = fma2(g23, u0[1], mul2(g01, u0[0]));
+            px = sum2(X);                                     // grad_w_weight (cuh:128-156)
+            py = sum2(Y);                                     // grad_h_weight
+            pa = sum2(fma2(LW, X, fma2(LH, e2, e0)));         // cuh:161: e0 + lw e1 + lh e2 + lw lh e3
+          }
+          // group sums: lane sub 0 holds pa, 1 px, 2 py; they replace words 0..2 of the record (its
+          // header / lw / lh are used up; word 3 keeps attn for the scaling in the final pass)
+          const float red = bin_reduce3<LPP>(pa, py, px, sub);
+          if (active && sub4 < 12u) sts_f32(rp + sub4, red);
+        }
+        // ---- flush: corner sums out of the basis sums, one L2 reduction per existing corner ----
+        {
+          auto red_row = [&](int off, u64 lo, u64 hi) {
+            float x0, x1, x2, x3;
+            unpack2(lo, x0, x1);
+            unpack2(hi, x2, x3);
+            red_add_v4(gacc + off, x0, x1, x2, x3);
+          };
+          const u64 c01a = sub2(A1[0], A3[0]), c01b = sub2(A1[1], A3[1]);
+          const u64 c10a = sub2(A2[0], A3[0]), c10b = sub2(A2[1], A3[1]);
+          const u64 c00a = sub2(sub2(A0[0], A1[0]), c10a), c00b = sub2(sub2(A0[1], A1[1]), c10b);
+          const unsigned vm = (key >> 3) & 15u;
+          int o00, o01, o10, o11;
+          geometry(key, o00, o01, o10, o11);
+          if (vm & 1u) red_row(o00, c00a, c00b);
+          if (vm & 2u) red_row(o01, c01a, c01b);
+          if (vm & 4u) red_row(o10, c10a, c10b);
+          if (vm & 8u) red_row(o11, A3[0], A3[1]);
+        }
+      }
+    }
+#else
     // ---- sweep: every lane group walks its segment of the cell-sorted records ----
     // Bilinear-basis form.  With value(lw, lh) = u0 + lw u1 + lh u2 + lw lh u3  (u0 = v00,
     // u1 = v01 - v00, u2 = v10 - v00, u3 = v11 - v10 - v01 + v00) the three per-sample results are
@@ -660,6 +830,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
       }
       flush();
     }
+#endif
     __syncthreads();
 
     // ---- final: coalesced grad_sampling_loc / grad_attn_weight in sample order ----

@@ -207,7 +207,7 @@ int binned_plan(const Dims& d, int dtype, unsigned flags, int smem_optin, const 
   const long long nc_bound = 2ll * d.S + 2ll * d.L;
   if (nc_bound > pct::kBinMaxCells) return 0;
   const int row_bytes = d.D * (int)elem_size(dtype);
-  const long long fixed = ((nc_bound + 1 + 3) & ~3ll) * 4 + 16 + 1024;   // + the kernel's static arrays
+  const long long fixed = pct::bin_bytes_fixed(nc_bound) + 1536;   // + the kernel's static arrays
   if (fixed + (long long)kBinMinChunk * pct::bin_bytes_per_query((int)LP, row_bytes) > smem_optin) return 0;
   const size_t vb = 4 * elem_size(dtype);
   if (!aligned(value, vb) || !aligned(grad_out, 16) || !aligned(acc, 16) || !aligned(loc, 8) ||
