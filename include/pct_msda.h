@@ -94,12 +94,11 @@ extern "C" {
 #define PCT_MSDA_FLAG_BWD_PER_TAP 0x20u   /* backward: use the per-tap scatter kernel (one L2 reduction per
                                             bilinear corner) even where the cell-binned kernel is the default */
 #define PCT_MSDA_FLAG_BWD_BINNED 0x40u    /* backward: use the cell-binned kernel whenever the shape fits it
-                                            (default only for head rows of >= 256 bytes, where it measured
-                                            faster) */
+                                            (since round 2 it is the default there; the flag is kept
+                                            for callers that set it) */
 /* bits 8..15: threads/32 of the persistent CTA; bits 16..19: CTAs per SM; bits 20..24: 1 + static
  * share of the task list in sixteenths; bits 25..31: cap of the binned backward's chunk size in
- * units of 8 queries; for the binned backward bits 16..19 are 1 + the cost of opening a cell in its
- * segment balance (tuning only) */
+ * units of 8 queries (tuning only) */
 
 int pct_msda_abi_version(void);
 
@@ -118,8 +117,8 @@ int pct_msda_kernel_family(int channels, int num_levels, int num_point, int valu
  * device (buffers assumed 16-byte aligned): 0 = generic scalar, 1 = per-tap vector scatter,
  * 2 = cell-binned (grad_value aggregated per bilinear cell on chip before any global reduction;
  * available when the head dim is 16/32/64/128 channels, L <= 8, L*P <= 64 and the level maps are
- * small enough for shared memory; the default for head rows of >= 256 bytes, otherwise selected
- * with PCT_MSDA_FLAG_BWD_BINNED).  Negative = error code negated. */
+ * small enough for shared memory -- fewer than 32 768 pixels per image; the default wherever it
+ * fits, PCT_MSDA_FLAG_BWD_PER_TAP overrides).  Negative = error code negated. */
 int pct_msda_backward_plan(int batch, int spatial_size, int num_heads, int channels,
                            int num_levels, int num_query, int num_point, int value_dtype,
                            unsigned flags);

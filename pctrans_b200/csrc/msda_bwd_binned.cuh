@@ -16,16 +16,19 @@
 //           tasks from a global counter.
 //   B1/B2/B3  counting sort of the chunk's QC*L*P samples by bilinear cell (level, y0, x0) in
 //           shared memory: one shared-memory integer atomic per sample (ATOMS.ADD is native for
-//           32-bit integers), a CTA-wide scan, and a 16-byte record {cell|query|level, lw, lh,
-//           attn} per in-range sample.  The chunk's grad_out rows are staged in shared memory
-//           with cp.async meanwhile.
-//   sweep  the sorted records are cut into segments of equal COST (records + cells opened), one
-//           per group of LPP lanes (a lane owns 4 channels).  A group keeps the four corner value
-//           rows of its current cell AND four fp32 accumulator rows in registers; per record it
-//           reads one grad_out row from shared memory, forms the four corner dot products
-//           (-> grad_attn, grad_loc, cuh:160-163) and adds w_k*attn*grad_out into the
-//           accumulators.  Only when the cell changes are the accumulators sent to L2
-//           (red.global.add.v4.f32) and four value rows loaded.
+//           32-bit integers), a CTA-wide scan, and a 16-byte record {cell geometry | query, lw,
+//           lh, attn} per in-range sample.  The scan also lists the non-empty cells in the order
+//           of their record counts (a 64-bin histogram).  The chunk's grad_out rows are staged in
+//           shared memory with cp.async meanwhile.
+//   sweep  in ROUNDS: a round gives each group of LPP lanes (a lane owns 4 channels) one cell, the
+//           groups of a warp taking neighbours of the count-ordered list, i.e. cells with the same
+//           number of records.  All groups load the four corner value rows of their cells
+//           together, walk their records together -- per record one grad_out row from shared
+//           memory, four dot products (-> grad_attn, grad_loc, cuh:160-163) and four
+//           multiply-adds into fp32 running sums in registers, no branch -- and then send the
+//           sums to L2 (red.global.add.v4.f32) together.  Value rows and running sums live in the
+//           BILINEAR BASIS (1, lw, lh, lw*lh) instead of per corner, so a record needs no corner
+//           weights; the change of basis is paid once per cell.
 //           Per-sample cost drops from 8 row transfers + 16 L2 sectors to 1 shared-memory row
 //           read, with 8 row transfers + 16 sectors per CELL.
 //   final  grad_sampling_loc / grad_attn_weight are written coalesced in sample order (the sweep
@@ -33,7 +36,8 @@
 //
 // Everything is fp32 arithmetic with fp32 accumulation (bf16 values accumulate into the caller's
 // fp32 workspace exactly like the per-tap kernel).  Summation order differs from the reference
-// (as any atomic scatter does); tests hold the result to 1e-4.
+// (as any atomic scatter does), and the corner sums are formed as differences of basis sums
+// (error of the order of 1e-7 of the cell's largest sum); tests hold the result to 1e-4.
 #pragma once
 
 #include "msda_kernels.cuh"
@@ -67,7 +71,6 @@ struct BinLaunch {
   int smem_bytes;   // dynamic shared memory of the launch
   int qc_cap;       // upper limit for the chunk size (0 = whatever fits)
   int slot;         // g_sched ring slot: [0] task counter, [1] CTA-exit counter
-  int cell_cost;    // cost of opening a cell in units of one record, for the segment balance
 };
 
 // Shared-memory bytes a chunk of one query needs: records + grad_out row + position of each sample.
@@ -191,9 +194,6 @@ __device__ __forceinline__ uint2 lds_v2(unsigned addr) {
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-#ifndef PCT_BIN_ROUNDS
-#define PCT_BIN_ROUNDS 1      // sweep in lock-step rounds over cells sorted by their record count
-#endif
 #ifndef PCT_BIN_EXPERIMENT
 #define PCT_BIN_EXPERIMENT 0   // timing experiments only (wrong results): 1 = never change cell, 2 = no sweep
 #endif
@@ -282,7 +282,6 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   __shared__ BinLevel s_lvl[kBinMaxLevels];
   __shared__ unsigned char s_slvl[kBinMaxSamples];   // level of sample s
   __shared__ unsigned int s_wsum[32];
-  __shared__ unsigned short s_bound[G + 1];          // first record of every group's segment
   __shared__ int s_nc, s_task;
   __shared__ unsigned int s_total;                   // (non-empty cells << 16) | records
   __shared__ unsigned int s_hist[64];                // non-empty cells per record count (descending)
@@ -334,7 +333,6 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
 
   const int grp = tid / LPP, sub = tid % LPP;
   unsigned int* const ctr = g_sched + 2 * bl.slot;
-  const unsigned kappa = (unsigned)bl.cell_cost;
 
   // one sample of the binning passes: cell index (or -1 when the reference skips it), fractions
   auto locate = [&](float2 xy, int s, float& lw, float& lh, int& lvl) -> int {
@@ -348,6 +346,27 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     return A.x + ((int)fy + 1) * A.z + (int)fx + 1;
   };
 
+  // the same plus the record's first word: the geometry of the sample's cell, worked out by ONE
+  // thread per sample -- first pixel of the cell clamped into the map (15 bits), which of its four
+  // corners exist (cuh:61-83; 4 bits), level (3 bits); the caller adds the query (10 bits)
+  auto locate_full = [&](float2 xy, int s, float& lw, float& lh, unsigned& hdr) -> int {
+    const int lvl = s_slvl[s];
+    const int4 A = *reinterpret_cast<const int4*>(&s_lvl[lvl]);          // cell_base, magic, wp1, W
+    const int4 Bq = *reinterpret_cast<const int4*>(&s_lvl[lvl].H);       // H, start, Hf, Wf
+    const float Hf = __int_as_float(Bq.z), Wf = __int_as_float(Bq.w);
+    const float y = bin_coord(xy.y, Hf), x = bin_coord(xy.x, Wf);
+    if (!(y > -1.f && x > -1.f && y < Hf && x < Wf)) return -1;         // cuh:293 (NaN: outside)
+    const float fy = floorf(y), fx = floorf(x);
+    lh = y - fy; lw = x - fx;
+    const int yy = (int)fy + 1, xx = (int)fx + 1;                        // y0 + 1, x0 + 1
+    const bool top = yy >= 1, bot = yy <= Bq.x - 1, lef = xx >= 1, rig = xx <= A.w - 1;
+    const unsigned vm = (top && lef ? 1u : 0u) | (top && rig ? 2u : 0u) |
+                        (bot && lef ? 4u : 0u) | (bot && rig ? 8u : 0u);
+    const unsigned pix = (unsigned)(Bq.y + max(yy - 1, 0) * A.w + max(xx - 1, 0));
+    PCT_BIN_ASSERT(pix < 32768u && vm != 0u);
+    hdr = (pix << 17) | (vm << 13) | ((unsigned)lvl << 10);
+    return A.x + yy * A.z + xx;
+  };
   for (;;) {
     if (tid == 0) s_task = (int)atomicAdd(ctr, 1u);
     __syncthreads();
@@ -419,9 +438,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
       for (int i = i0; i < i1; ++i) {
         const unsigned cv = cnt[i];
         sum += cv + (cv ? 0x10000u : 0u);
-#if PCT_BIN_ROUNDS
         if (cv) atomicAdd(&s_hist[63u - min(cv, 63u)], 1u);     // bin 0 = the fullest cells
-#endif
       }
       unsigned incl = sum;
 #pragma unroll
@@ -442,7 +459,6 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
         if (lane < NWARPS) s_wsum[lane] = inc2 - v;   // exclusive prefix of the warp totals
         if (lane == 31) { s_total = inc2; cnt[NC] = inc2; }
       }
-#if PCT_BIN_ROUNDS
       if (warp == 1) {   // exclusive scan of the 64 histogram bins (two per lane)
         const unsigned h0 = s_hist[2 * lane], h1 = s_hist[2 * lane + 1];
         unsigned inc2 = h0 + h1;
@@ -454,46 +470,18 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
         s_hist[2 * lane] = inc2 - h0 - h1;
         s_hist[2 * lane + 1] = inc2 - h1;
       }
-#endif
       __syncthreads();
       unsigned base = s_wsum[warp] + incl - sum;
       for (int i = i0; i < i1; ++i) {
         const unsigned cv = cnt[i];
         cnt[i] = base;
         base += cv + (cv ? 0x10000u : 0u);
-#if PCT_BIN_ROUNDS
         // the sweep visits the non-empty cells in the order of their record counts
         if (cv) klist[atomicAdd(&s_hist[63u - min(cv, 63u)], 1u)] = (unsigned short)i;
-#endif
       }
     }
     __syncthreads();
 
-#if !PCT_BIN_ROUNDS
-    // ---- segment bounds: equal cost per lane group, cost = records + kappa * cells opened ----
-    if (tid <= G) {
-      const unsigned tot = s_total;
-      const unsigned r_tot = tot & 0xffffu, e_tot = tot >> 16;
-      const unsigned target =
-          (unsigned)(((unsigned long long)(r_tot + kappa * e_tot) * (unsigned)tid) / (unsigned)G);
-      int lo = 0, hi = NC;     // largest cell index whose cost-before is <= target
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        const unsigned pv = cnt[mid];
-        if ((pv & 0xffffu) + kappa * (pv >> 16) <= target) lo = mid; else hi = mid - 1;
-      }
-      unsigned bound = r_tot;
-      if (lo < NC) {
-        const unsigned pv = cnt[lo], nx = cnt[lo + 1];
-        const unsigned r0 = pv & 0xffffu, count = (nx & 0xffffu) - r0;
-        const unsigned rem = target - (r0 + kappa * (pv >> 16));
-        const unsigned off = rem > kappa ? rem - kappa : 0u;
-        bound = r0 + (off < count ? off : count);
-      }
-      s_bound[tid] = (unsigned short)bound;
-    }
-    __syncthreads();
-#endif
 
     // ---- B3: write the records into their bins ----
     {
@@ -516,27 +504,14 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
           const int k = k0 + u * kBinThreads;
           if (k < ntaps) {
             float lw = 0.f, lh = 0.f;
-            int lvl;
-            const int cell = locate(xy[u], ss[u], lw, lh, lvl);
+            unsigned hdr = 0u;
+            const int cell = locate_full(xy[u], ss[u], lw, lh, hdr);
             unsigned pos = kBinNoPos;
             if (cell >= 0) {
               pos = atomicAdd(cnt + cell, 1u) & 0xffffu;
               PCT_BIN_ASSERT(pos < (unsigned)ntaps);
-              // the record's first word carries the geometry of its cell, worked out here by ONE
-              // thread per sample: first pixel of the cell clamped into the map (15 bits), which
-              // of its four corners exist (cuh:61-83), level, query
-              const int4 A = *reinterpret_cast<const int4*>(&s_lvl[lvl]);     // cell_base, magic, wp1, W
-              const int2 B = *reinterpret_cast<const int2*>(&s_lvl[lvl].H);   // H, start
-              const int cl = cell - A.x;
-              const int yy = (int)__umulhi((unsigned)cl, (unsigned)A.y);     // y0 + 1
-              const int xx = cl - yy * A.z;                                   // x0 + 1
-              const bool top = yy >= 1, bot = yy <= B.x - 1, lef = xx >= 1, rig = xx <= A.w - 1;
-              const unsigned vm = (top && lef ? 1u : 0u) | (top && rig ? 2u : 0u) |
-                                  (bot && lef ? 4u : 0u) | (bot && rig ? 8u : 0u);
-              const unsigned pix = (unsigned)(B.y + max(yy - 1, 0) * A.w + max(xx - 1, 0));
-              PCT_BIN_ASSERT(pix < 32768u && vm != 0u);
-              rec[pos] = make_uint4((pix << 17) | (vm << 13) | ((unsigned)lvl << 10) | (unsigned)qq[u],
-                                    __float_as_uint(lw), __float_as_uint(lh), __float_as_uint(aw[u]));
+              rec[pos] = make_uint4(hdr | (unsigned)qq[u], __float_as_uint(lw), __float_as_uint(lh),
+                                    __float_as_uint(aw[u]));
             }
             posarr[k] = (unsigned short)pos;
           }
@@ -546,7 +521,6 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-#if PCT_BIN_ROUNDS
     // ---- sweep: lock-step rounds over the non-empty cells, fullest cells first ----
     // Bilinear-basis form.  With value(lw, lh) = u0 + lw u1 + lh u2 + lw lh u3  (u0 = v00,
     // u1 = v01 - v00, u2 = v10 - v00, u3 = v11 - v10 - v01 + v00) the three per-sample results are
@@ -575,7 +549,13 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
 #if PCT_BIN_EXPERIMENT == 2
       if (false)
 #endif
-      for (int rd = warp; rd < nrounds; rd += NWARPS) {
+      // rounds go to the warps in snake order (w, 63-w, 64+w, 127-w, ...): the fullest cells come
+      // first, and a plain interleave gave warp 0 the longest round of every 32 (11 % of the
+      // kernel's stall samples sat at the barrier behind the sweep)
+      for (int j = 0;; ++j) {
+        const int rd = j * NWARPS + ((j & 1) ? NWARPS - 1 - warp : warp);
+        if (j * NWARPS >= nrounds) break;
+        if (rd >= nrounds) continue;
         const int ci = rd * GPW + (lane / LPP);
         unsigned rp = 0u, rend = 0u;                 // shared addresses of this group's records
         if (ci < ncell) {
@@ -682,155 +662,6 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
         }
       }
     }
-#else
-    // ---- sweep: every lane group walks its segment of the cell-sorted records ----
-    // Bilinear-basis form.  With value(lw, lh) = u0 + lw u1 + lh u2 + lw lh u3  (u0 = v00,
-    // u1 = v01 - v00, u2 = v10 - v00, u3 = v11 - v10 - v01 + v00) the three per-sample results are
-    //   val . grad_out = e0 + lw e1 + lh e2 + lw lh e3,   grad_w_weight = e1 + lh e3,
-    //   grad_h_weight  = e2 + lw e3                        (e_k = <grad_out, u_k>; cuh:128-161)
-    // and the four corner sums of grad_value are differences of the four running sums
-    //   A0 = sum a g, A1 = sum a lw g, A2 = sum a lh g, A3 = sum a lw lh g   (cuh:118-158),
-    // so the per-record work needs no corner weights at all; the change of basis is paid once per
-    // CELL (when its rows are loaded / its sums are flushed), and the cell's geometry comes
-    // ready-made in the record's first word.
-    {
-      // (the launcher guarantees N*S*M*D < 2^31: one 32-bit element offset serves value and gacc)
-      const int img_off = (b * S * M + m) * D + sub * VE;
-      unsigned go_sa = (unsigned)__cvta_generic_to_shared(go_s) + (unsigned)(sub * VB);
-      unsigned sub4 = (unsigned)sub * 4u;
-      asm volatile("" : "+r"(go_sa), "+r"(sub4));   // kept in registers, not re-derived per record
-      const unsigned lvl_sa = (unsigned)__cvta_generic_to_shared(s_lvl);
-      const unsigned zero_sa = (unsigned)__cvta_generic_to_shared(s_zero);
-      unsigned rp = (unsigned)__cvta_generic_to_shared(rec) + (unsigned)s_bound[grp] * 16u;   // next record
-      const unsigned rend = (unsigned)__cvta_generic_to_shared(rec) + (unsigned)s_bound[grp + 1] * 16u;
-
-      unsigned cur = 0u;                 // (pixel, corner mask, level) of the open cell; 0 = none
-      u64 u0[2], u1[2], u2[2], u3[2];    // value rows of the cell in the bilinear basis
-      u64 A0[2], A1[2], A2[2], A3[2];    // running sums of grad_value in the same basis
-#pragma unroll
-      for (int k2 = 0; k2 < 2; ++k2) {
-        u0[k2] = u1[k2] = u2[k2] = u3[k2] = 0ull;
-        A0[k2] = A1[k2] = A2[k2] = A3[k2] = 0ull;
-      }
-      // element offsets of the four corner rows of cell `key`, clamped into the map (a corner the
-      // map does not have shares the row of its neighbour and is never touched)
-      auto geometry = [&](unsigned key, int& o00, int& o01, int& o10, int& o11) {
-        const unsigned vm = key >> 3;
-        const int Wl = (int)lds_u32(lvl_sa + (key & 7u) * 32u + 12u);
-        const int xs = ((vm & (vm >> 1)) & 5u) ? MD : 0;          // left and right column both in the map
-        const int ys = ((vm & (vm >> 2)) & 3u) ? Wl * MD : 0;     // top and bottom row both in the map
-        o00 = img_off + (int)(key >> 7) * MD;
-        o01 = o00 + xs;
-        o10 = o00 + ys;
-        o11 = o10 + xs;
-      };
-      auto red_row = [&](int off, u64 lo, u64 hi) {
-        float x0, x1, x2, x3;
-        unpack2(lo, x0, x1);
-        unpack2(hi, x2, x3);
-        red_add_v4(gacc + off, x0, x1, x2, x3);
-      };
-      auto flush = [&]() {
-        if (cur == 0u) return;
-        int o00, o01, o10, o11;
-        geometry(cur, o00, o01, o10, o11);
-        const unsigned vm = (cur >> 3) & 15u;   // bit k: corner 00, 01, 10, 11 exists
-        const u64 c01a = sub2(A1[0], A3[0]), c01b = sub2(A1[1], A3[1]);
-        const u64 c10a = sub2(A2[0], A3[0]), c10b = sub2(A2[1], A3[1]);
-        const u64 c00a = sub2(sub2(A0[0], A1[0]), c10a), c00b = sub2(sub2(A0[1], A1[1]), c10b);
-        if (vm == 15u) {                   // interior cell: no tests
-          red_row(o00, c00a, c00b);
-          red_row(o01, c01a, c01b);
-          red_row(o10, c10a, c10b);
-          red_row(o11, A3[0], A3[1]);
-        } else {
-          if (vm & 1u) red_row(o00, c00a, c00b);
-          if (vm & 2u) red_row(o01, c01a, c01b);
-          if (vm & 4u) red_row(o10, c10a, c10b);
-          if (vm & 8u) red_row(o11, A3[0], A3[1]);
-        }
-      };
-
-      // warp-uniform loop (shuffles inside): groups past their end idle
-#if PCT_BIN_EXPERIMENT == 2
-      rp = rend;
-#endif
-      while (__any_sync(0xffffffffu, rp < rend)) {
-        const bool active = rp < rend;
-        float pa = 0.f, px = 0.f, py = 0.f;
-        if (active) {
-          const uint4 rc = lds_v4(rp);
-          u64 g01, g23;
-          BinRowS<T>::load(go_sa + (rc.x & 0x3ffu) * ROWB, g01, g23);
-          const unsigned key = rc.x >> 10;
-#if PCT_BIN_EXPERIMENT == 1
-          if (cur == 0u) {
-#else
-          if (key != cur) {
-#endif
-            // the new cell's rows are requested FIRST; the old cell is flushed while they travel
-            int o00, o01, o10, o11;
-            geometry(key, o00, o01, o10, o11);
-            const unsigned vm = (key >> 3) & 15u;
-            PCT_CHECK_TAP(o00 - img_off, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
-            PCT_CHECK_TAP(o11 - img_off, 0, 0, (m * D + sub * VE), VE, (long long)S * MD);
-            u64 v01[2], v10[2], v11[2];
-            if (vm == 15u) {
-              BinVal<T>::load_all(value + o00, u0[0], u0[1]);
-              BinVal<T>::load_all(value + o01, v01[0], v01[1]);
-              BinVal<T>::load_all(value + o10, v10[0], v10[1]);
-              BinVal<T>::load_all(value + o11, v11[0], v11[1]);
-            } else {
-              // corners the reference skips read as 0 (cuh:61-83): zero-initialised, load predicated
-              BinVal<T>::load(value + o00, vm & 1u, u0[0], u0[1]);
-              BinVal<T>::load(value + o01, vm & 2u, v01[0], v01[1]);
-              BinVal<T>::load(value + o10, vm & 4u, v10[0], v10[1]);
-              BinVal<T>::load(value + o11, vm & 8u, v11[0], v11[1]);
-            }
-            flush();
-            cur = key;
-            // the running sums restart from zeros READ from shared memory: as constants ptxas
-            // routes them through 32 uniform-register moves at the end of this block
-            {
-              const uint4 z0 = lds_v4(zero_sa), z1 = lds_v4(zero_sa + 16u), z2 = lds_v4(zero_sa + 32u), z3 = lds_v4(zero_sa + 48u);
-              A0[0] = pack2u(z0.x, z0.y); A0[1] = pack2u(z0.z, z0.w);
-              A1[0] = pack2u(z1.x, z1.y); A1[1] = pack2u(z1.z, z1.w);
-              A2[0] = pack2u(z2.x, z2.y); A2[1] = pack2u(z2.z, z2.w);
-              A3[0] = pack2u(z3.x, z3.y); A3[1] = pack2u(z3.z, z3.w);
-            }
-#pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2) {
-              u1[k2] = sub2(v01[k2], u0[k2]);
-              u2[k2] = sub2(v10[k2], u0[k2]);
-              u3[k2] = sub2(sub2(v11[k2], v10[k2]), u1[k2]);
-            }
-          }
-          const float lw = __uint_as_float(rc.y), lh = __uint_as_float(rc.z);
-          const float a = __uint_as_float(rc.w);
-          const u64 LW = pack2(lw, lw), LH = pack2(lh, lh), AA = pack2(a, a);
-          const u64 T1 = mul2(AA, LW), T2 = mul2(AA, LH), T3 = mul2(T1, LH);
-          A0[0] = fma2(AA, g01, A0[0]); A0[1] = fma2(AA, g23, A0[1]);
-          A1[0] = fma2(T1, g01, A1[0]); A1[1] = fma2(T1, g23, A1[1]);
-          A2[0] = fma2(T2, g01, A2[0]); A2[1] = fma2(T2, g23, A2[1]);
-          A3[0] = fma2(T3, g01, A3[0]); A3[1] = fma2(T3, g23, A3[1]);
-          const u64 e3 = fma2(g23, u3[1], mul2(g01, u3[0]));
-          const u64 X = fma2(LH, e3, fma2(g23, u1[1], mul2(g01, u1[0])));   // e1 + lh e3
-          const u64 e2 = fma2(g23, u2[1], mul2(g01, u2[0]));
-          const u64 Y = fma2(LW, e3, e2);                                   // e2 + lw e3
-          const u64 e0 = fma2(g23, u0[1], mul2(g01, u0[0]));
-          px = sum2(X);                                     // grad_w_weight (cuh:128-156)
-          py = sum2(Y);                                     // grad_h_weight
-          pa = sum2(fma2(LW, X, fma2(LH, e2, e0)));         // cuh:161: e0 + lw e1 + lh e2 + lw lh e3
-        }
-        // group sums: lane sub 0 holds pa, 1 px, 2 py; they replace words 0..2 of the record (its
-        // header / lw / lh are used up; word 3 keeps attn for the scaling in the final pass)
-        const float red = bin_reduce3<LPP>(pa, py, px, sub);
-        if (active && sub4 < 12u) sts_f32(rp + sub4, red);
-        rp += 16u;
-      }
-      flush();
-    }
-#endif
     __syncthreads();
 
     // ---- final: coalesced grad_sampling_loc / grad_attn_weight in sample order ----

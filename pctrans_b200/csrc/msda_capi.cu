@@ -191,11 +191,11 @@ int binned_plan(const Dims& d, int dtype, unsigned flags, int smem_optin, const 
                 const void* grad_out, const void* acc, const void* loc, const void* attn,
                 const void* grad_loc) {
   if (flags & (PCT_MSDA_FLAG_FORCE_GENERIC | PCT_MSDA_FLAG_BWD_PER_TAP)) return 0;
-  // Measured on B200 (profiles/r02_binned_*.log): the binned kernel wins where a head row is 256 bytes
-  // or more (D = 64 fp32: 0.95 vs 1.11 ms) and with unstructured sampling locations, ties at 64-byte
-  // rows and loses 5 % at 128-byte rows with PCTrans's local sampling pattern -- so it is the
-  // default only for the wide rows; PCT_MSDA_FLAG_BWD_BINNED selects it everywhere it fits.
-  if (!(flags & PCT_MSDA_FLAG_BWD_BINNED) && (size_t)d.D * elem_size(dtype) < 256) return 0;
+  // Measured on B200 (profiles/r02_binned_v3_*.log): in its round-2 form (bilinear-basis sweep in
+  // lock-step rounds) the binned kernel is faster than the per-tap kernel on every shape it fits
+  // -- 64-, 128- and 256-byte head rows, fp32 and bf16, PCTrans's local sampling pattern and
+  // uniform-random locations, batch 1 to 32 -- so it is the default; PCT_MSDA_FLAG_BWD_PER_TAP
+  // selects the other one.
   if (dtype != PCT_MSDA_F32 && dtype != PCT_MSDA_BF16) return 0;
   if (d.D % 4 != 0) return 0;
   const int lanes = d.D / 4;

@@ -8,8 +8,6 @@
 namespace pctl {
 namespace {
 
-constexpr int kDefaultCellCost = 2;
-
 template <typename T, int LPP>
 int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                       const void* attn, const void* grad_out, void* gacc, void* grad_loc,
@@ -36,9 +34,24 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
   pct::BinLaunch bl;
   bl.smem_bytes = dyn;
   bl.qc_cap = (int)((flags >> 25) & 0x7fu) * 8;
+  if (bl.qc_cap == 0) {
+    // Small problems: when the chunks that fit shared memory would leave SMs without a task,
+    // shorter chunks give every SM one (the kernel takes the smaller of this cap and what fits).
+    const long long streams = (long long)d.N * d.M;
+    const long long per_q = pct::bin_bytes_per_query(d.L * d.P, LPP * 4 * (int)sizeof(T));
+    long long qc_fit = (dyn - pct::bin_bytes_fixed(2ll * d.S + 2ll * d.L)) / per_q;
+    if (qc_fit > pct::kBinMaxQc) qc_fit = pct::kBinMaxQc;
+    if (qc_fit < kBinMinChunk) qc_fit = kBinMinChunk;
+    const long long chunks_fit = (d.Lq + qc_fit - 1) / qc_fit;
+    const long long sms = (long long)sm_count * pct::kBinCtasPerSm;
+    if (streams * chunks_fit * 4 < sms * 3) {
+      const long long want_chunks = (sms + streams - 1) / streams;
+      long long cap = ((d.Lq + want_chunks - 1) / want_chunks + 7) & ~7ll;
+      if (cap < kBinMinChunk) cap = kBinMinChunk;
+      if (cap < qc_fit) bl.qc_cap = (int)cap;
+    }
+  }
   bl.slot = (int)(next_sched_slot());
-  const int fk = (int)((flags >> 16) & 0xfu);   // tuning: 1 + cost of opening a cell, in records
-  bl.cell_cost = fk > 0 ? fk - 1 : kDefaultCellCost;
   const long long want = (long long)d.N * d.M * ((d.Lq + kBinMinChunk - 1) / kBinMinChunk);
   const long long cap = (long long)sm_count * pct::kBinCtasPerSm;
   const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);

@@ -1,7 +1,7 @@
 """GPU parity of the cell-binned backward (pctrans_b200/csrc/msda_bwd_binned.cuh) through the C ABI.
 
-The binned kernel is the default gradient kernel for wide head rows (>= 256 bytes) and selectable
-everywhere with ``PCT_MSDA_FLAG_BWD_BINNED``; these cases pin it against (a) the CPU oracle
+The binned kernel is the default gradient kernel wherever the shape fits it (round 2, second
+form: bilinear-basis sweep in lock-step rounds); these cases pin it against (a) the CPU oracle
 (fp64 closed form of cuh:93-164) and (b) the per-tap scatter kernel it replaces
 (``PCT_MSDA_FLAG_BWD_PER_TAP``), over the shapes that stress its bookkeeping: several chunks per
 (image, head), chunk sizes that do not divide Lq, L*P that does not divide the CTA size, one-pixel
@@ -148,8 +148,12 @@ def test_binned_back_to_back_launches_share_nothing():
     assert torch.equal(first[1], last[1]) and torch.equal(first[2], last[2])
 
 
-def test_binned_is_the_default_for_wide_rows():
-    assert _cabi.backward_plan(2, 5376, 8, 64, 3, 5376, 4, torch.float32, 0) == 2
-    assert _cabi.backward_plan(2, 5376, 8, 32, 3, 5376, 4, torch.float32, 0) == 1
+def test_binned_is_the_default_where_it_fits():
+    for D in (16, 32, 64, 128):
+        for dt in (torch.float32, torch.bfloat16):
+            assert _cabi.backward_plan(2, 5376, 8, D, 3, 5376, 4, dt, 0) == 2
+    assert _cabi.backward_plan(2, 5376, 8, 32, 3, 5376, 4, torch.float32, _cabi.FLAG_BWD_PER_TAP) == 1
     assert _cabi.backward_plan(2, 5376, 8, 32, 3, 5376, 4, torch.float32, _cabi.FLAG_BWD_BINNED) == 2
     assert _cabi.backward_plan(2, 5376, 8, 30, 3, 5376, 4, torch.float32, _cabi.FLAG_BWD_BINNED) == 0
+    # more pixels per image than the record header holds (15 bits): per-tap kernel
+    assert _cabi.backward_plan(1, 40000, 8, 32, 1, 100, 4, torch.float32, 0) == 1
