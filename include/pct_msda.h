@@ -84,9 +84,10 @@ extern "C" {
                                             half the L2 reduction traffic (6-20 % faster), about twice
                                             the error (4-7e-3 against 2-3e-3 of max|grad_value|).  The
                                             scale (from max|grad_out|, max sum|attn| and Lq) rules out
-                                            overflow, but an element that receives more than ~2000
-                                            same-signed contributions stops growing (11-bit running
-                                            sum) -- hence opt-in */
+                                            overflow, but an element that receives hundreds of EQUAL
+                                            same-signed contributions is off by percents (biased
+                                            rounding) and beyond ~2000 it stops growing (11-bit
+                                            running sum) -- hence opt-in */
 #define PCT_MSDA_FLAG_DETERMINISTIC 0x10u /* backward: bit-reproducible grad_value (64-bit fixed-point
                                             integer reductions; needs pct_msda_backward_workspace_bytes_ex
                                             bytes of workspace; vector-path shapes only, else

@@ -413,7 +413,8 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
   if ((flags & PCT_MSDA_FLAG_BF16_F16_ACCUM) && value_dtype == PCT_MSDA_BF16 && !det_fn && !bf16_accum &&
       n_value >= 64 && n_pairs > 0 && !(flags & PCT_MSDA_FLAG_FORCE_GENERIC) &&
       aligned(grad_sampling_loc, 8) && workspace && aligned(workspace, 16) &&
-      !binned_plan(d, value_dtype, fused ? (flags | PCT_MSDA_FLAG_BWD_PER_TAP) : flags, smem_optin, value,
+      // (an explicit request for the binned kernel wins over this per-tap option, the default does not)
+      !binned_plan(d, value_dtype, (fused || !(flags & PCT_MSDA_FLAG_BWD_BINNED)) ? (flags | PCT_MSDA_FLAG_BWD_PER_TAP) : flags, smem_optin, value,
                    grad_output, workspace, sampling_loc, attn_weight, grad_sampling_loc)) {
     const VecPlan p = vec_eligible(d, value_dtype, flags, value, grad_output, workspace, sampling_loc,
                                    attn_weight);

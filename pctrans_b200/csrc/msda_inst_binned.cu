@@ -35,8 +35,8 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
   bl.smem_bytes = dyn;
   bl.qc_cap = (int)((flags >> 25) & 0x7fu) * 8;
   if (bl.qc_cap == 0) {
-    // Small problems: when the chunks that fit shared memory would leave SMs without a task,
-    // shorter chunks give every SM one (the kernel takes the smaller of this cap and what fits).
+    // Small problems: when the chunks that fit shared memory would give the SMs fewer than one and
+    // a half tasks each, shorter chunks do (the kernel takes the smaller of this cap and what fits).
     const long long streams = (long long)d.N * d.M;
     const long long per_q = pct::bin_bytes_per_query(d.L * d.P, LPP * 4 * (int)sizeof(T));
     long long qc_fit = (dyn - pct::bin_bytes_fixed(2ll * d.S + 2ll * d.L)) / per_q;
@@ -44,8 +44,13 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
     if (qc_fit < kBinMinChunk) qc_fit = kBinMinChunk;
     const long long chunks_fit = (d.Lq + qc_fit - 1) / qc_fit;
     const long long sms = (long long)sm_count * pct::kBinCtasPerSm;
-    if (streams * chunks_fit * 4 < sms * 3) {
-      const long long want_chunks = (sms + streams - 1) / streams;
+    if (streams * chunks_fit * 2 < sms * 3) {
+      // Measured (profiles/r02_binned_v3_small_batches.log): with fewer tasks than SMs, one task per
+      // SM; with about one per SM, one and a half -- tasks differ in length (the chunk that holds
+      // the coarse levels' queries touches cells all over the maps) and are handed out dynamically.
+      const long long want_chunks = streams * chunks_fit * 4 < sms * 3
+                                        ? (sms + streams - 1) / streams
+                                        : (3 * sms + 2 * streams - 1) / (2 * streams);
       long long cap = ((d.Lq + want_chunks - 1) / want_chunks + 7) & ~7ll;
       if (cap < kBinMinChunk) cap = kBinMinChunk;
       if (cap < qc_fit) bl.qc_cap = (int)cap;

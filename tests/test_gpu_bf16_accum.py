@@ -33,7 +33,9 @@ def test_fp16_accumulator_accuracy(shapes, D, regime, gscale):
     g = torch.randn(2, loc.shape[1], 8 * D, generator=torch.Generator().manual_seed(2)) * gscale
     value, g = value.bfloat16().float(), g.bfloat16().float()
     gv, gl, ga = run(value, sh, lsi, loc, attn, g, flags=_cabi.FLAG_BF16_F16_ACCUM)
-    fv, fl, fa = run(value, sh, lsi, loc, attn, g)
+    # (the same per-tap kernel with the default fp32 scratch image; the library's default for these
+    # shapes is the cell-binned kernel, whose other two gradients differ in the last bits)
+    fv, fl, fa = run(value, sh, lsi, loc, attn, g, flags=_cabi.FLAG_BWD_PER_TAP)
     rv, rl, ra = oracle.backward_c(value, sh, lsi, loc, attn, g)
     e_half, e_f32 = rel(gv, rv), rel(fv, rv)
     print(f"grad_value error vs fp64 oracle: fp16 accumulator {e_half:.2e}, fp32 scratch {e_f32:.2e}")
@@ -46,8 +48,10 @@ def test_fp16_accumulator_accuracy(shapes, D, regime, gscale):
 def test_fp16_accumulator_cannot_overflow(Lq):
     """Worst case for the bound: every query puts all of its weight on the same pixel and grad_out
     is constant and large -> one element receives Lq * max|grad_out| (x a row sum above one).  The
-    scale keeps it finite; up to ~2000 same-signed addends the 11-bit running sum is also accurate,
-    beyond that it stops growing -- the documented reason the mode is opt-in."""
+    scale keeps it finite.  With EQUAL same-signed addends round-to-nearest is biased the same way at
+    every step (the sum walks on a grid coarser than the addend), so a few hundred of them already
+    cost percents, and beyond ~2000 the 11-bit running sum stops growing -- the documented reason
+    the mode is opt-in."""
     shapes = ((8, 8), (4, 4))
     N, M, D, L, P = 1, 2, 32, 2, 2
     sh, lsi, S = synth.level_tensors(shapes)
@@ -61,7 +65,7 @@ def test_fp16_accumulator_cannot_overflow(Lq):
     assert torch.isfinite(gv.float()).all()
     assert abs(float(rv.max()) / (1.75 * 3.0e4 * Lq) - 1) < 0.01   # the bound is attained
     if Lq <= 2000:
-        assert rel(gv, rv) <= 1e-2
+        assert rel(gv, rv) <= 0.1      # biased rounding of equal addends, bounded (measured 5e-2)
     else:
         assert rel(gv, rv) > 1e-2      # stagnation; the default fp32 scratch image has no such limit
         fv, _, _ = run(value, sh, lsi, loc, attn, g)
