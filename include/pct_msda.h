@@ -198,6 +198,19 @@ int pct_msda_fused_backward(const void* value, const int64_t* spatial_shapes,
                             int value_dtype, void* workspace, size_t workspace_bytes,
                             void* cuda_stream);
 
+/* The same with option bits: PCT_MSDA_FLAG_BWD_PER_TAP / PCT_MSDA_FLAG_BWD_BINNED choose between the
+ * fused per-tap and the fused cell-binned gradient kernel (default: cell-binned wherever it fits,
+ * as for pct_msda_backward_ex), PCT_MSDA_FLAG_BF16_F16_ACCUM as above; any other option bit returns
+ * PCT_MSDA_E_UNSUPPORTED. */
+int pct_msda_fused_backward_ex(const void* value, const int64_t* spatial_shapes,
+                               const int64_t* level_start_index, const void* reference_points,
+                               int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                               const void* grad_output, void* grad_value, void* grad_offsets,
+                               void* grad_logits, int batch, int spatial_size, int num_heads,
+                               int channels, int num_levels, int num_query, int num_point,
+                               int value_dtype, void* workspace, size_t workspace_bytes,
+                               void* cuda_stream, unsigned flags);
+
 /*
  * Host pipeline: the same op for callers whose tensors live in HOST memory (the end-to-end path
  * bench.py reports as `e2e`).  A context owns three CUDA streams and device staging buffers that

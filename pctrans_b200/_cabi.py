@@ -26,7 +26,7 @@ EXPORTS = (
     "pct_msda_kernel_family", "pct_msda_backward_plan", "pct_msda_forward", "pct_msda_forward_ex",
     "pct_msda_backward_workspace_bytes", "pct_msda_backward_workspace_bytes_ex",
     "pct_msda_backward", "pct_msda_backward_ex",
-    "pct_msda_fused_forward", "pct_msda_fused_backward",
+    "pct_msda_fused_forward", "pct_msda_fused_backward", "pct_msda_fused_backward_ex",
     "pct_msda_host_ctx_create", "pct_msda_host_ctx_destroy", "pct_msda_host_forward",
     "pct_msda_host_forward_backward",
 )
@@ -95,6 +95,8 @@ def load():
         lib.pct_msda_fused_forward.argtypes = [vp] * 4 + [i32] + [vp] * 3 + [i32] * 8 + [vp]
         lib.pct_msda_fused_backward.restype = i32
         lib.pct_msda_fused_backward.argtypes = [vp] * 4 + [i32] + [vp] * 6 + [i32] * 8 + [vp, sz, vp]
+        lib.pct_msda_fused_backward_ex.restype = i32
+        lib.pct_msda_fused_backward_ex.argtypes = [vp] * 4 + [i32] + [vp] * 6 + [i32] * 8 + [vp, sz, vp, u32]
         # include/pct_linear.h
         lib.pct_linear_packed_bytes.restype = sz
         lib.pct_linear_packed_bytes.argtypes = [i32, i32]
@@ -213,7 +215,7 @@ def fused_forward(value, spatial_shapes, level_start_index, reference_points, sa
 
 
 def fused_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
-                   attn_logits, grad_output, workspace=None):
+                   attn_logits, grad_output, workspace=None, flags=0):
     """Returns (grad_value, grad_sampling_offsets, grad_attn_logits)."""
     lib = load()
     N, S, M, D = value.shape
@@ -228,13 +230,13 @@ def fused_backward(value, spatial_shapes, level_start_index, reference_points, s
     if ws_bytes and (ws is None or ws.numel() < ws_bytes):
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device)
     with torch.cuda.device_of(value):
-        rc = lib.pct_msda_fused_backward(
+        rc = lib.pct_msda_fused_backward_ex(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             reference_points.data_ptr(), reference_points.shape[-1], sampling_offsets.data_ptr(),
             attn_logits.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
             grad_off.data_ptr(), grad_logits.data_ptr(), N, S, M, D, L, Lq, P, code,
-            ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(value.device))
-    check(rc, "pct_msda_fused_backward")
+            ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(value.device), flags)
+    check(rc, "pct_msda_fused_backward_ex")
     return grad_value, grad_off, grad_logits
 
 

@@ -74,8 +74,9 @@ struct BinLaunch {
 };
 
 // Shared-memory bytes a chunk of one query needs: records + grad_out row + position of each sample.
-__host__ __device__ inline int bin_bytes_per_query(int LP, int row_bytes) {
-  return LP * 16 + row_bytes + LP * 2;
+// (fused: + the pair's softmax maximum, 1/normaliser and sum_t a_t g_t)
+__host__ __device__ inline int bin_bytes_per_query(int LP, int row_bytes, bool fused = false) {
+  return LP * 16 + row_bytes + LP * 2 + (fused ? 12 : 0);
 }
 // Shared-memory bytes that depend on the number of cells NC only: the counters / bin offsets and
 // the list of non-empty cells in the order of the sweep.
@@ -261,14 +262,19 @@ struct BinRowS<__nv_bfloat16> {
 #define PCT_BIN_ASSERT(c) do { } while (0)
 #endif
 
-template <typename T, int LPP>
+// FUSED (same contract as the FUSED per-tap kernels in msda_kernels.cuh):
+// `loc` holds the module's raw sampling offsets and `attn` its raw attention logits; the binning
+// passes evaluate loc = ref + off/(W,H) (or the box form) and the softmax over the pair's L*P
+// logits, and the final pass writes d/d(offsets) and the softmax backward a_s (g_s - sum_t a_t g_t)
+// instead of grad_sampling_loc / grad_attn_weight.
+template <typename T, int LPP, bool FUSED>
 __global__ void __launch_bounds__(kBinThreads, kBinCtasPerSm)
 msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                        const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                        const float* __restrict__ attn, const T* __restrict__ grad_out,
                        float* __restrict__ gacc, float* __restrict__ grad_loc,
                        float* __restrict__ grad_attn, int N, int S, int M, int L, int Lq, int P,
-                       BinLaunch bl) {
+                       BinLaunch bl, FusedRef fr) {
   constexpr int VE = 4;
   constexpr int VB = VE * (int)sizeof(T);
   using CV = ChanVec<T, VB>;
@@ -313,7 +319,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   // ---- chunk geometry (identical in every CTA: a function of the shapes only) ----
   const int NC = s_nc;
   const int cnt_words = (NC + 1 + 3) & ~3;
-  const int per_q = bin_bytes_per_query(LP, ROWB);
+  const int per_q = bin_bytes_per_query(LP, ROWB, FUSED);
   int qc_max = (bl.smem_bytes - (int)bin_bytes_fixed(NC)) / per_q;
   if (qc_max > kBinMaxQc) qc_max = kBinMaxQc;
   if (qc_max > 65528 / LP) qc_max = 65528 / LP;   // 16-bit record positions, 0xffff = none
@@ -330,6 +336,10 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   unsigned int* const cnt = reinterpret_cast<unsigned int*>(smem + (size_t)QC * ROWB + (size_t)QC * LP * 16);
   unsigned short* const posarr = reinterpret_cast<unsigned short*>(cnt + cnt_words);
   unsigned short* const klist = posarr + (size_t)QC * LP;   // (QC*LP*2 is a multiple of 16)
+  // fused softmax state per query of the chunk: maximum logit, 1 / normaliser, sum_t a_t g_t
+  float* const sm_max = reinterpret_cast<float*>(klist + ((NC + 7) & ~7));
+  float* const sm_inv = sm_max + QC;
+  float* const sm_dot = sm_inv + QC;
 
   const int grp = tid / LPP, sub = tid % LPP;
   unsigned int* const ctr = g_sched + 2 * bl.slot;
@@ -387,6 +397,27 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     // ---- P0: clear the cell counters, start staging the chunk's grad_out rows ----
     for (int i = tid; i < cnt_words; i += kBinThreads) cnt[i] = 0u;
     if (tid < 64) s_hist[tid] = 0u;
+    // reference points of the chunk's first query (fused): (L, ref_dim) floats per query
+    const float* const ref0 = FUSED ? fr.ref + ((long long)b * Lq + q0) * L * fr.ref_dim : nullptr;
+    if (FUSED) {
+      // softmax over the L*P logits of every (query, head) pair of the chunk (mod.py:104)
+      for (int ql = tid; ql < nq; ql += kBinThreads) {
+        const float* ap = attn1 + ql * qstep;
+        float mx = -INFINITY, es = 0.f;
+        for (int s = 0; s < LP; ++s) mx = fmaxf(mx, __ldg(ap + s));
+        for (int s = 0; s < LP; ++s) es += expf(__ldg(ap + s) - mx);
+        sm_max[ql] = mx;
+        sm_inv[ql] = 1.f / es;
+      }
+    }
+    // sampling location of sample (ql, s) from what `loc` holds
+    auto sample_xy = [&](float2 raw, int ql, int s) -> float2 {
+      if (!FUSED) return raw;
+      if (ql >= nq) return make_float2(-4.f, -4.f);   // padding of the last batch: outside every map
+      const int lvl = s_slvl[s];
+      const int2 hw = make_int2(s_lvl[lvl].H, s_lvl[lvl].W);
+      return fused_location(ref0 + (long long)ql * L * fr.ref_dim, fr.ref_dim, lvl, raw, hw.x, hw.y, P);
+    };
     {
       const T* gsrc = grad_out + ((long long)((long long)b * Lq + q0) * M + m) * D;
       const unsigned dst0 = (unsigned)__cvta_generic_to_shared(go_s);
@@ -407,10 +438,10 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
       int ql = tid / LP, s = tid - ql * LP;
       for (int k0 = tid; k0 < ntaps; k0 += UB * kBinThreads) {
         float2 xy[UB];
-        int ss[UB];
+        int ss[UB], qq[UB];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-          ss[u] = s;
+          ss[u] = s; qq[u] = ql;
           xy[u] = (k0 + u * kBinThreads < ntaps) ? __ldg(loc2 + ql * qstep + s)
                                                 : make_float2(-4.f, -4.f);   // outside every map
           ql += dq; s += ds;
@@ -420,7 +451,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
         for (int u = 0; u < UB; ++u) {
           float lw, lh;
           int lvl;
-          const int cell = locate(xy[u], ss[u], lw, lh, lvl);
+          const int cell = locate(sample_xy(xy[u], qq[u], ss[u]), ss[u], lw, lh, lvl);
           if (cell >= 0) {
             PCT_BIN_ASSERT(cell < NC);
             atomicAdd(cnt + cell, 1u);
@@ -505,13 +536,14 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
           if (k < ntaps) {
             float lw = 0.f, lh = 0.f;
             unsigned hdr = 0u;
-            const int cell = locate_full(xy[u], ss[u], lw, lh, hdr);
+            const int cell = locate_full(sample_xy(xy[u], qq[u], ss[u]), ss[u], lw, lh, hdr);
             unsigned pos = kBinNoPos;
             if (cell >= 0) {
               pos = atomicAdd(cnt + cell, 1u) & 0xffffu;
               PCT_BIN_ASSERT(pos < (unsigned)ntaps);
+              const float a = FUSED ? expf(aw[u] - sm_max[qq[u]]) * sm_inv[qq[u]] : aw[u];
               rec[pos] = make_uint4(hdr | (unsigned)qq[u], __float_as_uint(lw), __float_as_uint(lh),
-                                    __float_as_uint(aw[u]));
+                                    __float_as_uint(a));
             }
             posarr[k] = (unsigned short)pos;
           }
@@ -665,20 +697,50 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     __syncthreads();
 
     // ---- final: coalesced grad_sampling_loc / grad_attn_weight in sample order ----
+    if (FUSED) {
+      // sum_t a_t g_t of every pair for the softmax backward (samples the reference skips have g = 0)
+      for (int ql = tid; ql < nq; ql += kBinThreads) {
+        float dot = 0.f;
+        for (int s = 0; s < LP; ++s) {
+          const unsigned pos = posarr[ql * LP + s];
+          if (pos != kBinNoPos) {
+            const uint4 rc = rec[pos];
+            dot = fmaf(__uint_as_float(rc.w), __uint_as_float(rc.x), dot);
+          }
+        }
+        sm_dot[ql] = dot;
+      }
+      __syncthreads();
+    }
     {
       int ql = tid / LP, s = tid - ql * LP;
       for (int k2 = tid; k2 < ntaps; k2 += kBinThreads) {
         const unsigned pos = posarr[k2];
         float ga = 0.f, gx = 0.f, gy = 0.f;    // out-of-range samples: exact zeros (cu:126-128)
+        float a = 0.f;
+        const int lvl = s_slvl[s];
         if (pos != kBinNoPos) {
           const uint4 rc = rec[pos];           // {val . grad_out, grad_w_weight, grad_h_weight, attn}
-          const float2 F = *reinterpret_cast<const float2*>(&s_lvl[s_slvl[s]].Hf);
-          const float a = __uint_as_float(rc.w);
+          const float2 F = *reinterpret_cast<const float2*>(&s_lvl[lvl].Hf);
+          a = __uint_as_float(rc.w);
           ga = __uint_as_float(rc.x);                       // cuh:161
           gx = F.y * __uint_as_float(rc.y) * a;             // cuh:162  W * grad_w_weight * attn
           gy = F.x * __uint_as_float(rc.z) * a;             // cuh:163  H * grad_h_weight * attn
         }
         const long long si = samp0 + ql * qstep + s;
+        if (FUSED) {
+          // d(location)/d(raw offset) (mod.py:106-112) and the softmax backward
+          if (pos == kBinNoPos) a = expf(__ldg(attn + si) - sm_max[ql]) * sm_inv[ql];
+          else if (fr.ref_dim == 2) {
+            gx *= __fdiv_rn(1.f, (float)s_lvl[lvl].W);
+            gy *= __fdiv_rn(1.f, (float)s_lvl[lvl].H);
+          } else {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(ref0 + (long long)ql * L * 4) + lvl);
+            gx *= __fdiv_rn(r.z * 0.5f, (float)P);
+            gy *= __fdiv_rn(r.w * 0.5f, (float)P);
+          }
+          ga = a * (ga - sm_dot[ql]);
+        }
         __stcs(grad_attn + si, ga);
         __stcs(reinterpret_cast<float2*>(grad_loc) + si, make_float2(gx, gy));
         ql += dq; s += ds;

@@ -189,7 +189,7 @@ int device_smem_optin(int* out) {
 // 0 = not eligible, else lanes per (query, head) row
 int binned_plan(const Dims& d, int dtype, unsigned flags, int smem_optin, const void* value,
                 const void* grad_out, const void* acc, const void* loc, const void* attn,
-                const void* grad_loc) {
+                const void* grad_loc, bool fused = false) {
   if (flags & (PCT_MSDA_FLAG_FORCE_GENERIC | PCT_MSDA_FLAG_BWD_PER_TAP)) return 0;
   // Measured on B200 (profiles/r02_binned_v3_*.log): in its round-2 form (bilinear-basis sweep in
   // lock-step rounds) the binned kernel is faster than the per-tap kernel on every shape it fits
@@ -208,7 +208,7 @@ int binned_plan(const Dims& d, int dtype, unsigned flags, int smem_optin, const 
   if (nc_bound > pct::kBinMaxCells) return 0;
   const int row_bytes = d.D * (int)elem_size(dtype);
   const long long fixed = pct::bin_bytes_fixed(nc_bound) + 1536;   // + the kernel's static arrays
-  if (fixed + (long long)kBinMinChunk * pct::bin_bytes_per_query((int)LP, row_bytes) > smem_optin) return 0;
+  if (fixed + (long long)kBinMinChunk * pct::bin_bytes_per_query((int)LP, row_bytes, fused) > smem_optin) return 0;
   const size_t vb = 4 * elem_size(dtype);
   if (!aligned(value, vb) || !aligned(grad_out, 16) || !aligned(acc, 16) || !aligned(loc, 8) ||
       !aligned(attn, 4) || !aligned(grad_loc, 8))
@@ -414,8 +414,8 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
       n_value >= 64 && n_pairs > 0 && !(flags & PCT_MSDA_FLAG_FORCE_GENERIC) &&
       aligned(grad_sampling_loc, 8) && workspace && aligned(workspace, 16) &&
       // (an explicit request for the binned kernel wins over this per-tap option, the default does not)
-      !binned_plan(d, value_dtype, (fused || !(flags & PCT_MSDA_FLAG_BWD_BINNED)) ? (flags | PCT_MSDA_FLAG_BWD_PER_TAP) : flags, smem_optin, value,
-                   grad_output, workspace, sampling_loc, attn_weight, grad_sampling_loc)) {
+      !binned_plan(d, value_dtype, !(flags & PCT_MSDA_FLAG_BWD_BINNED) ? (flags | PCT_MSDA_FLAG_BWD_PER_TAP) : flags, smem_optin, value,
+                   grad_output, workspace, sampling_loc, attn_weight, grad_sampling_loc, fused)) {
     const VecPlan p = vec_eligible(d, value_dtype, flags, value, grad_output, workspace, sampling_loc,
                                    attn_weight);
     if (p.lanes > 0) half_fn = pick_bwd_half_accum(fused, p);
@@ -501,14 +501,15 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
-  const int bin_lanes = (det_fn || bf16_accum || half_fn || fused)
+  const int bin_lanes = (det_fn || bf16_accum || half_fn)
                             ? 0
                             : binned_plan(d, value_dtype, flags, smem_optin, value, grad_output, acc_image,
-                                          sampling_loc, attn_weight, grad_sampling_loc);
+                                          sampling_loc, attn_weight, grad_sampling_loc, fused);
   if (bin_lanes) {
     rc = dispatch_bwd_binned(bin_lanes, value_dtype, value, spatial_shapes, level_start_index,
                              sampling_loc, attn_weight, grad_output, acc_image, grad_sampling_loc,
-                             grad_attn_weight, d, sm_count, smem_optin, st, flags);
+                             grad_attn_weight, d, sm_count, smem_optin, st, flags,
+                             fused ? fr : pct::FusedRef{nullptr, 0});
   } else if (BwdLauncher fn = det_fn          ? det_fn
                               : half_fn       ? half_fn
                               : bf16_accum    ? bf16_accum
@@ -593,6 +594,24 @@ int pct_msda_fused_backward(const void* value, const int64_t* spatial_shapes,
                             int channels, int num_levels, int num_query, int num_point,
                             int value_dtype, void* workspace, size_t workspace_bytes,
                             void* cuda_stream) {
+  return pct_msda_fused_backward_ex(value, spatial_shapes, level_start_index, reference_points, ref_dim,
+                                    sampling_offsets, attn_logits, grad_output, grad_value,
+                                    grad_offsets, grad_logits, batch, spatial_size, num_heads,
+                                    channels, num_levels, num_query, num_point, value_dtype,
+                                    workspace, workspace_bytes, cuda_stream, 0u);
+}
+
+int pct_msda_fused_backward_ex(const void* value, const int64_t* spatial_shapes,
+                               const int64_t* level_start_index, const void* reference_points,
+                               int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                               const void* grad_output, void* grad_value, void* grad_offsets,
+                               void* grad_logits, int batch, int spatial_size, int num_heads,
+                               int channels, int num_levels, int num_query, int num_point,
+                               int value_dtype, void* workspace, size_t workspace_bytes,
+                               void* cuda_stream, unsigned flags) {
+  if (flags & ~(PCT_MSDA_FLAG_BWD_PER_TAP | PCT_MSDA_FLAG_BWD_BINNED | PCT_MSDA_FLAG_BF16_F16_ACCUM |
+                0xffffff00u))
+    return PCT_MSDA_E_UNSUPPORTED;   // the other options exist for the plain entry point only
   if (ref_dim != 2 && ref_dim != 4) return PCT_MSDA_E_BAD_SHAPE;
   if ((long long)batch * num_query > 0 && !reference_points) return PCT_MSDA_E_NULL_POINTER;
   if (!aligned(reference_points, ref_dim == 2 ? 8 : 16)) return PCT_MSDA_E_MISALIGNED;
@@ -601,7 +620,7 @@ int pct_msda_fused_backward(const void* value, const int64_t* spatial_shapes,
   return backward_impl(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
                        grad_output, grad_value, grad_offsets, grad_logits, batch, spatial_size,
                        num_heads, channels, num_levels, num_query, num_point, value_dtype,
-                       workspace, workspace_bytes, cuda_stream, 0u,
+                       workspace, workspace_bytes, cuda_stream, flags,
                        pct::FusedRef{(const float*)reference_points, ref_dim});
 }
 

@@ -8,16 +8,16 @@
 namespace pctl {
 namespace {
 
-template <typename T, int LPP>
+template <typename T, int LPP, bool FUSED>
 int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                       const void* attn, const void* grad_out, void* gacc, void* grad_loc,
                       void* grad_attn, const Dims& d, int sm_count, int smem_optin, cudaStream_t st,
-                      unsigned flags) {
+                      unsigned flags, pct::FusedRef fr) {
   static std::atomic<int> configured[64];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
-  auto kern = pct::msda_bwd_binned_kernel<T, LPP>;
+  auto kern = pct::msda_bwd_binned_kernel<T, LPP, FUSED>;
   // dynamic shared memory = the opt-in maximum minus the kernel's static arrays
   int dyn = (dev >= 0 && dev < 64) ? configured[dev].load(std::memory_order_acquire) : 0;
   if (dyn == 0) {
@@ -38,7 +38,7 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
     // Small problems: when the chunks that fit shared memory would give the SMs fewer than one and
     // a half tasks each, shorter chunks do (the kernel takes the smaller of this cap and what fits).
     const long long streams = (long long)d.N * d.M;
-    const long long per_q = pct::bin_bytes_per_query(d.L * d.P, LPP * 4 * (int)sizeof(T));
+    const long long per_q = pct::bin_bytes_per_query(d.L * d.P, LPP * 4 * (int)sizeof(T), FUSED);
     long long qc_fit = (dyn - pct::bin_bytes_fixed(2ll * d.S + 2ll * d.L)) / per_q;
     if (qc_fit > pct::kBinMaxQc) qc_fit = pct::kBinMaxQc;
     if (qc_fit < kBinMinChunk) qc_fit = kBinMinChunk;
@@ -62,7 +62,7 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
   const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
   kern<<<grid, pct::kBinThreads, dyn, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
-      (float*)gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, bl);
+      (float*)gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, bl, fr);
   count_launches(1);
   return (int)cudaGetLastError();
 }
@@ -72,10 +72,14 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
 int dispatch_bwd_binned(int lanes, int dtype, const void* value, const int64_t* shapes,
                         const int64_t* lsi, const void* loc, const void* attn, const void* grad_out,
                         void* gacc, void* grad_loc, void* grad_attn, const Dims& d, int sm_count,
-                        int smem_optin, cudaStream_t st, unsigned flags) {
+                        int smem_optin, cudaStream_t st, unsigned flags, pct::FusedRef fr) {
 #define PCT_BIN_CASE(T, LPP)                                                                       \
-  return launch_bwd_binned<T, LPP>(value, shapes, lsi, loc, attn, grad_out, gacc, grad_loc,        \
-                                   grad_attn, d, sm_count, smem_optin, st, flags)
+  return fr.ref ? launch_bwd_binned<T, LPP, true>(value, shapes, lsi, loc, attn, grad_out, gacc,   \
+                                                  grad_loc, grad_attn, d, sm_count, smem_optin,    \
+                                                  st, flags, fr)                                   \
+                : launch_bwd_binned<T, LPP, false>(value, shapes, lsi, loc, attn, grad_out, gacc,  \
+                                                   grad_loc, grad_attn, d, sm_count, smem_optin,   \
+                                                   st, flags, fr)
   if (dtype == PCT_MSDA_F32) {
     switch (lanes) {
       case 4: PCT_BIN_CASE(float, 4);

@@ -157,3 +157,30 @@ def test_binned_is_the_default_where_it_fits():
     assert _cabi.backward_plan(2, 5376, 8, 30, 3, 5376, 4, torch.float32, _cabi.FLAG_BWD_BINNED) == 0
     # more pixels per image than the record header holds (15 bits): per-tap kernel
     assert _cabi.backward_plan(1, 40000, 8, 32, 1, 100, 4, torch.float32, 0) == 1
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("D,dtype", [(32, torch.float32), (16, torch.float32), (32, torch.bfloat16)])
+def test_fused_binned_matches_fused_per_tap(ref_dim, D, dtype):
+    """Fused prologue (raw offsets / logits in, d/d(offsets) and the softmax backward out) inside
+    the binned kernel, several chunks per (image, head): against the fused per-tap kernel and --
+    through tests/test_gpu_fused.py's composed fp64 reference -- against the oracle."""
+    from test_gpu_fused import make_case, reference
+    shapes, M, P = synth.CVPPP_448, 4, 4
+    value, sh, lsi, ref, off, logits, gout, norm = make_case(2, shapes, M, D, P, ref_dim, seed=11 + D)
+    if dtype == torch.bfloat16:
+        value, gout = value.bfloat16().float(), gout.bfloat16().float()
+    args = (value.to(DEV, dtype), sh.to(DEV), lsi.to(DEV), ref.to(DEV), off.to(DEV), logits.to(DEV),
+            gout.to(DEV, dtype))
+    bv, bo, bl = _cabi.fused_backward(*args, flags=_cabi.FLAG_BWD_BINNED)
+    pv, po, pl = _cabi.fused_backward(*args, flags=_cabi.FLAG_BWD_PER_TAP)
+    dv, do, dl = _cabi.fused_backward(*args)                      # the default is the binned kernel
+    torch.cuda.synchronize()
+    assert not torch.equal(bo, po)                                # two different kernels ran
+    assert torch.equal(bo, do) and torch.equal(bl, dl)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    _, r_gv, r_goff, r_glog = reference(value, sh, lsi, ref, off, logits, gout, norm, P)
+    for name, got, per_tap, want in (("grad_value", bv, pv, r_gv), ("grad_offsets", bo, po, r_goff),
+                                     ("grad_logits", bl, pl, r_glog)):
+        assert rel(got, want) <= tol, (name, rel(got, want))
+        assert rel(got, per_tap.float().cpu().numpy()) <= 2 * tol, name
