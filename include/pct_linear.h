@@ -38,6 +38,10 @@ extern "C" {
                                      not combinable with RESIDUAL / LAYERNORM */
 #define PCT_LINEAR_LAYERNORM 0x4u /* y = LayerNorm(. ) * gamma + beta over the out dim;
                                      needs out_features <= 256 (one tile holds a whole row) */
+#define PCT_LINEAR_ROWMASK 0x10u  /* rows whose byte in the (rows,) uint8 / bool mask passed in `residual` is
+                                     non-zero are written as zeros: the masked_fill of padded positions
+                                     after value_proj (OPS/modules/ms_deform_attn.py:100-101) in the
+                                     epilogue; not combinable with RESIDUAL / GATE / LAYERNORM */
 
 /* Constraints everywhere: in_features % 16 == 0, out_features % 16 == 0; x, packed weight, residual,
  * y, pre_norm, grad_y, grad_w, grad_bias 16-byte aligned (bias / LayerNorm vectors: 4-byte). */

@@ -32,7 +32,7 @@ EXPORTS = (
 )
 LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_forward",
                   "pct_linear_forward_train", "pct_linear_wgrad")
-LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM, LINEAR_GATE = 0x1, 0x2, 0x4, 0x8
+LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM, LINEAR_GATE, LINEAR_ROWMASK = 0x1, 0x2, 0x4, 0x8, 0x10
 E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
 FLAG_BF16_ACCUM = 0x8
@@ -256,10 +256,11 @@ def linear_pack_weight(weight):
 
 def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weight=None,
                    ln_bias=None, ln_eps: float = 1e-5, relu: bool = False, out=None,
-                   save_for_backward: bool = False, gate=None):
+                   save_for_backward: bool = False, gate=None, row_mask=None):
     """y = epilogue(x @ W^T + bias) on the tensor cores (3xTF32); x (rows, in) fp32 contiguous.
     With ``save_for_backward`` (LayerNorm epilogue only) returns (y, pre_norm, mean, rstd).
-    ``gate`` (rows, out): y is zeroed where gate <= 0 (ReLU backward fused into a dgrad GEMM)."""
+    ``gate`` (rows, out): y is zeroed where gate <= 0 (ReLU backward fused into a dgrad GEMM).
+    ``row_mask`` (rows,) bool / uint8: rows with a non-zero entry are written as zeros."""
     rows, k = x.shape
     n = out_features
     flags = (LINEAR_RELU if relu else 0) | (LINEAR_RESIDUAL if residual is not None else 0) | \
@@ -268,6 +269,13 @@ def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weigh
         if residual is not None:
             raise ValueError("gate and residual share an argument slot of the C ABI")
         residual = gate
+    if row_mask is not None:
+        if residual is not None or ln_weight is not None:
+            raise ValueError("row_mask shares an argument slot of the C ABI with residual / gate")
+        if row_mask.numel() != rows or row_mask.element_size() != 1 or not row_mask.is_contiguous():
+            raise ValueError("row_mask must be a contiguous (rows,) bool / uint8 tensor")
+        residual = row_mask
+        flags |= LINEAR_ROWMASK
     y = out if out is not None else torch.empty((rows, n), dtype=x.dtype, device=x.device)
     ptr = lambda t: t.data_ptr() if t is not None else None
     pre = mean = rstd = None

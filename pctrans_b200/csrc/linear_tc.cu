@@ -191,6 +191,11 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
   const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
   const bool relu = a.flags & PCT_LINEAR_RELU, has_res = a.flags & PCT_LINEAR_RESIDUAL;
   const bool has_gate = a.flags & PCT_LINEAR_GATE;   // `residual` holds the gate tensor instead
+  // PCT_LINEAR_ROWMASK: `residual` holds one byte per row; rows with a non-zero byte are written
+  // as zeros (the masked_fill after value_proj, mod.py:100-101) -- row domain: a thread owns a row
+  const int my_row = m0 + warp * 32 + lane;
+  const bool row_masked = (a.flags & PCT_LINEAR_ROWMASK) && my_row < a.rows &&
+                          reinterpret_cast<const unsigned char*>(a.residual)[my_row] != 0;
   float* patch = reinterpret_cast<float*>(smem) + warp * (32 * kPatchStride);
   float* patch_row = patch + lane * kPatchStride;
   const int l_row = lane >> 3, l_c4 = (lane & 7) * 4;
@@ -282,6 +287,10 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
       if (relu) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (row_masked) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
       store_block(a.y, c, cw, has_gate);
       if (has_gate && c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
@@ -1065,16 +1074,23 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
   if ((ln_mean == nullptr) != (ln_rstd == nullptr)) return PCT_MSDA_E_NULL_POINTER;
   if ((pre_norm || ln_mean) && !(flags & PCT_LINEAR_LAYERNORM)) return PCT_MSDA_E_UNSUPPORTED;
   if (misaligned(pre_norm)) return PCT_MSDA_E_MISALIGNED;
-  if ((flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE)) && !residual) return PCT_MSDA_E_NULL_POINTER;
+  if ((flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE | PCT_LINEAR_ROWMASK)) && !residual)
+    return PCT_MSDA_E_NULL_POINTER;
   if ((flags & PCT_LINEAR_LAYERNORM) && (!ln_gamma || !ln_beta)) return PCT_MSDA_E_NULL_POINTER;
   if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
   if ((flags & PCT_LINEAR_LAYERNORM) && out_features > kBlockN) return PCT_MSDA_E_UNSUPPORTED;
-  if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM | PCT_LINEAR_GATE))
+  if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM | PCT_LINEAR_GATE |
+                PCT_LINEAR_ROWMASK))
     return PCT_MSDA_E_UNSUPPORTED;
   if ((flags & PCT_LINEAR_GATE) && (flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM)))
     return PCT_MSDA_E_UNSUPPORTED;
+  if ((flags & PCT_LINEAR_ROWMASK) &&
+      (flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM | PCT_LINEAR_GATE)))
+    return PCT_MSDA_E_UNSUPPORTED;
   // 16-byte accesses: x, packed W, residual, y, pre_norm; bias / gamma / beta are read as scalars
-  if (misaligned(x) || misaligned(w_packed) || misaligned(y) || misaligned(residual))
+  // (and the row mask as bytes)
+  if (misaligned(x) || misaligned(w_packed) || misaligned(y) ||
+      (!(flags & PCT_LINEAR_ROWMASK) && misaligned(residual)))
     return PCT_MSDA_E_MISALIGNED;
   if (((uintptr_t)bias | (uintptr_t)ln_gamma | (uintptr_t)ln_beta | (uintptr_t)ln_mean |
        (uintptr_t)ln_rstd) & 3u)

@@ -67,15 +67,19 @@ def eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
 
 
 class TensorCoreLinearFunction(Function):
-    """y = [relu](x @ W^T + b [+ residual]); gradients for x, W, b and residual."""
+    """y = [relu](x @ W^T + b [+ residual]); gradients for x, W, b and residual.  ``row_mask``
+    (bool, one entry per row of x): masked rows of y are zeros (mod.py:100-101) -- written by the
+    GEMM's epilogue -- and pass no gradient."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu):
+    def forward(ctx, x, weight, bias, residual, relu, row_mask=None):
         n, k = weight.shape
         x2 = x.reshape(-1, k).contiguous()
         res2 = residual.reshape(-1, n).contiguous() if residual is not None else None
         b = bias.detach().contiguous() if bias is not None else None
-        y = _cabi.linear_forward(x2, packed_weight(weight), n, b, res2, relu=relu)
+        mask = row_mask.reshape(-1).contiguous() if row_mask is not None else None
+        y = _cabi.linear_forward(x2, packed_weight(weight), n, b, res2, relu=relu, row_mask=mask)
+        ctx.mask = mask
         ctx.relu = relu
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
@@ -91,6 +95,8 @@ class TensorCoreLinearFunction(Function):
         g = grad_y.reshape(-1, n).contiguous()
         if ctx.relu:
             g = torch.ops.aten.threshold_backward(g, y, 0.0)     # one pass: g where y > 0 else 0
+        if ctx.mask is not None:
+            g = g.masked_fill(ctx.mask.view(-1, 1).bool(), 0.0)   # masked rows pass no gradient
         gx = gw = gb = gres = None
         if ctx.needs_input_grad[0]:
             # dX = dY @ W: the same kernel with the transposed weight as its operand
@@ -103,7 +109,7 @@ class TensorCoreLinearFunction(Function):
             gb = g.sum(0)
         if ctx.has_res and ctx.needs_input_grad[3]:
             gres = g.view(*ctx.x_shape[:-1], n)
-        return gx, gw, gb, gres, None
+        return gx, gw, gb, gres, None, None
 
 
 class LinearResidualLayerNormFunction(Function):
@@ -207,14 +213,18 @@ def ffn_block(src, linear1, linear2, norm):
     return linear_residual_layernorm(hidden, linear2.weight, linear2.bias, src, norm)
 
 
-def linear(x, weight, bias=None, residual=None, relu: bool = False):
-    """``[relu](F.linear(x, weight, bias) [+ residual])`` -- on the tensor cores when eligible."""
-    if eligible(x, weight):
-        return TensorCoreLinearFunction.apply(x, weight, bias, residual, relu)
+def linear(x, weight, bias=None, residual=None, relu: bool = False, row_mask=None):
+    """``[relu](F.linear(x, weight, bias) [+ residual])`` -- on the tensor cores when eligible.
+    ``row_mask`` (bool, shape of x without its last dim): ``.masked_fill(row_mask[..., None], 0)``
+    on the result, done by the GEMM's epilogue on the tensor-core path."""
+    if eligible(x, weight) and (row_mask is None or (residual is None and row_mask.is_cuda)):
+        return TensorCoreLinearFunction.apply(x, weight, bias, residual, relu, row_mask)
     y = F.linear(x, weight, bias)
     if residual is not None:
         y = y + residual
-    return F.relu(y) if relu else y
+    if relu:
+        y = F.relu(y)
+    return y.masked_fill(row_mask[..., None], 0.0) if row_mask is not None else y
 
 
 def linear_residual_layernorm(x, weight, bias, residual, norm: torch.nn.LayerNorm):

@@ -89,9 +89,14 @@ class MSDeformAttn(nn.Module):
     # -- pieces of forward ---------------------------------------------------------------------
     def _values(self, input_flatten, input_padding_mask):
         """(N, S, M, D) projected values with padded positions zeroed (mod.py:98-101)."""
-        value = self._proj(self.value_proj, input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        if self.tensor_core_linears:
+            # the padding mask rides in the epilogue of the projection (PCT_LINEAR_ROWMASK)
+            value = linear_tc.linear(input_flatten, self.value_proj.weight, self.value_proj.bias,
+                                     row_mask=input_padding_mask)
+        else:
+            value = self.value_proj(input_flatten)
+            if input_padding_mask is not None:
+                value = value.masked_fill(input_padding_mask[..., None], 0.0)
         n, s, _ = value.shape
         return value.view(n, s, self.n_heads, self.d_model // self.n_heads)
 

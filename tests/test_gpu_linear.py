@@ -357,3 +357,34 @@ def test_encoder_with_tensor_core_linears_matches_torch_linears(mode):
             worst[k] = float((grads[0][k].double() - grads[1][k].double()).norm()) / den
         bad = {k: v for k, v in worst.items() if v > 3e-2}
         assert not bad, sorted(bad.items(), key=lambda t: -t[1])[:5]
+
+
+def test_row_mask_epilogue_is_masked_fill_with_gradients():
+    """PCT_LINEAR_ROWMASK: value_proj + masked_fill(padding_mask) (mod.py:98-101) as one kernel --
+    output rows exactly zero, gradients of x / W / b those of the masked composition (fp64)."""
+    from pctrans_b200.functions import linear_tc
+    x, w, b, _ = _case(2 * 517, 256, 256, seed=11)
+    x = x.view(2, 517, 256)
+    mask = torch.zeros(2, 517, dtype=torch.bool, device="cuda")
+    mask[0, -40:] = True
+    mask[1, 100:130] = True
+    xg, wg, bg = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y = linear_tc.linear(xg, wg, bg, row_mask=mask)
+    assert bool((y[mask] == 0).all()) and bool((y[~mask] != 0).any())
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xd, wd, bd = (t.double().detach().requires_grad_(True) for t in (x, w, b))
+    yd = torch.nn.functional.linear(xd, wd, bd).masked_fill(mask[..., None], 0.0)
+    yd.backward(gy.double())
+    assert _rel(y, yd) < 1e-5
+    assert _rel(xg.grad, xd.grad) < 1e-5 and _rel(wg.grad, wd.grad) < 1e-5 and _rel(bg.grad, bd.grad) < 1e-5
+    assert bool((xg.grad[mask] == 0).all())
+    # an unaligned mask pointer is fine (bytes), the flag cannot be combined with a residual
+    from pctrans_b200 import _cabi
+    x2 = x.view(-1, 256)
+    m8 = torch.zeros(x2.shape[0] + 1, dtype=torch.uint8, device="cuda")[1:]
+    m8[5] = 1
+    y2 = _cabi.linear_forward(x2, _cabi.linear_pack_weight(w), 256, b, row_mask=m8)
+    assert bool((y2[5] == 0).all()) and bool((y2[6] != 0).any())
+    with pytest.raises(ValueError):
+        _cabi.linear_forward(x2, _cabi.linear_pack_weight(w), 256, b, residual=y2, row_mask=m8)
