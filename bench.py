@@ -148,6 +148,30 @@ def ncu_traffic(pyr_name: str, batch: int, dtype: str, which: str):
     return None
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPUs local to GPU `index` BEFORE any pinned host buffer is allocated,
+    so that the end-to-end arm's host buffers sit in the memory of the socket the GPU hangs off
+    (first touch).  With one process per GPU on a multi-socket box every rank otherwise shares
+    whichever node the allocator picks, and the ranks' H2D / D2H copies cross the socket link:
+    the round-1 e2e number grew only 1.8x from 1 to 8 GPUs.  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        node = None
+        try:
+            node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        return {"cpus_before": before, "cpus_after": len(after), "first_cpu": after[0] if after else None,
+                "numa_node": node}
+    except Exception as e:   # no NVML / not permitted in this container: run unpinned
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the benchmark runs."""
 
@@ -572,6 +596,8 @@ def main():
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)   # restored before the CPU baseline runs (it gets every core)
+    affinity = bind_to_gpu_numa(local_rank) if os.environ.get("PCT_BENCH_NO_AFFINITY") != "1" else None
     dist = None
     if world > 1:
         # NCCL prints "NCCL version ..." (and any NCCL_DEBUG output) to stdout while the
@@ -734,6 +760,10 @@ def main():
         if world == 1:
             subs.update(sub_records(dev, peak, args))
 
+    try:
+        os.sched_setaffinity(0, all_cpus)
+    except OSError:
+        pass
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -752,6 +782,7 @@ def main():
             "step_algorithmic_gbs": step_gbs, "step_frac_of_peak": step_gbs / peak,
             "onchip_bounds": onchip_bounds(pyr_name, N, args.dtype) if args.regime == "R" else None,
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "host_affinity": affinity,
             "sub_records": subs,
         }
         print(json.dumps(line), flush=True)
