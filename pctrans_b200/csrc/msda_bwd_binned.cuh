@@ -57,6 +57,10 @@ constexpr int kBinMaxSamples = 64;    // L*P
 constexpr int kBinMaxQc = 1024;       // queries per chunk: 10 bits of the record word
 constexpr int kBinMaxCells = 65535;   // 16 bits of the record word
 constexpr unsigned kBinNoPos = 0xffffu;
+#ifndef PCT_BIN_DYN_TAIL
+#define PCT_BIN_DYN_TAIL 4
+#endif
+constexpr int kBinDynTail = PCT_BIN_DYN_TAIL;   // rounds per warp handed out dynamically at the end of a sweep
 
 struct __align__(16) BinLevel {   // read as two 16-byte words
   int cell_base;                // cells of level l: cell_base + (y0+1)*(W+1) + (x0+1), y0 in [-1,H-1]
@@ -291,6 +295,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   __shared__ int s_nc, s_task;
   __shared__ unsigned int s_total;                   // (non-empty cells << 16) | records
   __shared__ unsigned int s_hist[64];                // non-empty cells per record count (descending)
+  __shared__ unsigned int s_round;                   // next round of the dynamic tail of the sweep
   __shared__ __align__(16) unsigned int s_zero[16];   // zeros the compiler cannot see through
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -397,6 +402,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     // ---- P0: clear the cell counters, start staging the chunk's grad_out rows ----
     for (int i = tid; i < cnt_words; i += kBinThreads) cnt[i] = 0u;
     if (tid < 64) s_hist[tid] = 0u;
+    if (tid == 64) s_round = 0u;
     // reference points of the chunk's first query (fused): (L, ref_dim) floats per query
     const float* const ref0 = FUSED ? fr.ref + ((long long)b * Lq + q0) * L * fr.ref_dim : nullptr;
     if (FUSED) {
@@ -584,10 +590,19 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
       // rounds go to the warps in snake order (w, 63-w, 64+w, 127-w, ...): the fullest cells come
       // first, and a plain interleave gave warp 0 the longest round of every 32 (11 % of the
       // kernel's stall samples sat at the barrier behind the sweep)
+      // The last kBinDynTail * NWARPS rounds (cells with one or two records) are handed out through
+      // a shared counter instead: warps that fell behind take fewer of them.
+      const int n_static = max(0, (nrounds / NWARPS - kBinDynTail) * NWARPS);
       for (int j = 0;; ++j) {
-        const int rd = j * NWARPS + ((j & 1) ? NWARPS - 1 - warp : warp);
-        if (j * NWARPS >= nrounds) break;
-        if (rd >= nrounds) continue;
+        int rd;
+        if (j * NWARPS < n_static) {
+          rd = j * NWARPS + ((j & 1) ? NWARPS - 1 - warp : warp);
+        } else {
+          rd = 0;
+          if (lane == 0) rd = n_static + (int)atomicAdd(&s_round, 1u);
+          rd = __shfl_sync(0xffffffffu, rd, 0);
+          if (rd >= nrounds) break;
+        }
         const int ci = rd * GPW + (lane / LPP);
         unsigned rp = 0u, rend = 0u;                 // shared addresses of this group's records
         if (ci < ncell) {
