@@ -118,8 +118,9 @@ int pct_msda_kernel_family(int channels, int num_levels, int num_point, int valu
  * device (buffers assumed 16-byte aligned): 0 = generic scalar, 1 = per-tap vector scatter,
  * 2 = cell-binned (grad_value aggregated per bilinear cell on chip before any global reduction;
  * available when the head dim is 16/32/64/128 channels, L <= 8, L*P <= 64 and the level maps are
- * small enough for shared memory -- fewer than 32 768 pixels per image; the default wherever it
- * fits, PCT_MSDA_FLAG_BWD_PER_TAP overrides).  Negative = error code negated. */
+ * small enough for shared memory -- 12 bytes per pixel of one image beside a 64-query chunk, about
+ * 18 000 pixels on B200; the default wherever it fits, PCT_MSDA_FLAG_BWD_PER_TAP overrides).
+ * Negative = error code negated. */
 int pct_msda_backward_plan(int batch, int spatial_size, int num_heads, int channels,
                            int num_levels, int num_query, int num_point, int value_dtype,
                            unsigned flags);

@@ -184,3 +184,18 @@ def test_fused_binned_matches_fused_per_tap(ref_dim, D, dtype):
                                      ("grad_logits", bl, pl, r_glog)):
         assert rel(got, want) <= tol, (name, rel(got, want))
         assert rel(got, per_tap.float().cpu().numpy()) <= 2 * tol, name
+
+
+def test_binned_largest_map_that_fits():
+    """Maximum sizes: one 130 x 140 level.  The level shapes live in device memory, so the host sizes
+    shared memory from the bound 2S + 2L cells (6 bytes each): S = 18 200 is about the largest map
+    that leaves room for a 64-query chunk (the kernel then finds 18 471 real cells and takes ~800
+    queries per chunk); beyond that, and beyond 2^31 elements per tensor, the per-tap kernel runs."""
+    shapes = ((130, 140),)
+    S = 130 * 140
+    errs = run_case(1, shapes, 1, 16, 4, "U", 21, Lq=1700)
+    assert errs["gv"] <= 1e-4
+    assert _cabi.backward_plan(1, S, 1, 16, 1, 100, 4, torch.float32, 0) == 2
+    assert _cabi.backward_plan(1, 19000, 1, 16, 1, 100, 4, torch.float32, 0) == 1     # counters do not fit
+    assert _cabi.backward_plan(1, 32768, 1, 16, 1, 100, 4, torch.float32, 0) == 1
+    assert _cabi.backward_plan(30000, S, 1, 16, 1, 100, 4, torch.float32, 0) == 1     # N S M D >= 2^31: 64-bit offsets
