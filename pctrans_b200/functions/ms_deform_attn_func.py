@@ -29,6 +29,11 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
+# Tuning hook for A/B measurements (scripts/): option bits of include/pct_msda.h added to every
+# backward call, e.g. PCT_MSDA_BWD_FLAGS=0x20 forces the per-tap gradient kernel.  Default 0.
+import os as _os
+_TUNE_BWD_FLAGS = int(_os.environ.get("PCT_MSDA_BWD_FLAGS", "0"), 0)
+
 from .. import _cabi
 
 
@@ -100,7 +105,7 @@ class MSDeformAttnFunction(Function):
                                    f"for value dtype {value.dtype} / head dim {D}")
         try:
             grad_value, grad_loc, grad_attn = _cabi.backward(value, shapes, lsi, loc, attn,
-                                                             grad_output, flags=flags)
+                                                             grad_output, flags=flags or _TUNE_BWD_FLAGS)
         except _cabi.MSDAError as e:
             if not (flags and e.code == _cabi.E_UNSUPPORTED):
                 raise
@@ -163,7 +168,8 @@ class MSDeformAttnFusedFunction(Function):
         grad_output = grad_output.contiguous()
         if grad_output.dtype != value.dtype:
             grad_output = grad_output.to(value.dtype)
-        gv, goff, glog = _cabi.fused_backward(value, shapes, lsi, ref, offsets, logits, grad_output)
+        gv, goff, glog = _cabi.fused_backward(value, shapes, lsi, ref, offsets, logits, grad_output,
+                                              flags=_TUNE_BWD_FLAGS)
         return gv, None, None, None, goff, glog
 
 
