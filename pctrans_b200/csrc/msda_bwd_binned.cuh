@@ -111,26 +111,6 @@ __device__ __forceinline__ float bin_reduce3(float a, float x, float y, int sub)
   return k;
 }
 
-template <typename T>
-struct BinRow;   // one lane's 4 channels of a staged grad_out row
-template <>
-struct BinRow<float> {
-  static __device__ __forceinline__ void load(const unsigned char* p, float (&g)[4]) {
-    const float4 r = *reinterpret_cast<const float4*>(p);
-    g[0] = r.x; g[1] = r.y; g[2] = r.z; g[3] = r.w;
-  }
-};
-template <>
-struct BinRow<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const unsigned char* p, float (&g)[4]) {
-    const uint2 r = *reinterpret_cast<const uint2*>(p);
-    g[0] = __uint_as_float(r.x << 16);
-    g[1] = __uint_as_float(r.x & 0xffff0000u);
-    g[2] = __uint_as_float(r.y << 16);
-    g[3] = __uint_as_float(r.y & 0xffff0000u);
-  }
-};
-
 // ---- packed fp32 pairs (fma.rn.f32x2 = FFMA2 on sm_100a) and raw shared-window accesses ----
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pack2(float lo, float hi) {
@@ -281,11 +261,9 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
                        BinLaunch bl, FusedRef fr) {
   constexpr int VE = 4;
   constexpr int VB = VE * (int)sizeof(T);
-  using CV = ChanVec<T, VB>;
   constexpr int D = LPP * VE;
   constexpr int ROWB = D * (int)sizeof(T);     // bytes of one (query, head) grad_out row
   constexpr int PPR = ROWB / 16;               // 16-byte pieces per row
-  constexpr int G = kBinThreads / LPP;         // lane groups per CTA
   static_assert(LPP >= 4 && LPP <= 32 && ROWB % 16 == 0, "binned backward: 4..32 lanes of 4 channels");
 
   extern __shared__ __align__(16) unsigned char smem[];
@@ -346,7 +324,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   float* const sm_inv = sm_max + QC;
   float* const sm_dot = sm_inv + QC;
 
-  const int grp = tid / LPP, sub = tid % LPP;
+  const int sub = tid % LPP;
   unsigned int* const ctr = g_sched + 2 * bl.slot;
 
   // one sample of the binning passes: cell index (or -1 when the reference skips it), fractions

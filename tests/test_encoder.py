@@ -228,6 +228,10 @@ def test_linear_helpers_on_cpu_are_plain_torch():
                        torch.relu(lin(x) + res))
     assert torch.equal(linear_tc.linear_residual_layernorm(x, lin.weight, lin.bias, res, norm),
                        norm(res + lin(x)))
+    mask = torch.zeros(5, 7, dtype=torch.bool)
+    mask[2, 3:] = True
+    assert torch.equal(linear_tc.linear(x, lin.weight, lin.bias, row_mask=mask),
+                       lin(x).masked_fill(mask[..., None], 0.0))          # mod.py:100-101
 
 
 @pytest.mark.gpu
