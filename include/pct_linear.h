@@ -78,6 +78,20 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
 int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
                      int in_features, int out_features, void* cuda_stream);
 
+/* Backward of the LayerNorm fused into pct_linear_forward_train (PD/msdeformattn.py:107-126: the two
+ * `norm(residual + linear(x))` blocks of an encoder layer), one pass over the rows:
+ *   x_hat = (pre_norm - mean) * rstd,   g = grad_y * gamma
+ *   grad_pre   = rstd * (g - mean_n(g) - x_hat * mean_n(g * x_hat))         (rows, features)
+ *   grad_gamma = sum_rows grad_y * x_hat,   grad_beta = sum_rows grad_y     (features,)
+ * features in {128, 256, 384, 512}; grad_y / pre_norm / grad_pre / gamma 16-byte aligned.  grad_gamma
+ * and grad_beta are fully overwritten (cleared by the callee on `cuda_stream`, combined with fp32
+ * reductions: like pct_linear_wgrad not bit-reproducible run to run).  grad_pre is also the gradient
+ * of the residual input and the operand of the Linear's dgrad / wgrad. */
+int pct_linear_layernorm_backward(const float* grad_y, const float* pre_norm, const float* mean,
+                           const float* rstd, const float* gamma, float* grad_pre,
+                           float* grad_gamma, float* grad_beta, int rows, int features,
+                           void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,7 @@ EXPORTS = (
     "pct_msda_host_forward_backward",
 )
 LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_forward",
-                  "pct_linear_forward_train", "pct_linear_wgrad")
+                  "pct_linear_forward_train", "pct_linear_wgrad", "pct_linear_layernorm_backward")
 LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM, LINEAR_GATE, LINEAR_ROWMASK = 0x1, 0x2, 0x4, 0x8, 0x10
 E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
@@ -104,6 +104,8 @@ def load():
         lib.pct_linear_pack_weight.argtypes = [vp, vp, i32, i32, vp]
         lib.pct_linear_wgrad.restype = i32
         lib.pct_linear_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+        lib.pct_linear_layernorm_backward.restype = i32
+        lib.pct_linear_layernorm_backward.argtypes = [vp] * 8 + [i32, i32, vp]
         lib.pct_linear_forward_train.restype = i32
         lib.pct_linear_forward_train.argtypes = [vp] * 6 + [ctypes.c_float] + [vp] * 4 + [i32] * 3 + [u32, vp]
         lib.pct_linear_forward.restype = i32
@@ -289,6 +291,25 @@ def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weigh
             ptr(ln_bias), float(ln_eps), y.data_ptr(), ptr(pre), ptr(mean), ptr(rstd), rows, k, n,
             flags, _stream_ptr(x.device)), "pct_linear_forward")
     return (y, pre, mean, rstd) if save_for_backward else y
+
+
+def layernorm_backward_supported(features: int) -> bool:
+    return features % 128 == 0 and 128 <= features <= 512
+
+
+def layernorm_backward(grad_y, pre_norm, mean, rstd, gamma):
+    """One-pass LayerNorm backward: returns (grad_pre (rows, n), grad_gamma (n,), grad_beta (n,))
+    for y = (pre_norm - mean) * rstd * gamma + beta over the last dim; fp32 contiguous tensors."""
+    rows, n = grad_y.shape
+    g = torch.empty_like(grad_y)
+    gg = torch.empty((n,), dtype=grad_y.dtype, device=grad_y.device)
+    gb = torch.empty((n,), dtype=grad_y.dtype, device=grad_y.device)
+    with torch.cuda.device_of(grad_y):
+        check(load().pct_linear_layernorm_backward(
+            grad_y.data_ptr(), pre_norm.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+            gamma.data_ptr(), g.data_ptr(), gg.data_ptr(), gb.data_ptr(), rows, n,
+            _stream_ptr(grad_y.device)), "pct_linear_layernorm_backward")
+    return g, gg, gb
 
 
 def linear_wgrad(grad_y, x, with_bias: bool = False):

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libpctrans_msda.so")
 SOURCES = ["msda_capi.cu", "msda_inst_fwd.cu", "msda_inst_bwd.cu", "msda_inst_binned.cu",
-           "msda_host.cu", "linear_tc.cu"]
+           "msda_host.cu", "linear_tc.cu", "layernorm_bwd.cu"]
 HEADERS = ["msda_kernels.cuh", "msda_bwd_binned.cuh", "msda_launch.h",
            os.path.join("..", "..", "include", "pct_msda.h"),
            os.path.join("..", "..", "include", "pct_linear.h")]
@@ -28,6 +28,7 @@ NOT_INCLUDED = {
     "msda_inst_binned.cu": ["pct_linear.h"],
     "msda_host.cu": ["msda_kernels.cuh", "msda_bwd_binned.cuh", "msda_launch.h", "pct_linear.h"],
     "linear_tc.cu": ["msda_kernels.cuh", "msda_bwd_binned.cuh", "msda_launch.h"],
+    "layernorm_bwd.cu": ["msda_kernels.cuh", "msda_bwd_binned.cuh", "msda_launch.h"],
 }
 # every translation unit is compiled on its own (in parallel, objects cached by source hash) and
 # linked into one shared library

@@ -114,8 +114,8 @@ class TensorCoreLinearFunction(Function):
 
 class LinearResidualLayerNormFunction(Function):
     """y = LayerNorm(x @ W^T + b + residual) in one kernel, with autograd: the kernel also writes
-    LayerNorm's input and row statistics, the backward is aten's LayerNorm backward followed by the
-    tensor-core input / weight gradients."""
+    LayerNorm's input and row statistics, the backward is the one-pass LayerNorm backward of
+    csrc/layernorm_bwd.cu followed by the tensor-core input / weight gradients."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, ln_weight, ln_bias, eps):
@@ -137,8 +137,7 @@ class LinearResidualLayerNormFunction(Function):
         x2, weight, pre, mean, rstd, ln_weight, ln_bias = ctx.saved_tensors
         n, k = weight.shape
         gy = grad_y.reshape(-1, n).contiguous()
-        g, g_lnw, g_lnb = torch.ops.aten.native_layer_norm_backward(
-            gy, pre, [n], mean, rstd, ln_weight, ln_bias, [True, True, True])
+        g, g_lnw, g_lnb = _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = _cabi.linear_forward(g, packed_weight(weight, transposed=True), k).view(ctx.x_shape)
@@ -149,6 +148,17 @@ class LinearResidualLayerNormFunction(Function):
             gb = g.sum(0)
         gres = g.view(*ctx.x_shape[:-1], n) if ctx.needs_input_grad[3] else None
         return gx, gw, gb, gres, g_lnw, g_lnb, None
+
+
+def _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias):
+    """(d pre_norm, d gamma, d beta): the one-pass kernel of csrc/layernorm_bwd.cu -- or aten's under
+    ``torch.use_deterministic_algorithms(True)`` (its column sums are fp32 reductions in arbitrary
+    order) and for widths it does not cover."""
+    n = gy.shape[1]
+    if _cabi.layernorm_backward_supported(n) and not torch.are_deterministic_algorithms_enabled():
+        return _cabi.layernorm_backward(gy, pre, mean, rstd, ln_weight.detach().contiguous())
+    return torch.ops.aten.native_layer_norm_backward(gy, pre, [n], mean, rstd, ln_weight, ln_bias,
+                                                     [True, True, True])
 
 
 def _wgrad(g, x2, want_bias):
@@ -164,7 +174,7 @@ def _wgrad(g, x2, want_bias):
 class FFNFunction(Function):
     """y = LayerNorm(src + linear2(relu(linear1(src)))) -- the encoder layer's FFN block
     (PD/msdeformattn.py:107-120) as three kernels forward (GEMM+ReLU, GEMM+residual+LayerNorm) and
-    five backward: aten's LayerNorm backward, two weight-gradient GEMMs (bias gradients included)
+    five backward: the one-pass LayerNorm backward, two weight-gradient GEMMs (bias gradients included)
     and two input-gradient GEMMs whose epilogues carry the ReLU mask and the residual branch."""
 
     @staticmethod
@@ -185,8 +195,7 @@ class FFNFunction(Function):
         x2, w1, w2, h, pre, mean, rstd, ln_weight, ln_bias = ctx.saved_tensors
         c, f = w1.shape[1], w1.shape[0]
         gy = grad_y.reshape(-1, c).contiguous()
-        g, g_lnw, g_lnb = torch.ops.aten.native_layer_norm_backward(
-            gy, pre, [c], mean, rstd, ln_weight, ln_bias, [True, True, True])
+        g, g_lnw, g_lnb = _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias)
         gw2, gb2 = _wgrad(g, h, True)
         # d(hidden) = (g @ W2) masked by the ReLU, straight out of the GEMM's epilogue
         gh = _cabi.linear_forward(g, packed_weight(w2, transposed=True), f, gate=h)

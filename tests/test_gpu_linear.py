@@ -388,3 +388,23 @@ def test_row_mask_epilogue_is_masked_fill_with_gradients():
     assert bool((y2[5] == 0).all()) and bool((y2[6] != 0).any())
     with pytest.raises(ValueError):
         _cabi.linear_forward(x2, _cabi.linear_pack_weight(w), 256, b, residual=y2, row_mask=m8)
+
+
+@pytest.mark.parametrize("rows,n", [(1000, 256), (86016, 256), (517, 128), (33, 512), (1, 384)])
+def test_layernorm_backward_matches_fp64(rows, n):
+    """pct_linear_layernorm_backward (one pass: grad of the pre-norm row + column sums for gamma / beta)
+    against torch's LayerNorm differentiated in fp64."""
+    from pctrans_b200 import _cabi
+    g = torch.Generator().manual_seed(rows + n)
+    x = (torch.randn(rows, n, generator=g) * 2 + 0.5).cuda()
+    gamma = (torch.randn(n, generator=g) * 0.5 + 1).cuda()
+    beta = torch.randn(n, generator=g).cuda()
+    gy = torch.randn(rows, n, generator=g).cuda()
+    xd = x.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    F.layer_norm(xd, (n,), gd, bd, 1e-5).backward(gy.double())
+    mean = x.double().mean(1, keepdim=True)
+    rstd = (x.double().var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    gp, gg, gb = _cabi.layernorm_backward(gy, x, mean.float().contiguous(), rstd.float().contiguous(), gamma)
+    assert _rel(gp, xd.grad) < 2e-5 and _rel(gg, gd.grad) < 2e-5 and _rel(gb, bd.grad) < 2e-5
+    assert not _cabi.layernorm_backward_supported(64) and not _cabi.layernorm_backward_supported(1024)
