@@ -77,6 +77,9 @@ extern "C" {
 
 /* flags for the *_ex entry points (0 = library default; used by the tuning harness) */
 #define PCT_MSDA_FLAG_FORCE_GENERIC 0x1u /* use the any-D scalar kernels even when a vector path fits */
+#define PCT_MSDA_FLAG_FWD_STAGED 0x4u    /* forward, fp32 values, 32-channel heads, power-of-two head count: stage the
+                                            smallest levels of a head in shared memory (an experiment kept for
+                                            measurements; same results) */
 #define PCT_MSDA_FLAG_BF16_ACCUM 0x8u    /* backward, bf16 values: accumulate grad_value directly in bf16
                                             (packed bf16x2 reductions, no workspace; every tap rounds) */
 #define PCT_MSDA_FLAG_BF16_F16_ACCUM 0x80u /* backward, bf16 values: accumulate grad_value in a scaled fp16

@@ -1,4 +1,6 @@
 // msda_inst_fwd.cu -- instantiations and launchers of the forward kernels (msda_kernels.cuh).
+#include <type_traits>
+
 #include "../../include/pct_msda.h"
 #include "msda_launch.h"
 
@@ -11,6 +13,35 @@ int launch_fwd_vec(const void* value, const int64_t* shapes, const int64_t* lsi,
   constexpr int PPW = 32 / LPP;
   const long long n_tasks = (long long)d.N * d.M * ((d.Lq + PPW - 1) / PPW);
   const LaunchShape ls = vec_launch_shape(n_tasks, sm_count, flags, pct::kVecThreads);
+  if constexpr (std::is_same<T, float>::value && LPP == 8 && VB == 16 && !FUSED) {
+    // experiment (PCT_MSDA_FLAG_FWD_STAGED): the smallest levels of a head staged in shared memory
+    if ((flags & PCT_MSDA_FLAG_FWD_STAGED) && d.M > 0 && (d.M & (d.M - 1)) == 0) {
+      auto kern = pct::msda_fwd_vec_kernel<float, 8, 16, false, true>;
+      static int dyn_bytes[64] = {};
+      int dev = 0;
+      cudaError_t e = cudaGetDevice(&dev);
+      if (e != cudaSuccess) return (int)e;
+      if (dev < 0 || dev >= 64) return PCT_MSDA_E_UNSUPPORTED;
+      if (dyn_bytes[dev] == 0) {
+        int optin = 0;
+        cudaFuncAttributes fa;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return (int)e;
+        const int dyn = (optin - (int)fa.sharedSizeBytes) & ~127;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+        if (e != cudaSuccess) return (int)e;
+        dyn_bytes[dev] = dyn;
+      }
+      const int dyn = dyn_bytes[dev];
+      kern<<<ls.grid, ls.block, dyn, st>>>(
+          (const float*)value, shapes, lsi, (const float*)loc, (const float*)attn, (float*)out, d.N,
+          d.S, d.M, d.L, d.Lq, d.P, fr, make_sched(n_tasks, ls.grid, ls.block / 32, flags),
+          dyn / (32 * (int)sizeof(float)));
+      count_launches(1);
+      return (int)cudaGetLastError();
+    }
+  }
   pct::msda_fwd_vec_kernel<T, LPP, VB, FUSED><<<ls.grid, ls.block, 0, st>>>(
       (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (T*)out, d.N, d.S, d.M,
       d.L, d.Lq, d.P, fr, make_sched(n_tasks, ls.grid, ls.block / 32, flags));

@@ -394,16 +394,29 @@ __device__ __forceinline__ float2 fused_location(const float* __restrict__ rp, i
                      r.y + __fdiv_rn(off.y, (float)P) * r.w * 0.5f);
 }
 
+// four fp32 channels of a staged value row (STAGED forward, fp32 values with 16-byte lanes only)
+__device__ __forceinline__ void load_shared_f4(unsigned addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+               : "r"(addr));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward, vector path.  T = float | bf16; LPP lanes per (query, head) pair, each owning VB
 // bytes of the head's channels: D = LPP * VB/sizeof(T); a warp covers 32/LPP pairs.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int LPP, int VB, bool FUSED>
+// STAGED (experiment of round 2, PCT_MSDA_FLAG_FWD_STAGED; BASELINE.json's north_star: "per-level value
+// tiles staged in shared memory"): before a CTA walks the queries of one (image, head) stream it
+// copies the value rows of that head for the smallest levels -- as many whole levels as fit the
+// dynamic shared memory, a contiguous pixel range -- into shared memory (cp.async) and takes the
+// taps of those levels with LDS.128 instead of LDG.128.  The static slice of a CTA is walked in
+// per-stream segments (CTA-wide barriers around the copy); the dynamic tail reads global memory.
+template <typename T, int LPP, int VB, bool FUSED, bool STAGED = false>
 __global__ void __launch_bounds__(kVecThreads, 1)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, T* __restrict__ out, int N, int S, int M,
-                    int L, int Lq, int P, FusedRef fr, SchedArgs sched) {
+                    int L, int Lq, int P, FusedRef fr, SchedArgs sched, int stage_cap_pix = 0) {
   using CV = ChanVec<T, VB>;
   constexpr int VE = CV::kElems;
   constexpr int D = LPP * VE;
@@ -419,6 +432,26 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   __shared__ int s_tapo[kSmemTaps ? kVecThreads / 32 : 1][kSlots];
 #endif
   fill_level_table(s_tab, shapes, lsi, L, P);
+  extern __shared__ __align__(16) unsigned char s_tile[];   // STAGED: value rows of one head
+  __shared__ int s_stage[3];                                 // first pixel, pixels, level mask
+  if (STAGED && threadIdx.x == 0) {
+    // whole levels from the front or from the back of the pixel order, whichever covers more levels
+    int npre = 0, lpre = 0, nsuf = 0, lsuf = 0;
+    for (int l = 0; l < L; ++l) {
+      const int n = (int)(shapes[2 * l] * shapes[2 * l + 1]);
+      if (npre + n > stage_cap_pix) break;
+      npre += n; ++lpre;
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const int n = (int)(shapes[2 * l] * shapes[2 * l + 1]);
+      if (nsuf + n > stage_cap_pix) break;
+      nsuf += n; ++lsuf;
+    }
+    const bool pre = lpre > lsuf || (lpre == lsuf && npre >= nsuf);
+    s_stage[0] = pre ? 0 : S - nsuf;
+    s_stage[1] = pre ? npre : nsuf;
+    s_stage[2] = pre ? ((1 << lpre) - 1) : (((1 << lsuf) - 1) << (L - lsuf));
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -429,17 +462,26 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   // the launcher guarantees n_tasks < 2^31, so the per-task index math stays 32-bit
   const int n_tasks = N * M * tasks_per_stream;
   TaskIter iter(sched, n_tasks, warp, nwarps, lane);
+  // STAGED state: the stream whose rows sit in s_tile, the shift that turns an element offset
+  // (multiple of M*D; the launcher guarantees M is a power of two) into pixel*D, this lane's base
+  const int stage_pix0 = STAGED ? s_stage[0] : 0, stage_npix = STAGED ? s_stage[1] : 0;
+  const unsigned stage_lmask = STAGED ? (unsigned)s_stage[2] : 0u;
+  const int sh_m = STAGED ? __ffs(M) - 1 : 0;
+  const unsigned tile_lane = (unsigned)__cvta_generic_to_shared(s_tile) + (unsigned)(sub * VB) -
+                             (unsigned)(stage_pix0 * D * (int)sizeof(T));
+  int staged_stream = -1;
 #if PCT_FWD_SMEM_TAPS
   float4* const my_w = &s_tapw[kSmemTaps ? warp : 0][kSmemTaps ? grp * (LPP + 1) : 0];
   int* const my_o = &s_tapo[kSmemTaps ? warp : 0][kSmemTaps ? grp * (LPP + 1) : 0];
 #endif
 
-  for (int t = iter.next(); t >= 0; t = iter.next()) {
+  auto process = [&](const int t) {
     const int stream = t / tasks_per_stream;
     const int tq = t - stream * tasks_per_stream;
     const int b = stream / M, m = stream - b * M;
     const int q = tq * PPW + grp;
     const bool qvalid = q < Lq;
+    const bool in_tile = STAGED && stream == staged_stream;     // warp-uniform
     const long long pair = ((long long)b * Lq + (qvalid ? q : Lq - 1)) * M + m;
     const float2* lp = reinterpret_cast<const float2*>(loc) + pair * LP;
     const float* ap = attn + pair * LP;
@@ -524,7 +566,7 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         __syncwarp();
       }
 #endif
-      auto tap = [&](const int j, const int pitch) {
+      auto tap = [&](const int j, const int pitch, const bool from_tile = false) {
 #if PCT_FWD_SMEM_TAPS && PCT_PACK_TAPS
         int wd;
         float b00, b01, b10, b11;
@@ -562,10 +604,26 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         // 32-bit corner offsets first: each address is then ONE wide multiply-add off the base
         const int o01 = o + ox, o10 = o + oy, o11 = o10 + ox;
         float v00[VE], v01[VE], v10[VE], v11[VE];
-        CV::load(vimg + o, v00);
-        CV::load(vimg + o01, v01);
-        CV::load(vimg + o10, v10);
-        CV::load(vimg + o11, v11);
+        bool done = false;
+        if constexpr (STAGED) {
+          if (from_tile) {
+            // the same four rows out of the staged tile: element offset / M = pixel * D
+            const unsigned a00 = tile_lane + ((unsigned)o >> sh_m) * (unsigned)sizeof(T);
+            const unsigned sx = ((unsigned)ox >> sh_m) * (unsigned)sizeof(T);
+            const unsigned sy = ((unsigned)oy >> sh_m) * (unsigned)sizeof(T);
+            load_shared_f4(a00, v00);
+            load_shared_f4(a00 + sx, v01);
+            load_shared_f4(a00 + sy, v10);
+            load_shared_f4(a00 + sy + sx, v11);
+            done = true;
+          }
+        }
+        if (!done) {
+          CV::load(vimg + o, v00);
+          CV::load(vimg + o01, v01);
+          CV::load(vimg + o10, v10);
+          CV::load(vimg + o11, v11);
+        }
 #pragma unroll
         for (int i = 0; i < VE; ++i)
           acc[i] = fmaf(b00, v00[i], fmaf(b01, v01[i], fmaf(b10, v10[i], fmaf(b11, v11[i], acc[i]))));
@@ -579,8 +637,13 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         if (s0 + j0 + kBlk <= LP) {
           if (P % kBlk == 0) {   // the block lies inside one level (s0 + j0 is a multiple of kBlk)
             const int pitch = PCT_PACK_TAPS ? s_tab[s0 + j0].y * MD : 0;
+            if (STAGED && in_tile && ((stage_lmask >> s_tab[s0 + j0].w) & 1u)) {
 #pragma unroll
-            for (int j = 0; j < kBlk; ++j) tap(j0 + j, pitch);
+              for (int j = 0; j < kBlk; ++j) tap(j0 + j, pitch, true);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kBlk; ++j) tap(j0 + j, pitch);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < kBlk; ++j) tap(j0 + j, PCT_PACK_TAPS ? s_tab[s0 + j0 + j].y * MD : 0);
@@ -598,7 +661,37 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       for (int i = 0; i < VE; ++i) acc[i] *= inv;
     }
     if (qvalid) CV::store_stream(out + pair * D + sub * VE, acc);
+  };
+  if (STAGED) {
+    // the static slice in per-stream segments, the head's small levels staged before each
+    const int seg_last = min(n_tasks, blockIdx.x * sched.static_per_cta + sched.static_per_cta);
+    for (int seg = blockIdx.x * sched.static_per_cta; seg < seg_last;) {
+      const int stream = seg / tasks_per_stream;
+      const int seg_end = min(seg_last, (stream + 1) * tasks_per_stream);
+      __syncthreads();                                      // the previous tile is no longer read
+      {
+        const int b = stream / M, m = stream - b * M;
+        constexpr int PPR = D * (int)sizeof(T) / 16;        // 16-byte pieces per row
+        const T* src = value + (((long long)b * S + stage_pix0) * M + m) * D;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s_tile);
+        for (int i = threadIdx.x; i < stage_npix * PPR; i += blockDim.x) {
+          const int pix = i / PPR, part = i - pix * PPR;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)i * 16u),
+                       "l"(src + (long long)pix * MD + part * (16 / (int)sizeof(T)))
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      staged_stream = stream;
+      for (int t = seg + warp; t < seg_end; t += nwarps) process(t);
+      seg = seg_end;
+    }
+    staged_stream = -1;
+    iter.t_static_end = -1;                                 // only the dynamic tail is left
   }
+  for (int t = iter.next(); t >= 0; t = iter.next()) process(t);
   __syncthreads();
   iter.finish();
 }

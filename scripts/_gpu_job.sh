@@ -1,9 +1,4 @@
-timeout 900 python bench.py > gpurun_out/bench_r02_f32.json 2> gpurun_out/bench_r02_f32.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_r02_f32.json'))
-print(round(d['value']/1e6,2), round(d['ms_per_step'],4), d['roofline']['frac'], d['forward']['ms'], d['backward']['ms'], d['e2e']['value'], d['cpu_baseline']['value'], d['gpu_launches'])
-for k in ('cfg4_bbbc_encoder6_train_b32','cfg2_decoder_infer_b8','cfg5_encoder6_train'):
-    v=d['sub_records'][k]; print(k, round(v['ms_per_step'],2), round(v['images_per_s'],1))
-PY
-timeout 300 python scripts/bench_encoder.py --mode infer --batch 8 2>&1 | tail -1 | cut -c1-300
+timeout 600 ncu --set full --clock-control none -k regex:"msda_fwd" -c 4 -o gpurun_out/r02_fwd_staged python scripts/tune.py --only fwd --flags 0,0x4 --dtypes f32 --regimes R --iters 1 --warm 1 > gpurun_out/r02_fwd_staged_ncu.log 2>&1
+( timeout 300 python scripts/tune.py --only fwd --flags 0,0x4 --dtypes f32 --regimes R,U
+  timeout 300 python scripts/tune.py --only fwd --flags 0,0x4 --dtypes f32 --regimes R --pyramid BBBC_520x696 --batch 32
+  timeout 300 python scripts/tune.py --only fwd --flags 0,0x4 --dtypes f32 --regimes R --batch 4 ) > gpurun_out/r02_fwd_staged_tiles.log 2>&1

@@ -523,3 +523,16 @@ def test_deterministic_backward_is_bit_reproducible(dtype, D):
                                        torch.rand(1, 4, 2, 1, 2, device=DEV, dtype=torch.float64), 128).sum().backward()
     finally:
         torch.use_deterministic_algorithms(False)
+
+
+@pytest.mark.parametrize("shapes,N", [(synth.CVPPP_512, 3), (synth.BBBC_520x696, 2), (((5, 7), (3, 2)), 5)])
+def test_staged_forward_is_bit_identical(shapes, N):
+    """PCT_MSDA_FLAG_FWD_STAGED (the smallest levels of a head staged in shared memory, an experiment
+    kept for measurements) reads the same values in the same order: identical output bits."""
+    from pctrans_b200 import _cabi
+    value, sh, lsi, loc, attn = synth.make_inputs(N, shapes, M=8, D=32, P=4, regime="R", seed=3)
+    args = (value.cuda(), sh.cuda(), lsi.cuda(), loc.cuda(), attn.cuda())
+    ref = _cabi.forward(*args)
+    out = _cabi.forward(*args, flags=0x4)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
