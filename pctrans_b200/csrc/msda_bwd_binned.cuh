@@ -57,6 +57,9 @@ constexpr int kBinMaxSamples = 64;    // L*P
 constexpr int kBinMaxQc = 1024;       // queries per chunk: 10 bits of the record word
 constexpr int kBinMaxCells = 65535;   // 16 bits of the record word
 constexpr unsigned kBinNoPos = 0xffffu;
+#ifndef PCT_BIN_UB
+#define PCT_BIN_UB 4        // samples per thread and batch of the binning passes (loads in flight)
+#endif
 #ifndef PCT_BIN_DYN_TAIL
 #define PCT_BIN_DYN_TAIL 4
 #endif
@@ -416,7 +419,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     __syncthreads();
 
     // ---- B1: count the samples of every cell (the loads of a batch first, then the atomics) ----
-    constexpr int UB = 4;
+    constexpr int UB = PCT_BIN_UB;
     const int dq = kBinThreads / LP, ds = kBinThreads - dq * LP;
     {
       int ql = tid / LP, s = tid - ql * LP;
