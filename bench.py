@@ -596,8 +596,11 @@ def main():
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    all_cpus = os.sched_getaffinity(0)   # restored before the CPU baseline runs (it gets every core)
-    affinity = bind_to_gpu_numa(local_rank) if os.environ.get("PCT_BENCH_NO_AFFINITY") != "1" else None
+    all_cpus = os.sched_getaffinity(0)
+    # one process per GPU: pin each to its GPU's socket.  Not at N=1 -- nothing competes for the host
+    # links there, and the CPU baseline that runs later in this process must see every core
+    affinity = (bind_to_gpu_numa(local_rank)
+                if world > 1 and os.environ.get("PCT_BENCH_NO_AFFINITY") != "1" else None)
     dist = None
     if world > 1:
         # NCCL prints "NCCL version ..." (and any NCCL_DEBUG output) to stdout while the
