@@ -273,7 +273,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   __shared__ BinLevel s_lvl[kBinMaxLevels];
   __shared__ unsigned char s_slvl[kBinMaxSamples];   // level of sample s
   __shared__ unsigned int s_wsum[32];
-  __shared__ int s_nc, s_task;
+  __shared__ int s_nc, s_task[2];                    // this task and the next one (fetched one ahead)
   __shared__ unsigned int s_total;                   // (non-empty cells << 16) | records
   __shared__ unsigned int s_hist[64];                // non-empty cells per record count (descending)
   __shared__ unsigned int s_round;                   // next round of the dynamic tail of the sweep
@@ -363,10 +363,13 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     hdr = (pix << 17) | (vm << 13) | ((unsigned)lvl << 10);
     return A.x + yy * A.z + xx;
   };
-  for (;;) {
-    if (tid == 0) s_task = (int)atomicAdd(ctr, 1u);
-    __syncthreads();
-    const int t = s_task;
+  // tasks come from a global counter; the next index is fetched while the final pass of this task
+  // runs (its round trip and a barrier per task used to be exposed) -- not earlier: a task reserved
+  // long before it starts cannot go to an SM that finishes sooner
+  if (tid == 0) s_task[0] = (int)atomicAdd(ctr, 1u);
+  __syncthreads();
+  for (int it = 0;; ++it) {
+    const int t = s_task[it & 1];
     if (t >= n_tasks) break;
     const int m = t % M;
     const int tc = t / M;
@@ -693,6 +696,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     __syncthreads();
 
     // ---- final: coalesced grad_sampling_loc / grad_attn_weight in sample order ----
+    if (tid == 0) s_task[(it + 1) & 1] = (int)atomicAdd(ctr, 1u);   // read after the barrier below
     if (FUSED) {
       // sum_t a_t g_t of every pair for the softmax backward (samples the reference skips have g = 0)
       for (int ql = tid; ql < nq; ql += kBinThreads) {
@@ -743,7 +747,7 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
         if (s >= LP) { s -= LP; ++ql; }
       }
     }
-    __syncthreads();   // the next task reuses the shared arrays (and s_task)
+    __syncthreads();   // the next task reuses the shared arrays
   }
 
   // last CTA out resets the counters of this ring slot
