@@ -122,11 +122,23 @@ int pct_msda_kernel_family(int channels, int num_levels, int num_point, int valu
  * 2 = cell-binned (grad_value aggregated per bilinear cell on chip before any global reduction;
  * available when the head dim is 16/32/64/128 channels, L <= 8, L*P <= 64 and the level maps are
  * small enough for shared memory -- 12 bytes per pixel of one image beside a 64-query chunk, about
- * 18 000 pixels on B200; the default wherever it fits, PCT_MSDA_FLAG_BWD_PER_TAP overrides).
+ * 18 000 pixels on B200, or 6 bytes per bilinear cell when the level shapes are passed on the host,
+ * see pct_msda_backward_plan_ex; the default wherever it fits, PCT_MSDA_FLAG_BWD_PER_TAP overrides).
  * Negative = error code negated. */
 int pct_msda_backward_plan(int batch, int spatial_size, int num_heads, int channels,
                            int num_levels, int num_query, int num_point, int value_dtype,
                            unsigned flags);
+
+/* The level shapes live in DEVICE memory, so for the cell-binned kernel the library sizes shared
+ * memory from a bound that holds for any shapes (2S + 2L cells, about twice the count of square
+ * maps).  A caller that also has spatial_shapes on the HOST can pass that copy ((L, 2) int64 rows
+ * (H_l, W_l), must describe the same S pixels, else PCT_MSDA_E_BAD_SHAPE) to the _ex2 / _plan_ex
+ * entry points below: the exact cell count then decides, which extends the binned kernel from
+ * ~18 000 to ~30 000 pixels per image (e.g. a 1024 x 1024 input at strides 8/16/32).  NULL = the
+ * plain entry points' behaviour.  The host copy is read during the call only. */
+int pct_msda_backward_plan_ex(int batch, int spatial_size, int num_heads, int channels,
+                              int num_levels, int num_query, int num_point, int value_dtype,
+                              unsigned flags, const int64_t* host_spatial_shapes);
 
 /* out[b,q,m,:] = sum_{l,p} attn[b,q,m,l,p] * bilinear(value_l[b,:,m,:], loc[b,q,m,l,p]).
  * Replaces ms_deform_attn_cuda_forward (cu:25-85).  The reference's `im2col_step` has no
@@ -172,6 +184,16 @@ int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
                          int num_query, int num_point, int value_dtype, void* workspace,
                          size_t workspace_bytes, void* cuda_stream, unsigned flags);
 
+/* The same with an optional host copy of spatial_shapes (see pct_msda_backward_plan_ex). */
+int pct_msda_backward_ex2(const void* value, const int64_t* spatial_shapes,
+                          const int64_t* level_start_index, const void* sampling_loc,
+                          const void* attn_weight, const void* grad_output, void* grad_value,
+                          void* grad_sampling_loc, void* grad_attn_weight, int batch,
+                          int spatial_size, int num_heads, int channels, int num_levels,
+                          int num_query, int num_point, int value_dtype, void* workspace,
+                          size_t workspace_bytes, void* cuda_stream, unsigned flags,
+                          const int64_t* host_spatial_shapes);
+
 /*
  * Fused prologue: the same op, fed with what the module's Linears
  * produce instead of materialised locations / weights.  Replaces, together with the kernels,
@@ -214,6 +236,17 @@ int pct_msda_fused_backward_ex(const void* value, const int64_t* spatial_shapes,
                                int channels, int num_levels, int num_query, int num_point,
                                int value_dtype, void* workspace, size_t workspace_bytes,
                                void* cuda_stream, unsigned flags);
+
+/* The same with an optional host copy of spatial_shapes (see pct_msda_backward_plan_ex). */
+int pct_msda_fused_backward_ex2(const void* value, const int64_t* spatial_shapes,
+                                const int64_t* level_start_index, const void* reference_points,
+                                int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                                const void* grad_output, void* grad_value, void* grad_offsets,
+                                void* grad_logits, int batch, int spatial_size, int num_heads,
+                                int channels, int num_levels, int num_query, int num_point,
+                                int value_dtype, void* workspace, size_t workspace_bytes,
+                                void* cuda_stream, unsigned flags,
+                                const int64_t* host_spatial_shapes);
 
 /*
  * Host pipeline: the same op for callers whose tensors live in HOST memory (the end-to-end path

@@ -8,6 +8,7 @@ reproduced).
 from __future__ import annotations
 
 import ctypes
+import weakref
 import os
 import threading
 
@@ -27,6 +28,7 @@ EXPORTS = (
     "pct_msda_backward_workspace_bytes", "pct_msda_backward_workspace_bytes_ex",
     "pct_msda_backward", "pct_msda_backward_ex",
     "pct_msda_fused_forward", "pct_msda_fused_backward", "pct_msda_fused_backward_ex",
+    "pct_msda_fused_backward_ex2", "pct_msda_backward_ex2", "pct_msda_backward_plan_ex",
     "pct_msda_host_ctx_create", "pct_msda_host_ctx_destroy", "pct_msda_host_forward",
     "pct_msda_host_forward_backward",
 )
@@ -97,6 +99,12 @@ def load():
         lib.pct_msda_fused_backward.argtypes = [vp] * 4 + [i32] + [vp] * 6 + [i32] * 8 + [vp, sz, vp]
         lib.pct_msda_fused_backward_ex.restype = i32
         lib.pct_msda_fused_backward_ex.argtypes = [vp] * 4 + [i32] + [vp] * 6 + [i32] * 8 + [vp, sz, vp, u32]
+        lib.pct_msda_fused_backward_ex2.restype = i32
+        lib.pct_msda_fused_backward_ex2.argtypes = [vp] * 4 + [i32] + [vp] * 6 + [i32] * 8 + [vp, sz, vp, u32, vp]
+        lib.pct_msda_backward_ex2.restype = i32
+        lib.pct_msda_backward_ex2.argtypes = bwd_args + [u32, vp]
+        lib.pct_msda_backward_plan_ex.restype = i32
+        lib.pct_msda_backward_plan_ex.argtypes = [i32] * 8 + [u32, vp]
         # include/pct_linear.h
         lib.pct_linear_packed_bytes.restype = sz
         lib.pct_linear_packed_bytes.argtypes = [i32, i32]
@@ -133,9 +141,44 @@ def kernel_family(channels: int, num_levels: int, num_point: int, dtype: torch.d
                                              int(backward)))
 
 
-def backward_plan(N, S, M, D, L, Lq, P, dtype: torch.dtype, flags: int = 0) -> int:
-    """0 generic, 1 per-tap vector scatter, 2 cell-binned (needs a current CUDA device)."""
-    rc = int(load().pct_msda_backward_plan(N, S, M, D, L, Lq, P, DTYPE_CODES[dtype], flags))
+# Host copies of spatial_shapes tensors, so that the backward can tell the library the exact cell
+# count of the pyramid (pct_msda_backward_ex2).  Keyed on the tensor OBJECT; a tensor is read back
+# once (one device sync per pyramid, like the reference's own length assert, mod.py:96) and never
+# while a CUDA graph is being captured.
+_HOST_SHAPES = {}
+
+
+def register_host_shapes(spatial_shapes: torch.Tensor, shapes) -> None:
+    """Tell the binding what a device ``spatial_shapes`` tensor holds (callers that built it from
+    Python numbers: no device sync at all)."""
+    arr = (ctypes.c_int64 * (2 * len(shapes)))(*[int(v) for hw in shapes for v in hw])
+    key = id(spatial_shapes)
+    _HOST_SHAPES[key] = (weakref.ref(spatial_shapes, lambda _r, k=key: _HOST_SHAPES.pop(k, None)),
+                         getattr(spatial_shapes, "_version", 0) if not spatial_shapes.is_inference() else 0,
+                         arr)
+
+
+def host_shapes_of(spatial_shapes: torch.Tensor):
+    """ctypes int64 array (L*2) with the rows of ``spatial_shapes``, or None when it cannot be had
+    without disturbing the caller (graph capture in progress)."""
+    hit = _HOST_SHAPES.get(id(spatial_shapes))
+    if hit is not None and hit[0]() is spatial_shapes:
+        ver = getattr(spatial_shapes, "_version", 0) if not spatial_shapes.is_inference() else 0
+        if ver == hit[1]:
+            return hit[2]
+    if spatial_shapes.is_cuda and torch.cuda.is_current_stream_capturing():
+        return None
+    register_host_shapes(spatial_shapes, spatial_shapes.tolist())
+    return _HOST_SHAPES[id(spatial_shapes)][2]
+
+
+def backward_plan(N, S, M, D, L, Lq, P, dtype: torch.dtype, flags: int = 0, host_shapes=None) -> int:
+    """0 generic, 1 per-tap vector scatter, 2 cell-binned (needs a current CUDA device).
+    ``host_shapes``: what ``host_shapes_of`` returns, or a sequence of (H, W)."""
+    if host_shapes is not None and not isinstance(host_shapes, ctypes.Array):
+        host_shapes = (ctypes.c_int64 * (2 * len(host_shapes)))(*[int(v) for hw in host_shapes for v in hw])
+    rc = int(load().pct_msda_backward_plan_ex(N, S, M, D, L, Lq, P, DTYPE_CODES[dtype], flags,
+                                              host_shapes))
     if rc < 0:
         check(-rc, "pct_msda_backward_plan")
     return rc
@@ -165,7 +208,7 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
 
 
 def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-             flags: int = 0, out=None, workspace=None):
+             flags: int = 0, out=None, workspace=None, host_shapes=None):
     """Raw backward.  Returns (grad_value, grad_sampling_loc, grad_attn_weight); ``out`` may
     supply the three tensors and ``workspace`` a uint8 scratch tensor to avoid allocations."""
     lib = load()
@@ -184,12 +227,12 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     if ws_bytes and (ws is None or ws.numel() < ws_bytes):
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device)
     with torch.cuda.device_of(value):
-        rc = lib.pct_msda_backward_ex(
+        rc = lib.pct_msda_backward_ex2(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
             N, S, M, D, L, Lq, P, code, ws.data_ptr() if ws is not None else None, ws_bytes,
-            _stream_ptr(value.device), flags)
+            _stream_ptr(value.device), flags, host_shapes)
     check(rc, "pct_msda_backward")
     return grad_value, grad_loc, grad_attn
 
@@ -217,7 +260,7 @@ def fused_forward(value, spatial_shapes, level_start_index, reference_points, sa
 
 
 def fused_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
-                   attn_logits, grad_output, workspace=None, flags=0):
+                   attn_logits, grad_output, workspace=None, flags=0, host_shapes=None):
     """Returns (grad_value, grad_sampling_offsets, grad_attn_logits)."""
     lib = load()
     N, S, M, D = value.shape
@@ -232,13 +275,14 @@ def fused_backward(value, spatial_shapes, level_start_index, reference_points, s
     if ws_bytes and (ws is None or ws.numel() < ws_bytes):
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device)
     with torch.cuda.device_of(value):
-        rc = lib.pct_msda_fused_backward_ex(
+        rc = lib.pct_msda_fused_backward_ex2(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             reference_points.data_ptr(), reference_points.shape[-1], sampling_offsets.data_ptr(),
             attn_logits.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
             grad_off.data_ptr(), grad_logits.data_ptr(), N, S, M, D, L, Lq, P, code,
-            ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(value.device), flags)
-    check(rc, "pct_msda_fused_backward_ex")
+            ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(value.device), flags,
+            host_shapes)
+    check(rc, "pct_msda_fused_backward_ex2")
     return grad_value, grad_off, grad_logits
 
 

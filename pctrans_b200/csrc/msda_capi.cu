@@ -187,9 +187,13 @@ int device_smem_optin(int* out) {
 }
 
 // 0 = not eligible, else lanes per (query, head) row
+// `cells` = sum_l (H_l+1)(W_l+1) when the caller supplied the level shapes on the host, else 0: the
+// bound 2S + 2L (H + W <= H*W + 1) stands in, which is about twice the count of square maps.
+long long cells_bound(const Dims& d, long long cells) { return cells > 0 ? cells : 2ll * d.S + 2ll * d.L; }
+
 int binned_plan(const Dims& d, int dtype, unsigned flags, int smem_optin, const void* value,
                 const void* grad_out, const void* acc, const void* loc, const void* attn,
-                const void* grad_loc, bool fused = false) {
+                const void* grad_loc, bool fused = false, long long cells = 0) {
   if (flags & (PCT_MSDA_FLAG_FORCE_GENERIC | PCT_MSDA_FLAG_BWD_PER_TAP)) return 0;
   // Measured on B200 (profiles/r02_binned_v3_*.log): in its round-2 form (bilinear-basis sweep in
   // lock-step rounds) the binned kernel is faster than the per-tap kernel on every shape it fits
@@ -204,8 +208,8 @@ int binned_plan(const Dims& d, int dtype, unsigned flags, int smem_optin, const 
   if (d.L > pct::kBinMaxLevels || LP > pct::kBinMaxSamples) return 0;
   if ((long long)d.N * d.S * d.M * d.D >= (1ll << 31) || d.S == 0) return 0;   // 32-bit element offsets
   if ((long long)d.N * d.M * ((long long)d.Lq / 8 + 1) >= (1ll << 31)) return 0;   // task index
-  const long long nc_bound = 2ll * d.S + 2ll * d.L;
-  if (nc_bound > pct::kBinMaxCells) return 0;
+  const long long nc_bound = cells_bound(d, cells);
+  if (nc_bound > pct::kBinMaxCells || d.S > 32767) return 0;   // 16-bit cell ids, 15-bit pixel indices
   const int row_bytes = d.D * (int)elem_size(dtype);
   const long long fixed = pct::bin_bytes_fixed(nc_bound) + 1536;   // + the kernel's static arrays
   if (fixed + (long long)kBinMinChunk * pct::bin_bytes_per_query((int)LP, row_bytes, fused) > smem_optin) return 0;
@@ -360,16 +364,35 @@ size_t pct_msda_backward_workspace_bytes(int batch, int spatial_size, int num_he
 
 namespace {
 
+// Exact cell count from a HOST copy of spatial_shapes (optional): must describe the same S pixels.
+int host_cells(const int64_t* host_shapes, const Dims& d, long long* cells) {
+  *cells = 0;
+  if (!host_shapes) return 0;
+  long long pixels = 0, n = 0;
+  for (int l = 0; l < d.L; ++l) {
+    const long long H = host_shapes[2 * l], W = host_shapes[2 * l + 1];
+    if (H < 0 || W < 0 || H > (1ll << 30) || W > (1ll << 30)) return PCT_MSDA_E_BAD_SHAPE;
+    pixels += H * W;
+    if (H > 0 && W > 0) n += (H + 1) * (W + 1);
+  }
+  if (pixels != d.S) return PCT_MSDA_E_BAD_SHAPE;
+  *cells = n > 0 ? n : 1;
+  return 0;
+}
+
 int backward_impl(const void* value, const int64_t* spatial_shapes,
                   const int64_t* level_start_index, const void* sampling_loc,
                   const void* attn_weight, const void* grad_output, void* grad_value,
                   void* grad_sampling_loc, void* grad_attn_weight, int batch, int spatial_size,
                   int num_heads, int channels, int num_levels, int num_query, int num_point,
                   int value_dtype, void* workspace, size_t workspace_bytes, void* cuda_stream,
-                  unsigned flags, pct::FusedRef fr) {
+                  unsigned flags, pct::FusedRef fr, const int64_t* host_shapes = nullptr) {
   const bool fused = fr.ref != nullptr;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   int rc = check_dims(d, value_dtype);
+  if (rc) return rc;
+  long long cells = 0;
+  rc = host_cells(host_shapes, d, &cells);
   if (rc) return rc;
   const long long n_value = (long long)d.N * d.S * d.M * d.D;
   const long long n_pairs = (long long)d.N * d.Lq * d.M;
@@ -415,7 +438,7 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
       aligned(grad_sampling_loc, 8) && workspace && aligned(workspace, 16) &&
       // (an explicit request for the binned kernel wins over this per-tap option, the default does not)
       !binned_plan(d, value_dtype, !(flags & PCT_MSDA_FLAG_BWD_BINNED) ? (flags | PCT_MSDA_FLAG_BWD_PER_TAP) : flags, smem_optin, value,
-                   grad_output, workspace, sampling_loc, attn_weight, grad_sampling_loc, fused)) {
+                   grad_output, workspace, sampling_loc, attn_weight, grad_sampling_loc, fused, cells)) {
     const VecPlan p = vec_eligible(d, value_dtype, flags, value, grad_output, workspace, sampling_loc,
                                    attn_weight);
     if (p.lanes > 0) half_fn = pick_bwd_half_accum(fused, p);
@@ -504,12 +527,12 @@ int backward_impl(const void* value, const int64_t* spatial_shapes,
   const int bin_lanes = (det_fn || bf16_accum || half_fn)
                             ? 0
                             : binned_plan(d, value_dtype, flags, smem_optin, value, grad_output, acc_image,
-                                          sampling_loc, attn_weight, grad_sampling_loc, fused);
+                                          sampling_loc, attn_weight, grad_sampling_loc, fused, cells);
   if (bin_lanes) {
     rc = dispatch_bwd_binned(bin_lanes, value_dtype, value, spatial_shapes, level_start_index,
                              sampling_loc, attn_weight, grad_output, acc_image, grad_sampling_loc,
                              grad_attn_weight, d, sm_count, smem_optin, st, flags,
-                             fused ? fr : pct::FusedRef{nullptr, 0});
+                             fused ? fr : pct::FusedRef{nullptr, 0}, cells_bound(d, cells));
   } else if (BwdLauncher fn = det_fn          ? det_fn
                               : half_fn       ? half_fn
                               : bf16_accum    ? bf16_accum
@@ -555,8 +578,18 @@ extern "C" {
 int pct_msda_backward_plan(int batch, int spatial_size, int num_heads, int channels,
                            int num_levels, int num_query, int num_point, int value_dtype,
                            unsigned flags) {
+  return pct_msda_backward_plan_ex(batch, spatial_size, num_heads, channels, num_levels, num_query,
+                                   num_point, value_dtype, flags, nullptr);
+}
+
+int pct_msda_backward_plan_ex(int batch, int spatial_size, int num_heads, int channels,
+                              int num_levels, int num_query, int num_point, int value_dtype,
+                              unsigned flags, const int64_t* host_spatial_shapes) {
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   int rc = check_dims(d, value_dtype);
+  if (rc) return -rc;
+  long long cells = 0;
+  rc = host_cells(host_spatial_shapes, d, &cells);
   if (rc) return -rc;
   const bool special = flags & (PCT_MSDA_FLAG_DETERMINISTIC | PCT_MSDA_FLAG_BF16_ACCUM);
   if (!special) {
@@ -564,7 +597,8 @@ int pct_msda_backward_plan(int batch, int spatial_size, int num_heads, int chann
     rc = device_smem_optin(&smem_optin);
     if (rc) return -rc;
     alignas(16) static const char dummy[16] = {0};
-    if (binned_plan(d, value_dtype, flags, smem_optin, dummy, dummy, dummy, dummy, dummy, dummy)) return 2;
+    if (binned_plan(d, value_dtype, flags, smem_optin, dummy, dummy, dummy, dummy, dummy, dummy, false, cells))
+      return 2;
   }
   if (flags & PCT_MSDA_FLAG_FORCE_GENERIC) return 0;
   if ((long long)d.S * d.M * d.D >= (1ll << 31) || d.S == 0) return 0;
@@ -579,11 +613,25 @@ int pct_msda_backward_ex(const void* value, const int64_t* spatial_shapes,
                          int spatial_size, int num_heads, int channels, int num_levels,
                          int num_query, int num_point, int value_dtype, void* workspace,
                          size_t workspace_bytes, void* cuda_stream, unsigned flags) {
+  return pct_msda_backward_ex2(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                               grad_output, grad_value, grad_sampling_loc, grad_attn_weight, batch,
+                               spatial_size, num_heads, channels, num_levels, num_query, num_point,
+                               value_dtype, workspace, workspace_bytes, cuda_stream, flags, nullptr);
+}
+
+int pct_msda_backward_ex2(const void* value, const int64_t* spatial_shapes,
+                          const int64_t* level_start_index, const void* sampling_loc,
+                          const void* attn_weight, const void* grad_output, void* grad_value,
+                          void* grad_sampling_loc, void* grad_attn_weight, int batch,
+                          int spatial_size, int num_heads, int channels, int num_levels,
+                          int num_query, int num_point, int value_dtype, void* workspace,
+                          size_t workspace_bytes, void* cuda_stream, unsigned flags,
+                          const int64_t* host_spatial_shapes) {
   return backward_impl(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                        grad_output, grad_value, grad_sampling_loc, grad_attn_weight, batch,
                        spatial_size, num_heads, channels, num_levels, num_query, num_point,
                        value_dtype, workspace, workspace_bytes, cuda_stream, flags,
-                       pct::FusedRef{nullptr, 0});
+                       pct::FusedRef{nullptr, 0}, host_spatial_shapes);
 }
 
 int pct_msda_fused_backward(const void* value, const int64_t* spatial_shapes,
@@ -609,6 +657,22 @@ int pct_msda_fused_backward_ex(const void* value, const int64_t* spatial_shapes,
                                int channels, int num_levels, int num_query, int num_point,
                                int value_dtype, void* workspace, size_t workspace_bytes,
                                void* cuda_stream, unsigned flags) {
+  return pct_msda_fused_backward_ex2(value, spatial_shapes, level_start_index, reference_points, ref_dim,
+                                     sampling_offsets, attn_logits, grad_output, grad_value,
+                                     grad_offsets, grad_logits, batch, spatial_size, num_heads,
+                                     channels, num_levels, num_query, num_point, value_dtype,
+                                     workspace, workspace_bytes, cuda_stream, flags, nullptr);
+}
+
+int pct_msda_fused_backward_ex2(const void* value, const int64_t* spatial_shapes,
+                                const int64_t* level_start_index, const void* reference_points,
+                                int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                                const void* grad_output, void* grad_value, void* grad_offsets,
+                                void* grad_logits, int batch, int spatial_size, int num_heads,
+                                int channels, int num_levels, int num_query, int num_point,
+                                int value_dtype, void* workspace, size_t workspace_bytes,
+                                void* cuda_stream, unsigned flags,
+                                const int64_t* host_spatial_shapes) {
   if (flags & ~(PCT_MSDA_FLAG_BWD_PER_TAP | PCT_MSDA_FLAG_BWD_BINNED | PCT_MSDA_FLAG_BF16_F16_ACCUM |
                 0xffffff00u))
     return PCT_MSDA_E_UNSUPPORTED;   // the other options exist for the plain entry point only
@@ -621,7 +685,7 @@ int pct_msda_fused_backward_ex(const void* value, const int64_t* spatial_shapes,
                        grad_output, grad_value, grad_offsets, grad_logits, batch, spatial_size,
                        num_heads, channels, num_levels, num_query, num_point, value_dtype,
                        workspace, workspace_bytes, cuda_stream, flags,
-                       pct::FusedRef{(const float*)reference_points, ref_dim});
+                       pct::FusedRef{(const float*)reference_points, ref_dim}, host_spatial_shapes);
 }
 
 int pct_msda_backward(const void* value, const int64_t* spatial_shapes,

@@ -12,7 +12,7 @@ template <typename T, int LPP, bool FUSED>
 int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
                       const void* attn, const void* grad_out, void* gacc, void* grad_loc,
                       void* grad_attn, const Dims& d, int sm_count, int smem_optin, cudaStream_t st,
-                      unsigned flags, pct::FusedRef fr) {
+                      unsigned flags, pct::FusedRef fr, long long cells_bound) {
   static std::atomic<int> configured[64];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -39,7 +39,7 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
     // a half tasks each, shorter chunks do (the kernel takes the smaller of this cap and what fits).
     const long long streams = (long long)d.N * d.M;
     const long long per_q = pct::bin_bytes_per_query(d.L * d.P, LPP * 4 * (int)sizeof(T), FUSED);
-    long long qc_fit = (dyn - pct::bin_bytes_fixed(2ll * d.S + 2ll * d.L)) / per_q;
+    long long qc_fit = (dyn - pct::bin_bytes_fixed(cells_bound)) / per_q;
     if (qc_fit > pct::kBinMaxQc) qc_fit = pct::kBinMaxQc;
     if (qc_fit < kBinMinChunk) qc_fit = kBinMinChunk;
     const long long chunks_fit = (d.Lq + qc_fit - 1) / qc_fit;
@@ -72,14 +72,15 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
 int dispatch_bwd_binned(int lanes, int dtype, const void* value, const int64_t* shapes,
                         const int64_t* lsi, const void* loc, const void* attn, const void* grad_out,
                         void* gacc, void* grad_loc, void* grad_attn, const Dims& d, int sm_count,
-                        int smem_optin, cudaStream_t st, unsigned flags, pct::FusedRef fr) {
+                        int smem_optin, cudaStream_t st, unsigned flags, pct::FusedRef fr,
+                        long long cells_bound) {
 #define PCT_BIN_CASE(T, LPP)                                                                       \
   return fr.ref ? launch_bwd_binned<T, LPP, true>(value, shapes, lsi, loc, attn, grad_out, gacc,   \
                                                   grad_loc, grad_attn, d, sm_count, smem_optin,    \
-                                                  st, flags, fr)                                   \
+                                                  st, flags, fr, cells_bound)                      \
                 : launch_bwd_binned<T, LPP, false>(value, shapes, lsi, loc, attn, grad_out, gacc,  \
                                                    grad_loc, grad_attn, d, sm_count, smem_optin,   \
-                                                   st, flags, fr)
+                                                   st, flags, fr, cells_bound)
   if (dtype == PCT_MSDA_F32) {
     switch (lanes) {
       case 4: PCT_BIN_CASE(float, 4);

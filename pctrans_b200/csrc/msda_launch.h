@@ -57,6 +57,7 @@ constexpr int kBinMinChunk = 64;   // below this many queries per chunk the per-
 int dispatch_bwd_binned(int lanes, int dtype, const void* value, const int64_t* shapes,
                         const int64_t* lsi, const void* loc, const void* attn, const void* grad_out,
                         void* gacc, void* grad_loc, void* grad_attn, const Dims& d, int sm_count,
-                        int smem_optin, cudaStream_t st, unsigned flags, pct::FusedRef fr);
+                        int smem_optin, cudaStream_t st, unsigned flags, pct::FusedRef fr,
+                        long long cells_bound);
 
 }  // namespace pctl

@@ -188,6 +188,11 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
                 spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=device)
                 level_start_index = torch.cat(
                     (spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+            if spatial_shapes.is_cuda:
+                # the backward kernels may use the exact cell count of the pyramid; the shapes are
+                # known here on the host, so the binding never has to read the tensor back
+                from . import _cabi
+                _cabi.register_host_shapes(spatial_shapes, shapes)
             cache[key] = (spatial_shapes, level_start_index)
         return cache[key]
 

@@ -105,7 +105,8 @@ class MSDeformAttnFunction(Function):
                                    f"for value dtype {value.dtype} / head dim {D}")
         try:
             grad_value, grad_loc, grad_attn = _cabi.backward(value, shapes, lsi, loc, attn,
-                                                             grad_output, flags=flags or _TUNE_BWD_FLAGS)
+                                                             grad_output, flags=flags or _TUNE_BWD_FLAGS,
+                                                             host_shapes=_cabi.host_shapes_of(shapes))
         except _cabi.MSDAError as e:
             if not (flags and e.code == _cabi.E_UNSUPPORTED):
                 raise
@@ -169,7 +170,8 @@ class MSDeformAttnFusedFunction(Function):
         if grad_output.dtype != value.dtype:
             grad_output = grad_output.to(value.dtype)
         gv, goff, glog = _cabi.fused_backward(value, shapes, lsi, ref, offsets, logits, grad_output,
-                                              flags=_TUNE_BWD_FLAGS)
+                                              flags=_TUNE_BWD_FLAGS,
+                                              host_shapes=_cabi.host_shapes_of(shapes))
         return gv, None, None, None, goff, glog
 
 

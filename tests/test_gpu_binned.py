@@ -199,3 +199,33 @@ def test_binned_largest_map_that_fits():
     assert _cabi.backward_plan(1, 19000, 1, 16, 1, 100, 4, torch.float32, 0) == 1     # counters do not fit
     assert _cabi.backward_plan(1, 32768, 1, 16, 1, 100, 4, torch.float32, 0) == 1
     assert _cabi.backward_plan(30000, S, 1, 16, 1, 100, 4, torch.float32, 0) == 1     # N S M D >= 2^31: 64-bit offsets
+
+
+def test_host_shapes_extend_the_binned_kernel_to_large_maps():
+    """With a host copy of spatial_shapes (pct_msda_backward_ex2) the exact cell count replaces
+    the 2S + 2L bound: a 1024 x 1024 input's pyramid (128^2 + 64^2 + 32^2 = 21 504 pixels, 21 955
+    cells) runs on the binned kernel -- same results as the per-tap kernel and the oracle -- and a
+    host copy that does not describe the same pixels is an error."""
+    shapes = ((32, 32), (64, 64), (128, 128))
+    N, M, D, P, Lq = 1, 2, 32, 4, 3000
+    value, sh, lsi, loc, attn = synth.make_inputs(N, shapes, M=M, D=D, P=P, regime="U", seed=31, Lq=Lq)
+    loc = synth.nudge_off_grid(loc, shapes)
+    S = value.shape[1]
+    g = torch.randn(N, Lq, M * D, generator=torch.Generator().manual_seed(32))
+    assert _cabi.backward_plan(N, S, M, D, 3, Lq, P, torch.float32, 0) == 1
+    assert _cabi.backward_plan(N, S, M, D, 3, Lq, P, torch.float32, 0, host_shapes=shapes) == 2
+    d_sh = sh.to(DEV)
+    args = (value.to(DEV), d_sh, lsi.to(DEV), loc.to(DEV), attn.to(DEV), g.to(DEV))
+    hs = _cabi.host_shapes_of(d_sh)
+    assert list(hs) == [v for hw in shapes for v in hw]
+    bv, bl, ba = _cabi.backward(*args, host_shapes=hs)
+    pv, pl, pa = _cabi.backward(*args)                      # no host copy: the per-tap kernel
+    torch.cuda.synchronize()
+    rv, rl, ra = oracle.backward_c(value, sh, lsi, loc, attn, g)
+    assert not torch.equal(bl, pl)
+    for got, tap, want in ((bv, pv, rv), (bl, pl, rl), (ba, pa, ra)):
+        assert rel(got, want) <= 1e-4 and rel(got, tap.double().cpu().numpy()) <= 1e-4
+    import ctypes
+    wrong = (ctypes.c_int64 * 6)(32, 32, 64, 64, 128, 127)
+    with pytest.raises(_cabi.MSDAError):
+        _cabi.backward(*args, host_shapes=wrong)
