@@ -541,6 +541,9 @@ msda_bwd_binned_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // launched as a programmatic dependent of the zero-fill of gacc: nothing above touches gacc,
+    // the reductions below do (a no-op after the first task and for a plain launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
 
     // ---- sweep: lock-step rounds over the non-empty cells, fullest cells first ----

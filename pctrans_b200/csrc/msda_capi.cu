@@ -128,6 +128,9 @@ int check_dims(const Dims& d, int dtype) {
   return 0;
 }
 
+#ifndef PCT_ZERO_CTAS_PER_SM
+#define PCT_ZERO_CTAS_PER_SM 4
+#endif
 // zero `bytes` at a 16-byte aligned address with a kernel (see msda_zero_kernel)
 int zero_fill(void* p, size_t bytes, int sm_count, cudaStream_t st) {
   if (bytes == 0) return 0;
@@ -135,7 +138,9 @@ int zero_fill(void* p, size_t bytes, int sm_count, cudaStream_t st) {
   const long long n16 = (long long)(bytes / 16);
   const int n_tail = (int)(bytes % 16);
   long long want = (n16 + 1023) / 1024;   // 4 stores per thread per pass
-  long long cap = (long long)sm_count * 8;
+  // 4 CTAs = 1024 threads per SM: enough stores in flight for the HBM rate, and room for the
+  // 1024-thread CTA of the cell-binned backward to become resident beside them (see msda_zero_kernel)
+  long long cap = (long long)sm_count * PCT_ZERO_CTAS_PER_SM;
   const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
   pct::msda_zero_kernel<<<grid, 256, 0, st>>>((uint4*)p, n16, (unsigned char*)p + n16 * 16, n_tail);
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -5,6 +5,10 @@
 #include "msda_bwd_binned.cuh"
 #include "msda_launch.h"
 
+#ifndef PCT_BIN_PDL
+#define PCT_BIN_PDL 1
+#endif
+
 namespace pctl {
 namespace {
 
@@ -60,11 +64,23 @@ int launch_bwd_binned(const void* value, const int64_t* shapes, const int64_t* l
   const long long want = (long long)d.N * d.M * ((d.Lq + kBinMinChunk - 1) / kBinMinChunk);
   const long long cap = (long long)sm_count * pct::kBinCtasPerSm;
   const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-  kern<<<grid, pct::kBinThreads, dyn, st>>>(
-      (const T*)value, shapes, lsi, (const float*)loc, (const float*)attn, (const T*)grad_out,
-      (float*)gacc, (float*)grad_loc, (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, bl, fr);
+  // Programmatic dependent launch behind the zero-fill of the accumulator image: the CTAs start
+  // while it still runs, sort their first chunk, and wait before the first reduction.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)pct::kBinThreads);
+  cfg.dynamicSmemBytes = (size_t)dyn;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = PCT_BIN_PDL;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, (const T*)value, shapes, lsi, (const float*)loc,
+                         (const float*)attn, (const T*)grad_out, (float*)gacc, (float*)grad_loc,
+                         (float*)grad_attn, d.N, d.S, d.M, d.L, d.Lq, d.P, bl, fr);
   count_launches(1);
-  return (int)cudaGetLastError();
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 }  // namespace

@@ -1001,6 +1001,10 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 // (pctrans_b200/host_pipeline.py) and stalls the backward of every chunk.
 static __global__ void msda_zero_kernel(uint4* __restrict__ dst, long long n16, unsigned char* tail,
                                  int n_tail) {
+  // programmatic dependent launch: the gradient kernel that follows on the stream may start its
+  // CTAs now -- the cell-binned backward sorts its first chunk while this kernel still writes, and
+  // waits (griddepcontrol.wait) before its first reduction into the cleared image
+  asm volatile("griddepcontrol.launch_dependents;");
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
