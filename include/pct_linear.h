@@ -43,6 +43,16 @@ extern "C" {
                                      after value_proj (OPS/modules/ms_deform_attn.py:100-101) in the
                                      epilogue; not combinable with RESIDUAL / GATE / LAYERNORM */
 
+#define PCT_LINEAR_BF16 0x20u     /* operand precision: x and W are rounded to bf16 (nearest even) on their
+                                     way into the tensor cores, products accumulate in fp32; tensors in
+                                     global memory stay fp32 and every epilogue above applies.  One
+                                     tcgen05.mma.kind::f16 instead of three kind::tf32 per K step: what
+                                     torch.autocast(bfloat16) computes for a Linear (without rounding
+                                     the result), for callers that trade the reference's fp32 accuracy
+                                     (PD/msdeformattn.py:314-320 disables autocast) for speed.
+                                     `w_packed` must come from pct_linear_pack_weight_bf16;
+                                     in_features % 32 == 0.  pct_linear_forward(_train) only. */
+
 /* Constraints everywhere: in_features % 16 == 0, out_features % 16 == 0; x, packed weight, residual,
  * y, pre_norm, grad_y, grad_w, grad_bias 16-byte aligned (bias / LayerNorm vectors: 4-byte). */
 
@@ -53,6 +63,12 @@ size_t pct_linear_packed_bytes(int in_features, int out_features);
  * followed by the fp32 remainder (w - head), each in tensor-core core-matrix order. */
 int pct_linear_pack_weight(const float* w, void* packed, int in_features, int out_features,
                            void* cuda_stream);
+
+/* The same for PCT_LINEAR_BF16: w (out, in) fp32 -> packed bf16, per 256-column tile and 32-element K
+ * step one piece in tensor-core core-matrix order.  in_features % 32 == 0. */
+size_t pct_linear_packed_bytes_bf16(int in_features, int out_features);
+int pct_linear_pack_weight_bf16(const float* w, void* packed, int in_features, int out_features,
+                                void* cuda_stream);
 
 /* y (rows, out) = epilogue(x (rows, in) @ W^T + bias).  bias may be NULL.  residual / ln_gamma /
  * ln_beta are read only when their flag is set.  rows >= 1. */

@@ -32,9 +32,11 @@ EXPORTS = (
     "pct_msda_host_ctx_create", "pct_msda_host_ctx_destroy", "pct_msda_host_forward",
     "pct_msda_host_forward_backward",
 )
-LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_forward",
+LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_packed_bytes_bf16",
+                  "pct_linear_pack_weight_bf16", "pct_linear_forward",
                   "pct_linear_forward_train", "pct_linear_wgrad", "pct_linear_layernorm_backward")
 LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM, LINEAR_GATE, LINEAR_ROWMASK = 0x1, 0x2, 0x4, 0x8, 0x10
+LINEAR_BF16 = 0x20
 E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
 FLAG_BF16_ACCUM = 0x8
@@ -110,6 +112,10 @@ def load():
         lib.pct_linear_packed_bytes.argtypes = [i32, i32]
         lib.pct_linear_pack_weight.restype = i32
         lib.pct_linear_pack_weight.argtypes = [vp, vp, i32, i32, vp]
+        lib.pct_linear_packed_bytes_bf16.restype = sz
+        lib.pct_linear_packed_bytes_bf16.argtypes = [i32, i32]
+        lib.pct_linear_pack_weight_bf16.restype = i32
+        lib.pct_linear_pack_weight_bf16.argtypes = [vp, vp, i32, i32, vp]
         lib.pct_linear_wgrad.restype = i32
         lib.pct_linear_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
         lib.pct_linear_layernorm_backward.restype = i32
@@ -286,31 +292,39 @@ def fused_backward(value, spatial_shapes, level_start_index, reference_points, s
     return grad_value, grad_off, grad_logits
 
 
-def linear_pack_weight(weight):
-    """(out, in) fp32 weight -> packed 3xTF32 operand (uint8 tensor) for linear_forward."""
+def linear_pack_weight(weight, bf16: bool = False):
+    """(out, in) fp32 weight -> packed operand (uint8 tensor) for linear_forward: the 3xTF32 split,
+    or with ``bf16`` the bf16 rounding (for ``linear_forward(..., bf16=True)``)."""
     w = weight.detach().contiguous()
     n, k = w.shape
-    nbytes = load().pct_linear_packed_bytes(k, n)
+    lib = load()
+    size_fn, pack_fn = ((lib.pct_linear_packed_bytes_bf16, lib.pct_linear_pack_weight_bf16) if bf16
+                        else (lib.pct_linear_packed_bytes, lib.pct_linear_pack_weight))
+    nbytes = size_fn(k, n)
     if nbytes == 0:
-        raise MSDAError(f"pct_linear: unsupported Linear dimensions in={k} out={n}", 1002)
+        raise MSDAError(f"pct_linear: unsupported Linear dimensions in={k} out={n}"
+                        + (" (bf16 operands)" if bf16 else ""), 1002)
     packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     with torch.cuda.device_of(w):
-        check(load().pct_linear_pack_weight(w.data_ptr(), packed.data_ptr(), k, n,
-                                            _stream_ptr(w.device)), "pct_linear_pack_weight")
+        check(pack_fn(w.data_ptr(), packed.data_ptr(), k, n, _stream_ptr(w.device)),
+              "pct_linear_pack_weight")
     return packed
 
 
 def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weight=None,
                    ln_bias=None, ln_eps: float = 1e-5, relu: bool = False, out=None,
-                   save_for_backward: bool = False, gate=None, row_mask=None):
+                   save_for_backward: bool = False, gate=None, row_mask=None, bf16: bool = False):
     """y = epilogue(x @ W^T + bias) on the tensor cores (3xTF32); x (rows, in) fp32 contiguous.
+    ``bf16``: operands rounded to bf16 on their way into the tensor cores (PCT_LINEAR_BF16);
+    ``w_packed`` must then come from ``linear_pack_weight(w, bf16=True)``.
     With ``save_for_backward`` (LayerNorm epilogue only) returns (y, pre_norm, mean, rstd).
     ``gate`` (rows, out): y is zeroed where gate <= 0 (ReLU backward fused into a dgrad GEMM).
     ``row_mask`` (rows,) bool / uint8: rows with a non-zero entry are written as zeros."""
     rows, k = x.shape
     n = out_features
     flags = (LINEAR_RELU if relu else 0) | (LINEAR_RESIDUAL if residual is not None else 0) | \
-        (LINEAR_LAYERNORM if ln_weight is not None else 0) | (LINEAR_GATE if gate is not None else 0)
+        (LINEAR_LAYERNORM if ln_weight is not None else 0) | (LINEAR_GATE if gate is not None else 0) | \
+        (LINEAR_BF16 if bf16 else 0)
     if gate is not None:
         if residual is not None:
             raise ValueError("gate and residual share an argument slot of the C ABI")

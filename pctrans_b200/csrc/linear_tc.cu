@@ -51,12 +51,32 @@ constexpr int kABytes = kBlockM * kBlockK * 4;        // one piece (hi or lo) of
 constexpr int kBBytes = kBlockN * kBlockK * 4;        // one piece of the W tile
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
 constexpr int kWStepBytes = 2 * kBBytes;              // packed W: hi piece then lo piece of one K step
-constexpr int kBarrierBytes = 64;
+constexpr int kBarrierBytes = 128;
 constexpr int kVecBytes = 3 * kBlockN * 4;            // bias, gamma, beta of the tile's columns
 constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + kVecBytes;
 constexpr int kAhead = 3;                             // K steps of x in flight per loader thread
 constexpr int kPatchStride = 36;                      // floats per patch row: conflict-free both ways
 static_assert(kLoaderWarps * 32 * kPatchStride * 4 <= kStages * kStageBytes, "epilogue patches reuse the ring");
+
+// The forward / input-gradient kernel exists in two operand precisions with the same byte geometry
+// (a K step is 64 bytes of every row: four 16-byte core-matrix columns, two MMAs' worth of K):
+//   3xTF32 (fp32 accuracy):  16 floats of K per step, every operand as a tf32 head and an fp32
+//                            remainder piece, 6 MMAs per step, 48 KB per stage, 2 stages;
+//   bf16 (PCT_LINEAR_BF16):  32 elements of K per step, operands rounded once to bf16, 2 MMAs per
+//                            step (kind::f16, fp32 accumulate), 24 KB per stage, 4 stages.
+template <bool BF16>
+struct Prec {
+  static constexpr int kPieces = BF16 ? 1 : 2;
+  static constexpr int kStepK = BF16 ? 32 : 16;             // elements of K per stage
+  static constexpr int kNumStages = BF16 ? 4 : 2;
+  static constexpr int kStage = kPieces * (kABytes + kBBytes);
+  static constexpr int kWStep = kPieces * kBBytes;
+  static constexpr int kXAhead = BF16 ? 2 : 3;               // K steps of x in flight per loader thread
+  static constexpr int kSmem = kNumStages * kStage + kBarrierBytes + kVecBytes;
+  static_assert(kLoaderWarps * 32 * kPatchStride * 4 <= kNumStages * kStage, "epilogue patches reuse the ring");
+  static_assert((3 * kNumStages + 1) * 8 + 4 <= kBarrierBytes, "barriers + TMEM slot");
+};
+static_assert(Prec<false>::kSmem == kSmemBytes && Prec<false>::kStage == kStageBytes, "3xTF32 geometry");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -81,6 +101,31 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// Instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n (kind::f16).
+__device__ __forceinline__ uint32_t make_instr_desc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// eight fp32 -> eight bf16 (round to nearest even), element 0 at the lowest address
+__device__ __forceinline__ uint4 pack_bf16x8(const float4& a, const float4& b) {
+  uint4 r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(a.y), "f"(a.x));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(a.w), "f"(a.z));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.z) : "f"(b.y), "f"(b.x));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.w) : "f"(b.w), "f"(b.z));
+  return r;
 }
 
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -350,8 +395,11 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const LinearArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+template <bool BF16>
+__device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* smem) {
+  using P = Prec<BF16>;
+  constexpr int kStages = P::kNumStages, kStageBytes = P::kStage, kWStepBytes = P::kWStep;
+  constexpr int kAhead = P::kXAhead;
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -396,13 +444,13 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  const int n_steps = a.K / kBlockK;
+  const int n_steps = a.K / P::kStepK;
   const uint32_t smem0 = smem_u32(smem);
 
   if (warp == kLoaderWarps) {
     // ---- issuer: one thread feeds the tensor core ----------------------------------------------
     if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(n_tile);
+      const uint32_t idesc = BF16 ? make_instr_desc_bf16(n_tile) : make_instr_desc(n_tile);
       for (int step = 0; step < n_steps; ++step) {
         const int s = step % kStages;
         const uint32_t parity = (step / kStages) & 1;
@@ -412,15 +460,20 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
         const uint32_t sa = smem0 + s * kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < kBlockK / kMmaK; ++ks) {
-          const uint32_t koff = ks * (kMmaK / 4) * kLbo;
-          const uint64_t d_ahi = make_smem_desc(sa + koff);
-          const uint64_t d_alo = make_smem_desc(sa + kABytes + koff);
-          const uint64_t d_bhi = make_smem_desc(sa + 2 * kABytes + koff);
-          const uint64_t d_blo = make_smem_desc(sa + 2 * kABytes + kBBytes + koff);
-          // consecutive MMAs share one operand (W_hi, then x_hi)
-          mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);
-          mma_tf32(tmem, d_ahi, d_bhi, idesc, 1u);
-          mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
+          const uint32_t koff = ks * (kMmaK / 4) * kLbo;   // 32 bytes of K per MMA in both precisions
+          if constexpr (BF16) {
+            mma_bf16(tmem, make_smem_desc(sa + koff), make_smem_desc(sa + kABytes + koff), idesc,
+                     (step | ks) != 0);
+          } else {
+            const uint64_t d_ahi = make_smem_desc(sa + koff);
+            const uint64_t d_alo = make_smem_desc(sa + kABytes + koff);
+            const uint64_t d_bhi = make_smem_desc(sa + 2 * kABytes + koff);
+            const uint64_t d_blo = make_smem_desc(sa + 2 * kABytes + kBBytes + koff);
+            // consecutive MMAs share one operand (W_hi, then x_hi)
+            mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);
+            mma_tf32(tmem, d_ahi, d_bhi, idesc, 1u);
+            mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
+          }
         }
         mma_commit(bar_empty + 8 * s);             // stage free once these MMAs have read it
         if (step == n_steps - 1) mma_commit(bar_done);
@@ -432,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
     auto fetch_w = [&](int step) {
       const int s = step % kStages;
       mbar_expect_tx(bar_wfull + 8 * s, kWStepBytes);
-      bulk_load(smem0 + s * kStageBytes + 2 * kABytes, w_tile + (size_t)step * kWStepBytes,
+      bulk_load(smem0 + s * kStageBytes + P::kPieces * kABytes, w_tile + (size_t)step * kWStepBytes,
                 kWStepBytes, bar_wfull + 8 * s);
     };
     if (lane == 0)
@@ -471,14 +524,20 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
       const int row = m0 + (rg + kLoaderWarps * j) * 8 + r8;
-      xrow[j] = row < a.rows ? a.x + (size_t)row * a.K + kc * 4 : nullptr;
+      xrow[j] = row < a.rows ? a.x + (size_t)row * a.K + kc * (P::kStepK / 4) : nullptr;
     }
-    float4 xq[kAhead][kPerThread];   // kAhead K steps in flight: the loads are DRAM-latency bound
+    // kAhead K steps in flight: the loads are DRAM-latency bound.  A thread's share of a row is one
+    // 16-byte chunk of the stage: 4 floats (3xTF32) or 8 floats rounded to bf16
+    constexpr int kQ = BF16 ? 2 : 1;
+    float4 xq[kAhead][kPerThread * kQ];
     auto fetch_x = [&](float4* dst, int step) {
 #pragma unroll
       for (int j = 0; j < kPerThread; ++j)
-        dst[j] = xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + step * kBlockK))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < kQ; ++h)
+          dst[j * kQ + h] =
+              xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + step * P::kStepK) + h)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
     };
 #pragma unroll
     for (int d = 0; d < kAhead; ++d)
@@ -491,15 +550,20 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
           const int s = step % kStages;
           if (step >= kStages) mbar_wait(bar_empty + 8 * s, ((step / kStages) - 1) & 1);
           float4* a_hi = reinterpret_cast<float4*>(smem + s * kStageBytes);
-          float4* a_lo = reinterpret_cast<float4*>(smem + s * kStageBytes + kABytes);
+          [[maybe_unused]] float4* a_lo = reinterpret_cast<float4*>(smem + s * kStageBytes + kABytes);
 #pragma unroll
           for (int j = 0; j < kPerThread; ++j) {
-            const float4 x4 = xq[d][j];
-            float4 h, l;
-            h.x = tf32_head(x4.x), h.y = tf32_head(x4.y), h.z = tf32_head(x4.z), h.w = tf32_head(x4.w);
-            l.x = x4.x - h.x, l.y = x4.y - h.y, l.z = x4.z - h.z, l.w = x4.w - h.w;
-            a_hi[tid + kLoaderWarps * 32 * j] = h;
-            a_lo[tid + kLoaderWarps * 32 * j] = l;
+            if constexpr (BF16) {
+              reinterpret_cast<uint4*>(a_hi)[tid + kLoaderWarps * 32 * j] =
+                  pack_bf16x8(xq[d][2 * j], xq[d][2 * j + 1]);
+            } else {
+              const float4 x4 = xq[d][j];
+              float4 h, l;
+              h.x = tf32_head(x4.x), h.y = tf32_head(x4.y), h.z = tf32_head(x4.z), h.w = tf32_head(x4.w);
+              l.x = x4.x - h.x, l.y = x4.y - h.y, l.z = x4.z - h.z, l.w = x4.w - h.w;
+              a_hi[tid + kLoaderWarps * 32 * j] = h;
+              a_lo[tid + kLoaderWarps * 32 * j] = l;
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
           __syncwarp();                                                    // one arrival per warp
@@ -525,6 +589,17 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
                  "r"((uint32_t)kBlockN)
                  : "memory");
   }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const LinearArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  linear_body<false>(a, smem);
+}
+
+// bf16 operands (PCT_LINEAR_BF16): same roles, barriers and epilogue; fp32 tensors in global memory
+__global__ void __launch_bounds__(kThreads, 2) linear_bf16_kernel(const LinearArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  linear_body<true>(a, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -803,6 +878,30 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float4* __restri
   }
 }
 
+// bf16 operand precision: W (N, K) fp32 -> per (256-column tile, 32-element K step) one 16 KB piece of
+// bf16 in the same core-matrix order (16-byte chunk i <-> column 8*(i/32) + i%8, elements
+// 8*((i/8)%4) .. +7 of the step); columns past N are zero.
+__global__ void pack_weight_bf16_kernel(const float* __restrict__ w, uint4* __restrict__ packed, int N,
+                                        int K) {
+  const int n_steps = K / Prec<true>::kStepK;
+  const size_t per_piece = kBBytes / 16;
+  const size_t total = (size_t)((N + kBlockN - 1) / kBlockN) * n_steps * per_piece;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % per_piece);
+    const size_t ts = idx / per_piece;                         // tile * n_steps + step
+    const int step = (int)(ts % n_steps), tile = (int)(ts / n_steps);
+    const int col = tile * kBlockN + (i >> 5) * 8 + (i & 7);
+    const int k = step * Prec<true>::kStepK + ((i >> 3) & 3) * 8;
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    if (col < N) {
+      x0 = *reinterpret_cast<const float4*>(w + (size_t)col * K + k);
+      x1 = *reinterpret_cast<const float4*>(w + (size_t)col * K + k + 4);
+    }
+    packed[idx] = pack_bf16x8(x0, x1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight gradient: dW (N, K) = dY^T (N, rows) @ X (rows, K), the reduction running over the rows.
 // Both operands are activations, so both are split on the fly, and both arrive transposed: global
@@ -1056,6 +1155,27 @@ int pct_linear_pack_weight(const float* w, void* packed, int in_features, int ou
   return (int)cudaGetLastError();
 }
 
+size_t pct_linear_packed_bytes_bf16(int in_features, int out_features) {
+  if (bad_dims(in_features, out_features) || in_features % Prec<true>::kStepK) return 0;
+  return (size_t)((out_features + kBlockN - 1) / kBlockN) * (in_features / Prec<true>::kStepK) *
+         Prec<true>::kWStep;
+}
+
+int pct_linear_pack_weight_bf16(const float* w, void* packed, int in_features, int out_features,
+                                void* cuda_stream) {
+  if (!w || !packed) return PCT_MSDA_E_NULL_POINTER;
+  if (bad_dims(in_features, out_features) || in_features % Prec<true>::kStepK)
+    return PCT_MSDA_E_BAD_SHAPE;
+  if (misaligned(w) || misaligned(packed)) return PCT_MSDA_E_MISALIGNED;
+  const size_t total = pct_linear_packed_bytes_bf16(in_features, out_features) / 16;
+  const int block = 256;
+  const size_t want = (total + block - 1) / block;
+  pack_weight_bf16_kernel<<<(int)(want < 1184 ? want : 1184), block, 0, (cudaStream_t)cuda_stream>>>(
+      w, reinterpret_cast<uint4*>(packed), out_features, in_features);
+  pct::count_launch();
+  return (int)cudaGetLastError();
+}
+
 int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
                        const float* residual, const float* ln_gamma, const float* ln_beta,
                        float ln_eps, float* y, int rows, int in_features, int out_features,
@@ -1080,8 +1200,9 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
   if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
   if ((flags & PCT_LINEAR_LAYERNORM) && out_features > kBlockN) return PCT_MSDA_E_UNSUPPORTED;
   if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM | PCT_LINEAR_GATE |
-                PCT_LINEAR_ROWMASK))
+                PCT_LINEAR_ROWMASK | PCT_LINEAR_BF16))
     return PCT_MSDA_E_UNSUPPORTED;
+  if ((flags & PCT_LINEAR_BF16) && in_features % Prec<true>::kStepK) return PCT_MSDA_E_BAD_SHAPE;
   if ((flags & PCT_LINEAR_GATE) && (flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM)))
     return PCT_MSDA_E_UNSUPPORTED;
   if ((flags & PCT_LINEAR_ROWMASK) &&
@@ -1111,6 +1232,18 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
   LinearArgs a{x, static_cast<const unsigned char*>(w_packed), bias, residual, ln_gamma, ln_beta,
                y, pre_norm, ln_mean, ln_rstd, ln_eps, rows, in_features, out_features, flags};
   dim3 grid((out_features + kBlockN - 1) / kBlockN, (unsigned)m_tiles);
+  if (flags & PCT_LINEAR_BF16) {
+    static bool bf16_attr[64] = {};
+    if (dev < 0 || dev >= 64 || !bf16_attr[dev]) {
+      e = cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Prec<true>::kSmem);
+      if (e != cudaSuccess) return (int)e;
+      if (dev >= 0 && dev < 64) bf16_attr[dev] = true;
+    }
+    linear_bf16_kernel<<<grid, kThreads, Prec<true>::kSmem, (cudaStream_t)cuda_stream>>>(a);
+    pct::count_launch();
+    return (int)cudaGetLastError();
+  }
   static const int use_pair = [] {
     const char* e = getenv("PCT_LINEAR_PAIR");
     return e ? atoi(e) : 0;

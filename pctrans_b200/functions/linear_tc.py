@@ -9,9 +9,17 @@ fp32-level, not TF32-level), with bias, ReLU and the residual add fused;
 ``linear_residual_layernorm`` also fuses the LayerNorm that follows ``output_proj`` / ``linear2``
 (with autograd it additionally writes what LayerNorm's backward needs).
 
-Scope: CUDA fp32 tensors with in/out features multiples of 16, outside autocast.  Anything else
-(CPU tensors, bf16/autocast, odd sizes) is simply not this kernel's job and goes to
-``torch.nn.functional.linear`` exactly as the reference does; this is the caller's GEMM, not the
+Operand precision (``PRECISION``): the default is the reference's fp32 bar (3xTF32).  Under
+``torch.autocast("cuda", dtype=torch.bfloat16)`` -- or everywhere with ``PRECISION = "bf16"`` -- the
+same kernels run with their operands rounded to bf16 (``PCT_LINEAR_BF16``: one ``kind::f16`` MMA
+instead of three ``kind::tf32`` per K step, fp32 accumulation, fp32 tensors in memory, the same
+fused epilogues), which is what autocast computes for a Linear except that the result is not
+rounded to bf16; forward and input-gradient GEMMs take the bf16 operands, weight gradients stay
+3xTF32.  The mode of a forward call is remembered for its backward.
+
+Scope: CUDA fp32 tensors with in/out features multiples of 16 (32 for the bf16 operands).  Anything
+else (CPU tensors, bf16 tensors, fp16 autocast, odd sizes) is simply not this kernel's job and goes
+to ``torch.nn.functional.linear`` exactly as the reference does; this is the caller's GEMM, not the
 MSDeformAttn op, which never has a fallback.
 """
 from __future__ import annotations
@@ -24,6 +32,8 @@ from torch.autograd.function import once_differentiable
 from .. import _cabi
 
 ENABLED = True            # process-wide switch (tests flip it to compare against torch)
+PRECISION = "auto"        # "fp32": 3xTF32 always (not eligible under autocast); "bf16": bf16 operands
+                          # always; "auto": bf16 operands under bf16 autocast, 3xTF32 otherwise
 _EPOCH = 0                # bumped by invalidate(): every cached packed weight becomes stale
 
 
@@ -45,25 +55,44 @@ def install_invalidation_hooks(module: torch.nn.Module) -> None:
     module.register_load_state_dict_post_hook(lambda mod, incompatible_keys: invalidate())
 
 
-def packed_weight(weight: torch.Tensor, transposed: bool = False) -> torch.Tensor:
-    """Packed 3xTF32 operand of ``weight`` (or of ``weight.T`` for the input gradient), cached
-    until the weight changes in place (optimizer step), is reallocated, or ``invalidate()`` runs."""
+def packed_weight(weight: torch.Tensor, transposed: bool = False, bf16: bool = False) -> torch.Tensor:
+    """Packed operand of ``weight`` (or of ``weight.T`` for the input gradient) -- 3xTF32 pieces or,
+    with ``bf16``, the bf16 rounding -- cached until the weight changes in place (optimizer step),
+    is reallocated, or ``invalidate()`` runs."""
     slot = weight.__dict__.setdefault("_pct_packed", {})
     tag = (weight._version if not weight.is_inference() else -1, weight.data_ptr(), weight.device, _EPOCH)
-    hit = slot.get(transposed)
+    hit = slot.get((transposed, bf16))
     if hit is not None and hit[0] == tag:
         return hit[1]
     w = weight.detach()
-    packed = _cabi.linear_pack_weight(w.t().contiguous() if transposed else w)
-    slot[transposed] = (tag, packed)
+    packed = _cabi.linear_pack_weight(w.t().contiguous() if transposed else w, bf16=bf16)
+    slot[(transposed, bf16)] = (tag, packed)
     return packed
 
 
+def bf16_operands() -> bool:
+    """Whether a tensor-core Linear called now rounds its operands to bf16 (see ``PRECISION``)."""
+    if PRECISION == "bf16":
+        return True
+    return (PRECISION == "auto" and torch.is_autocast_enabled()
+            and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+
+
 def eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
-    return (ENABLED and x.is_cuda and weight.is_cuda and x.dtype == torch.float32
-            and weight.dtype == torch.float32 and not torch.is_autocast_enabled()
+    if not (ENABLED and x.is_cuda and weight.is_cuda and x.dtype == torch.float32
+            and weight.dtype == torch.float32
             and weight.shape[0] % 16 == 0 and weight.shape[1] % 16 == 0 and x.numel() > 0
-            and x.data_ptr() % 16 == 0 and x.storage_offset() % 4 == 0)
+            and x.data_ptr() % 16 == 0 and x.storage_offset() % 4 == 0):
+        return False
+    if bf16_operands():
+        # both GEMM directions run with bf16 operands: K of the forward and of the input gradient
+        return weight.shape[0] % 32 == 0 and weight.shape[1] % 32 == 0
+    return not torch.is_autocast_enabled()
+
+
+def _gemm(x2, weight, n, bf16, transposed=False, **epilogue):
+    """``epilogue(x2 @ weight^T)`` (or ``x2 @ weight`` with ``transposed``: the input gradient)."""
+    return _cabi.linear_forward(x2, packed_weight(weight, transposed, bf16), n, bf16=bf16, **epilogue)
 
 
 class TensorCoreLinearFunction(Function):
@@ -72,13 +101,14 @@ class TensorCoreLinearFunction(Function):
     GEMM's epilogue -- and pass no gradient."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu, row_mask=None):
+    def forward(ctx, x, weight, bias, residual, relu, row_mask=None, bf16=False):
         n, k = weight.shape
         x2 = x.reshape(-1, k).contiguous()
         res2 = residual.reshape(-1, n).contiguous() if residual is not None else None
         b = bias.detach().contiguous() if bias is not None else None
         mask = row_mask.reshape(-1).contiguous() if row_mask is not None else None
-        y = _cabi.linear_forward(x2, packed_weight(weight), n, b, res2, relu=relu, row_mask=mask)
+        y = _gemm(x2, weight, n, bf16, bias=b, residual=res2, relu=relu, row_mask=mask)
+        ctx.bf16 = bf16
         ctx.mask = mask
         ctx.relu = relu
         ctx.has_bias = bias is not None
@@ -100,7 +130,7 @@ class TensorCoreLinearFunction(Function):
         gx = gw = gb = gres = None
         if ctx.needs_input_grad[0]:
             # dX = dY @ W: the same kernel with the transposed weight as its operand
-            gx = _cabi.linear_forward(g, packed_weight(weight, transposed=True), k).view(ctx.x_shape)
+            gx = _gemm(g, weight, k, ctx.bf16, transposed=True).view(ctx.x_shape)
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             # dW = dY^T @ X split over the rows; the bias gradient rides on the same pass over dY
@@ -109,7 +139,7 @@ class TensorCoreLinearFunction(Function):
             gb = g.sum(0)
         if ctx.has_res and ctx.needs_input_grad[3]:
             gres = g.view(*ctx.x_shape[:-1], n)
-        return gx, gw, gb, gres, None, None
+        return gx, gw, gb, gres, None, None, None
 
 
 class LinearResidualLayerNormFunction(Function):
@@ -118,14 +148,15 @@ class LinearResidualLayerNormFunction(Function):
     csrc/layernorm_bwd.cu followed by the tensor-core input / weight gradients."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, ln_weight, ln_bias, eps):
+    def forward(ctx, x, weight, bias, residual, ln_weight, ln_bias, eps, bf16=False):
         n, k = weight.shape
         x2 = x.reshape(-1, k).contiguous()
         res2 = residual.reshape(-1, n).contiguous()
         b = bias.detach().contiguous() if bias is not None else None
-        y, pre, mean, rstd = _cabi.linear_forward(
-            x2, packed_weight(weight), n, b, res2, ln_weight.detach(), ln_bias.detach(), eps,
-            save_for_backward=True)
+        y, pre, mean, rstd = _gemm(
+            x2, weight, n, bf16, bias=b, residual=res2, ln_weight=ln_weight.detach(),
+            ln_bias=ln_bias.detach(), ln_eps=eps, save_for_backward=True)
+        ctx.bf16 = bf16
         ctx.has_bias = bias is not None
         ctx.x_shape = x.shape
         ctx.save_for_backward(x2, weight, pre, mean, rstd, ln_weight, ln_bias)
@@ -140,14 +171,14 @@ class LinearResidualLayerNormFunction(Function):
         g, g_lnw, g_lnb = _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = _cabi.linear_forward(g, packed_weight(weight, transposed=True), k).view(ctx.x_shape)
+            gx = _gemm(g, weight, k, ctx.bf16, transposed=True).view(ctx.x_shape)
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             gw, gb = _wgrad(g, x2, want_b)
         elif want_b:
             gb = g.sum(0)
         gres = g.view(*ctx.x_shape[:-1], n) if ctx.needs_input_grad[3] else None
-        return gx, gw, gb, gres, g_lnw, g_lnb, None
+        return gx, gw, gb, gres, g_lnw, g_lnb, None, None
 
 
 def _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias):
@@ -178,13 +209,14 @@ class FFNFunction(Function):
     and two input-gradient GEMMs whose epilogues carry the ReLU mask and the residual branch."""
 
     @staticmethod
-    def forward(ctx, src, w1, b1, w2, b2, ln_weight, ln_bias, eps):
+    def forward(ctx, src, w1, b1, w2, b2, ln_weight, ln_bias, eps, bf16=False):
         c, f = w1.shape[1], w1.shape[0]
         x2 = src.reshape(-1, c).contiguous()
-        h = _cabi.linear_forward(x2, packed_weight(w1), f, b1.detach(), relu=True)
-        y, pre, mean, rstd = _cabi.linear_forward(
-            h, packed_weight(w2), c, b2.detach(), x2, ln_weight.detach(), ln_bias.detach(), eps,
-            save_for_backward=True)
+        h = _gemm(x2, w1, f, bf16, bias=b1.detach(), relu=True)
+        y, pre, mean, rstd = _gemm(
+            h, w2, c, bf16, bias=b2.detach(), residual=x2, ln_weight=ln_weight.detach(),
+            ln_bias=ln_bias.detach(), ln_eps=eps, save_for_backward=True)
+        ctx.bf16 = bf16
         ctx.src_shape = src.shape
         ctx.save_for_backward(x2, w1, w2, h, pre, mean, rstd, ln_weight, ln_bias)
         return y.view(src.shape)
@@ -198,11 +230,11 @@ class FFNFunction(Function):
         g, g_lnw, g_lnb = _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias)
         gw2, gb2 = _wgrad(g, h, True)
         # d(hidden) = (g @ W2) masked by the ReLU, straight out of the GEMM's epilogue
-        gh = _cabi.linear_forward(g, packed_weight(w2, transposed=True), f, gate=h)
+        gh = _gemm(g, w2, f, ctx.bf16, transposed=True, gate=h)
         gw1, gb1 = _wgrad(gh, x2, True)
         # d(src) = gh @ W1 + g (the residual branch), the add fused as well
-        gx = _cabi.linear_forward(gh, packed_weight(w1, transposed=True), c, residual=g)
-        return gx.view(ctx.src_shape), gw1, gb1, gw2, gb2, g_lnw, g_lnb, None
+        gx = _gemm(gh, w1, c, ctx.bf16, transposed=True, residual=g)
+        return gx.view(ctx.src_shape), gw1, gb1, gw2, gb2, g_lnw, g_lnb, None, None
 
 
 def ffn_block(src, linear1, linear2, norm):
@@ -217,7 +249,7 @@ def ffn_block(src, linear1, linear2, norm):
                                   norm.weight, norm.bias))
     if ok and needs_grad:
         return FFNFunction.apply(src, linear1.weight, linear1.bias, linear2.weight, linear2.bias,
-                                 norm.weight, norm.bias, norm.eps)
+                                 norm.weight, norm.bias, norm.eps, bf16_operands())
     hidden = linear(src, linear1.weight, linear1.bias, relu=True)
     return linear_residual_layernorm(hidden, linear2.weight, linear2.bias, src, norm)
 
@@ -227,7 +259,8 @@ def linear(x, weight, bias=None, residual=None, relu: bool = False, row_mask=Non
     ``row_mask`` (bool, shape of x without its last dim): ``.masked_fill(row_mask[..., None], 0)``
     on the result, done by the GEMM's epilogue on the tensor-core path."""
     if eligible(x, weight) and (row_mask is None or (residual is None and row_mask.is_cuda)):
-        return TensorCoreLinearFunction.apply(x, weight, bias, residual, relu, row_mask)
+        return TensorCoreLinearFunction.apply(x, weight, bias, residual, relu, row_mask,
+                                              bf16_operands())
     y = F.linear(x, weight, bias)
     if residual is not None:
         y = y + residual
@@ -249,8 +282,8 @@ def linear_residual_layernorm(x, weight, bias, residual, norm: torch.nn.LayerNor
         return norm(linear(x, weight, bias, residual=residual))
     if needs_grad:
         return LinearResidualLayerNormFunction.apply(x, weight, bias, residual, norm.weight,
-                                                     norm.bias, norm.eps)
+                                                     norm.bias, norm.eps, bf16_operands())
     x2 = x.reshape(-1, weight.shape[1]).contiguous()
-    y = _cabi.linear_forward(x2, packed_weight(weight), n, bias, residual.reshape(-1, n).contiguous(),
-                             norm.weight, norm.bias, norm.eps)
+    y = _gemm(x2, weight, n, bf16_operands(), bias=bias, residual=residual.reshape(-1, n).contiguous(),
+              ln_weight=norm.weight, ln_bias=norm.bias, ln_eps=norm.eps)
     return y.view(*x.shape[:-1], n)

@@ -78,6 +78,24 @@ def main():
             rec["us_torch_tf32"] = timeit(torch_path)
             torch.backends.cuda.matmul.allow_tf32 = False
             rec["tflops_tc"] = 2.0 * rows * k * n / rec["us_tc"] / 1e6
+            if k % 32 == 0:
+                # bf16 operand precision (PCT_LINEAR_BF16) against torch's bf16 autocast path on the
+                # same fp32 tensors (cast kernels + cuBLAS bf16 GEMM + epilogue kernels), and the
+                # HBM floor of the fp32 traffic (x, residual, y) at the measured 6 542 GB/s
+                wpb = _cabi.linear_pack_weight(w, bf16=True)
+                yb = _cabi.linear_forward(x, wpb, n, b, res, g, be, 1e-5, relu=(mode == "relu"), bf16=True)
+                rec["err_bf16"] = rel(yb, ref)
+                rec["us_bf16"] = timeit(lambda: _cabi.linear_forward(
+                    x, wpb, n, b, res, g, be, 1e-5, relu=(mode == "relu"), out=y, bf16=True))
+
+                def autocast_path():
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return torch_path()
+
+                rec["err_torch_autocast"] = rel(autocast_path().float(), ref)
+                rec["us_torch_autocast"] = timeit(autocast_path)
+                traffic = 4.0 * rows * (k + n + (n if res is not None else 0))
+                rec["us_hbm_floor"] = traffic / 6542.4e9 * 1e6
             gy = torch.randn(rows, n, device=dev)
             rec["err_wgrad"] = rel(_cabi.linear_wgrad(gy, x), gy.double().t() @ x.double())
             rec["us_wgrad_tc"] = timeit(lambda: _cabi.linear_wgrad(gy, x))

@@ -302,9 +302,20 @@ def test_ineligible_inputs_take_the_torch_linear():
     assert torch.equal(linear_tc.linear(x, lin.weight, lin.bias), lin(x))
     lin2 = torch.nn.Linear(32, 32).cuda()
     x2 = torch.randn(9, 32).cuda()
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    with torch.autocast("cuda", dtype=torch.float16):                # fp16 autocast: torch's Linear
         assert not linear_tc.eligible(x2, lin2.weight)
-        assert linear_tc.linear(x2, lin2.weight, lin2.bias).dtype == torch.bfloat16
+        assert linear_tc.linear(x2, lin2.weight, lin2.bias).dtype == torch.float16
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert linear_tc.eligible(x2, lin2.weight)                   # bf16 operands, own kernel
+        assert not linear_tc.eligible(x2.bfloat16(), lin2.weight)    # bf16 tensors: torch's Linear
+        lin3 = torch.nn.Linear(48, 32).cuda()                        # K % 32 != 0: torch's Linear
+        assert not linear_tc.eligible(torch.randn(9, 48).cuda(), lin3.weight)
+        linear_tc.PRECISION = "fp32"                                 # pinned to 3xTF32: not under autocast
+        try:
+            assert not linear_tc.eligible(x2, lin2.weight)
+            assert linear_tc.linear(x2, lin2.weight, lin2.bias).dtype == torch.bfloat16
+        finally:
+            linear_tc.PRECISION = "auto"
 
 
 @pytest.mark.parametrize("mode", ["infer", "train"])
@@ -408,3 +419,127 @@ def test_layernorm_backward_matches_fp64(rows, n):
     gp, gg, gb = _cabi.layernorm_backward(gy, x, mean.float().contiguous(), rstd.float().contiguous(), gamma)
     assert _rel(gp, xd.grad) < 2e-5 and _rel(gg, gd.grad) < 2e-5 and _rel(gb, bd.grad) < 2e-5
     assert not _cabi.layernorm_backward_supported(64) and not _cabi.layernorm_backward_supported(1024)
+
+
+# ---- bf16 operand precision (PCT_LINEAR_BF16) -----------------------------------------------------
+# The kernel rounds x and W to bf16 (nearest even) and accumulates exact products in fp32, so against
+# an fp64 GEMM of the ROUNDED operands it must be as tight as the 3xTF32 kernel is against the
+# unrounded ones (1e-5); against the unrounded fp64 result it sits at bf16 accuracy (BASELINE's
+# 2e-2 bar for bf16).
+
+def _r16(t):
+    return t.bfloat16().double()
+
+
+@pytest.mark.parametrize("rows,k,n", [
+    (1, 32, 16), (127, 32, 48), (128, 256, 256), (129, 256, 192), (1000, 256, 96),
+    (777, 256, 1024), (513, 1024, 256), (300, 128, 288), (5376, 256, 256), (86016, 256, 256)])
+def test_bf16_operand_forward_epilogues_match_fp64_of_rounded_operands(rows, k, n):
+    from pctrans_b200 import _cabi
+    x, w, b, res = _case(rows, k, n, seed=11)
+    wp = _cabi.linear_pack_weight(w, bf16=True)
+    fwd = lambda *a, **kw: _cabi.linear_forward(x, wp, n, *a, bf16=True, **kw)
+    ref = _r16(x) @ _r16(w).t()
+    assert _rel(fwd(), ref) < 1e-5
+    assert _rel(fwd(), x.double() @ w.double().t()) < 2e-2
+    ref_b = ref + b.double()
+    assert _rel(fwd(b), ref_b) < 1e-5
+    assert _rel(fwd(b, relu=True), ref_b.relu()) < 1e-5
+    assert _rel(fwd(b, res), ref_b + res.double()) < 1e-5
+    gate = torch.randn(rows, n, generator=torch.Generator().manual_seed(5)).cuda()
+    assert _rel(fwd(b, gate=gate), ref_b * (gate > 0)) < 1e-5
+    mask = (torch.rand(rows, generator=torch.Generator().manual_seed(6)) < 0.3).cuda()
+    assert _rel(fwd(b, row_mask=mask), ref_b.masked_fill(mask[:, None], 0.0)) < 1e-5
+    if n <= 256:
+        gamma, beta = torch.randn(n).cuda(), torch.randn(n).cuda()
+        ln = F.layer_norm(ref_b + res.double(), (n,), gamma.double(), beta.double(), 1e-5)
+        y, pre, mean, rstd = fwd(b, res, gamma, beta, 1e-5, save_for_backward=True)
+        assert _rel(y, ln) < 1e-5
+        assert _rel(pre, ref_b + res.double()) < 1e-5
+        assert _rel(mean.view(-1), (ref_b + res.double()).mean(1)) < 1e-5
+
+
+def test_bf16_operand_bad_arguments_are_error_codes():
+    from pctrans_b200 import _cabi
+    x, w, _, _ = _case(64, 48, 32)
+    with pytest.raises(_cabi.MSDAError):
+        _cabi.linear_pack_weight(w, bf16=True)            # in_features % 32 != 0
+    wp = _cabi.linear_pack_weight(w)
+    with pytest.raises(_cabi.MSDAError):
+        _cabi.linear_forward(x, wp, 32, bf16=True)
+
+
+def test_bf16_operands_under_autocast_with_gradients():
+    """Under bf16 autocast the Functions run the bf16-operand kernels forward and for the input
+    gradient (exact against fp64 GEMMs of the rounded operands), remember the mode for a backward
+    called outside the autocast region, and keep the weight gradient at fp32 accuracy."""
+    from pctrans_b200 import _cabi
+    from pctrans_b200.functions import linear_tc
+    x, w, b, res = _case(3000, 256, 192, seed=21)
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    b.requires_grad_(True)
+    n0 = _cabi.launch_count()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert linear_tc.bf16_operands()
+        y = linear_tc.linear(x, w, b, relu=True)
+    assert y.dtype == torch.float32 and _cabi.launch_count() > n0
+    ref = (_r16(x) @ _r16(w).t() + b.double()).relu()
+    assert _rel(y, ref) < 1e-5
+    gy = torch.randn_like(y)
+    y.backward(gy)                                        # outside the autocast region
+    g = gy.double() * (ref > 0)
+    assert _rel(x.grad, _r16(g.float()) @ _r16(w)) < 1e-5
+    assert _rel(w.grad, g.t() @ x.double()) < 1e-5       # 3xTF32 weight gradient
+    assert _rel(b.grad, g.sum(0)) < 1e-5
+    # the same call outside autocast is the 3xTF32 kernel
+    y32 = linear_tc.linear(x.detach(), w.detach(), b.detach(), relu=True)
+    assert _rel(y32, (x.double() @ w.double().t() + b.double()).relu()) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["infer", "train"])
+def test_encoder_under_bf16_autocast_runs_own_kernels_and_tracks_fp32(mode):
+    """Six-layer-style encoder under torch.autocast(bfloat16): every Linear is the bf16-operand
+    tensor-core kernel (no cuBLAS: the launch counter advances by the same number of own kernels as
+    in the fp32 run), the output tracks the fp32 run within BASELINE's bf16 bar (2e-2)."""
+    from pctrans_b200 import _cabi, encoder as enc, synth
+    torch.manual_seed(0)
+    pyramid = synth.CVPPP_448
+    model = enc.MSDeformAttnTransformerEncoderOnly(
+        d_model=256, nhead=8, num_encoder_layers=3, dim_feedforward=1024, dropout=0.0,
+        num_feature_levels=len(pyramid)).cuda()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, enc.MSDeformAttn):
+                m.sampling_offsets.weight.normal_(0, 0.02)
+                m.attention_weights.weight.normal_(0, 0.1)
+    srcs = [torch.randn(2, 256, h, w).cuda() for h, w in pyramid]
+    pos = [enc.PositionEmbeddingSine(128, normalize=True)(s) for s in srcs]
+
+    def run(amp):
+        model.zero_grad(set_to_none=True)
+        n0 = _cabi.launch_count()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            if mode == "infer":
+                with torch.no_grad():
+                    out = model(srcs, pos)[0]
+            else:
+                out = model(srcs, pos)[0]
+        grads = None
+        if mode == "train":
+            out.square().mean().backward()
+            grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+        return out.detach(), grads, _cabi.launch_count() - n0
+
+    run(True)                                             # packs the bf16 weights
+    o16, g16, n16 = run(True)
+    run(False)
+    o32, g32, n32 = run(False)
+    assert o16.dtype == torch.float32
+    assert n16 == n32, (n16, n32)                         # same own kernels, none replaced by cuBLAS
+    assert _rel(o16, o32.double()) < 2e-2
+    if mode == "train":
+        for k in ("encoder.layers.0.linear1.weight", "encoder.layers.2.self_attn.value_proj.weight",
+                  "encoder.layers.1.self_attn.output_proj.weight", "encoder.layers.2.norm2.weight"):
+            den = float(g32[k].double().norm())
+            assert float((g16[k].double() - g32[k].double()).norm()) / den < 5e-2, k
