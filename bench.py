@@ -409,11 +409,16 @@ def _encoder(dev, d_model, n_levels, seed=0):
         dim_feedforward=ENCODER_FFN, dropout=0.0, num_feature_levels=n_levels).to(dev)
 
 
-def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dist=None, world=1, rank=0):
+def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dist=None, world=1, rank=0,
+                         bf16_autocast=False):
     """BASELINE configs 4 / 5: the 6-layer deformable-attention encoder (PD/msdeformattn.py:23-161),
     forward + backward of a training step; with `dist` the parameter gradients (4.39 M floats at
     d256) are all-reduced over NCCL on a side stream, overlapped with the tail of the backward and
-    waited for where the optimizer would consume them."""
+    waited for where the optimizer would consume them.  `bf16_autocast`: the forward runs under
+    torch.autocast(bfloat16) -- the Linears' forward / input-gradient GEMMs take bf16 operands on
+    the own tensor-core kernels (PCT_LINEAR_BF16), tensors and the op stay fp32."""
+    import contextlib
+    amp = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if bf16_autocast else contextlib.nullcontext
     from pctrans_b200 import encoder as enc, synth
     pyramid = getattr(synth, PYRAMIDS[pyr_name])
     model = _encoder(dev, d_model, len(pyramid))
@@ -432,7 +437,8 @@ def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dis
 
     def step():
         model.zero_grad(set_to_none=True)
-        mem = model(srcs, pos)[0]
+        with amp():
+            mem = model(srcs, pos)[0]
         mem.float().square().mean().backward()
         if reducer is not None:
             reducer.finish()        # the optimizer step would start here
@@ -464,7 +470,10 @@ def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dis
     torch.cuda.empty_cache()
     return {
         "workload": f"{ENCODER_LAYERS}-layer MSDeformAttn encoder training step (fwd+bwd), {pyr_name} pyramid, "
-                    f"{batch} images/GPU, d_model {d_model}, fp32 (tensor-core 3xTF32 Linears, fused-prologue op)"
+                    f"{batch} images/GPU, d_model {d_model}, "
+                    + ("bf16 autocast (own tensor-core Linears with bf16 operands forward / dgrad, 3xTF32 "
+                       "wgrad, fp32 tensors, fused-prologue op)" if bf16_autocast else
+                       "fp32 (tensor-core 3xTF32 Linears, fused-prologue op)")
                     + (f", NCCL all-reduce of {n_params} param grads in {n_buckets} buckets on a side "
                        "stream, overlapped with the backward" if dist is not None else ""),
         "n_gpus": world, "batch_per_gpu": batch, "global_batch": batch * world, "ms_per_step": ms,
@@ -568,6 +577,8 @@ def sub_records(dev, peak, args):
     guarded("cfg4_bbbc_f32_op_b32", lambda: op_record(dev, peak, "bbbc", 32, 256, "f32"))
     guarded("cfg4_bbbc_bf16_op_b32", lambda: op_record(dev, peak, "bbbc", 32, 256, "bf16"))
     guarded("cfg4_bbbc_encoder6_train_b32", lambda: encoder_train_record(dev, "bbbc", 32))
+    guarded("cfg4_bbbc_encoder6_train_b32_bf16_autocast",
+            lambda: encoder_train_record(dev, "bbbc", 32, bf16_autocast=True))
     guarded("cfg2_decoder_infer_b8", lambda: decoder_infer_record(dev))
     return recs
 
@@ -760,6 +771,11 @@ def main():
                 dev, "cvppp512", args.cfg5_batch, dist=dist, world=world, rank=rank)
         except Exception as e:
             subs["cfg5_encoder6_train"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            subs["cfg5_encoder6_train_bf16_autocast"] = encoder_train_record(
+                dev, "cvppp512", args.cfg5_batch, dist=dist, world=world, rank=rank, bf16_autocast=True)
+        except Exception as e:
+            subs["cfg5_encoder6_train_bf16_autocast"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1:
             subs.update(sub_records(dev, peak, args))
 

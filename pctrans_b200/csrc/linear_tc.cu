@@ -233,6 +233,7 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
                                                 const float* vec_bias, const float* vec_gamma,
                                                 const float* vec_beta, int warp, int lane, int tid,
                                                 int m0, int n0, int n_tile) {
+  const int patch_id = warp, c_lo = 0, c_hi = n_tile;
   const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
   const bool relu = a.flags & PCT_LINEAR_RELU, has_res = a.flags & PCT_LINEAR_RESIDUAL;
   const bool has_gate = a.flags & PCT_LINEAR_GATE;   // `residual` holds the gate tensor instead
@@ -241,7 +242,7 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
   const int my_row = m0 + warp * 32 + lane;
   const bool row_masked = (a.flags & PCT_LINEAR_ROWMASK) && my_row < a.rows &&
                           reinterpret_cast<const unsigned char*>(a.residual)[my_row] != 0;
-  float* patch = reinterpret_cast<float*>(smem) + warp * (32 * kPatchStride);
+  float* patch = reinterpret_cast<float*>(smem) + patch_id * (32 * kPatchStride);
   float* patch_row = patch + lane * kPatchStride;
   const int l_row = lane >> 3, l_c4 = (lane & 7) * 4;
   const size_t warp_off = (size_t)(m0 + warp * 32) * a.N + n0;   // first row of this warp
@@ -320,14 +321,14 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
   };
 
   if (!(a.flags & PCT_LINEAR_LAYERNORM)) {
-    if (has_res || has_gate) fetch_residual(0, min(32, n_tile));
-    for (int c = 0; c < n_tile; c += 32) {
-      const int cw = min(32, n_tile - c);
+    if ((has_res || has_gate) && c_lo < c_hi) fetch_residual(c_lo, min(32, c_hi - c_lo));
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const int cw = min(32, c_hi - c);
       load_acc(c, cw);
       add_bias(c, cw);
       if (has_res) {
         add_residual(cw);
-        if (c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
+        if (c + 32 < c_hi) fetch_residual(c + 32, min(32, c_hi - c - 32));
       }
       if (relu) {
 #pragma unroll
@@ -338,23 +339,25 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
       store_block(a.y, c, cw, has_gate);
-      if (has_gate && c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
+      if (has_gate && c + 32 < c_hi) fetch_residual(c + 32, min(32, c_hi - c - 32));
     }
   } else {
     // pass 1: pre-norm row = acc + bias (+ residual), parked back in TMEM; row sum
     float sum = 0.f;
-    if (has_res) fetch_residual(0, min(32, n_tile));
-    for (int c = 0; c < n_tile; c += 32) {
-      const int cw = min(32, n_tile - c);
+    if (has_res && c_lo < c_hi) fetch_residual(c_lo, min(32, c_hi - c_lo));
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const int cw = min(32, c_hi - c);
       load_acc(c, cw);
       add_bias(c, cw);
       if (has_res) {
         add_residual(cw);
-        if (c + 32 < n_tile) fetch_residual(c + 32, min(32, n_tile - c - 32));
+        if (c + 32 < c_hi) fetch_residual(c + 32, min(32, c_hi - c - 32));
       }
+      float part[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains instead of one of 32 adds
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (i < cw) sum += v[i];
+        if (i < cw) part[i & 3] += v[i];
+      sum += (part[0] + part[1]) + (part[2] + part[3]);
       tmem_st16(t_row + c, v);
       if (cw > 16) tmem_st16(t_row + c + 16, v + 16);
       if (a.pre_norm) store_block(a.pre_norm, c, cw);   // training: LayerNorm's input is saved
@@ -363,18 +366,20 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
     const float mean = sum / (float)a.N;
     // pass 2: centred sum of squares
     float ssq = 0.f;
-    for (int c = 0; c < n_tile; c += 32) {
-      const int cw = min(32, n_tile - c);
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const int cw = min(32, c_hi - c);
       load_acc(c, cw);
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (i < cw) ssq += (v[i] - mean) * (v[i] - mean);
+        if (i < cw) part[i & 3] += (v[i] - mean) * (v[i] - mean);
+      ssq += (part[0] + part[1]) + (part[2] + part[3]);
     }
     const float rstd = rsqrtf(ssq / (float)a.N + a.eps);
     if (a.mean && m0 + tid < a.rows) a.mean[m0 + tid] = mean, a.rstd[m0 + tid] = rstd;
     // pass 3: normalise, scale, shift, store
-    for (int c = 0; c < n_tile; c += 32) {
-      const int cw = min(32, n_tile - c);
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const int cw = min(32, c_hi - c);
       load_acc(c, cw);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
