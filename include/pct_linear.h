@@ -51,7 +51,7 @@ extern "C" {
                                      the result), for callers that trade the reference's fp32 accuracy
                                      (PD/msdeformattn.py:314-320 disables autocast) for speed.
                                      `w_packed` must come from pct_linear_pack_weight_bf16;
-                                     in_features % 32 == 0.  pct_linear_forward(_train) only. */
+                                     in_features % 32 == 0 (forward); also accepted by pct_linear_wgrad_ex. */
 
 /* Constraints everywhere: in_features % 16 == 0, out_features % 16 == 0; x, packed weight, residual,
  * y, pre_norm, grad_y, grad_w, grad_bias 16-byte aligned (bias / LayerNorm vectors: 4-byte). */
@@ -93,6 +93,13 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
  * the bias gradient, the column sums of grad_y, from the same pass over grad_y. */
 int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
                      int in_features, int out_features, void* cuda_stream);
+
+/* The same with option flags: PCT_LINEAR_BF16 rounds both operands (grad_y, x) to bf16 on their way
+ * into the tensor cores (fp32 accumulation, fp32 grad_w / grad_bias; the bias gradient is summed
+ * from the unrounded grad_y) -- what torch.autocast(bfloat16) computes for a Linear's weight
+ * gradient.  flags = 0 is pct_linear_wgrad. */
+int pct_linear_wgrad_ex(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
+                        int in_features, int out_features, unsigned flags, void* cuda_stream);
 
 /* Backward of the LayerNorm fused into pct_linear_forward_train (PD/msdeformattn.py:107-126: the two
  * `norm(residual + linear(x))` blocks of an encoder layer), one pass over the rows:

@@ -34,7 +34,7 @@ EXPORTS = (
 )
 LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_packed_bytes_bf16",
                   "pct_linear_pack_weight_bf16", "pct_linear_forward",
-                  "pct_linear_forward_train", "pct_linear_wgrad", "pct_linear_layernorm_backward")
+                  "pct_linear_forward_train", "pct_linear_wgrad", "pct_linear_wgrad_ex", "pct_linear_layernorm_backward")
 LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM, LINEAR_GATE, LINEAR_ROWMASK = 0x1, 0x2, 0x4, 0x8, 0x10
 LINEAR_BF16 = 0x20
 E_UNSUPPORTED = 1007
@@ -118,6 +118,8 @@ def load():
         lib.pct_linear_pack_weight_bf16.argtypes = [vp, vp, i32, i32, vp]
         lib.pct_linear_wgrad.restype = i32
         lib.pct_linear_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+        lib.pct_linear_wgrad_ex.restype = i32
+        lib.pct_linear_wgrad_ex.argtypes = [vp, vp, vp, vp, i32, i32, i32, u32, vp]
         lib.pct_linear_layernorm_backward.restype = i32
         lib.pct_linear_layernorm_backward.argtypes = [vp] * 8 + [i32, i32, vp]
         lib.pct_linear_forward_train.restype = i32
@@ -370,15 +372,17 @@ def layernorm_backward(grad_y, pre_norm, mean, rstd, gamma):
     return g, gg, gb
 
 
-def linear_wgrad(grad_y, x, with_bias: bool = False):
-    """grad_w (out, in) = grad_y (rows, out)^T @ x (rows, in) on the tensor cores (3xTF32);
-    ``with_bias`` also returns grad_b (out,) = grad_y.sum(0) from the same pass."""
+def linear_wgrad(grad_y, x, with_bias: bool = False, bf16: bool = False):
+    """grad_w (out, in) = grad_y (rows, out)^T @ x (rows, in) on the tensor cores (3xTF32, or with
+    ``bf16`` both operands rounded to bf16); ``with_bias`` also returns grad_b (out,) =
+    grad_y.sum(0) from the same pass."""
     rows, n = grad_y.shape
     k = x.shape[1]
     gw = torch.empty((n, k), dtype=x.dtype, device=x.device)
     gb = torch.empty((n,), dtype=x.dtype, device=x.device) if with_bias else None
     with torch.cuda.device_of(x):
-        check(load().pct_linear_wgrad(grad_y.data_ptr(), x.data_ptr(), gw.data_ptr(),
-                                      gb.data_ptr() if with_bias else None, rows, k, n,
-                                      _stream_ptr(x.device)), "pct_linear_wgrad")
+        check(load().pct_linear_wgrad_ex(grad_y.data_ptr(), x.data_ptr(), gw.data_ptr(),
+                                         gb.data_ptr() if with_bias else None, rows, k, n,
+                                         LINEAR_BF16 if bf16 else 0, _stream_ptr(x.device)),
+              "pct_linear_wgrad")
     return (gw, gb) if with_bias else gw

@@ -28,6 +28,21 @@
 #ifndef PCT_PAIR_STAGES
 #define PCT_PAIR_STAGES 3
 #endif
+#ifndef PCT_LIN_XPF
+#define PCT_LIN_XPF 0   // L2 prefetch of the tile's x rows: 0 none, 1 every CTA, 2 first column tile only
+#endif
+#ifndef PCT_LIN_RPF
+#define PCT_LIN_RPF 1   // L2 prefetch of the tile's residual / gate rows ...
+#endif
+#ifndef PCT_LIN_RPF_LEAD
+#define PCT_LIN_RPF_LEAD 4   // ... this many K steps before the end of the main loop
+#endif
+#ifndef PCT_LIN_AHEAD_BF16
+#define PCT_LIN_AHEAD_BF16 4
+#endif
+#ifndef PCT_LIN_AHEAD_TF32
+#define PCT_LIN_AHEAD_TF32 4
+#endif
 #include <stdlib.h>
 
 namespace pct {
@@ -71,7 +86,7 @@ struct Prec {
   static constexpr int kNumStages = BF16 ? 4 : 2;
   static constexpr int kStage = kPieces * (kABytes + kBBytes);
   static constexpr int kWStep = kPieces * kBBytes;
-  static constexpr int kXAhead = BF16 ? 2 : 3;               // K steps of x in flight per loader thread
+  static constexpr int kXAhead = BF16 ? PCT_LIN_AHEAD_BF16 : PCT_LIN_AHEAD_TF32;   // K steps of x in flight per loader thread
   static constexpr int kSmem = kNumStages * kStage + kBarrierBytes + kVecBytes;
   static_assert(kLoaderWarps * 32 * kPatchStride * 4 <= kNumStages * kStage, "epilogue patches reuse the ring");
   static_assert((3 * kNumStages + 1) * 8 + 4 <= kBarrierBytes, "barriers + TMEM slot");
@@ -400,6 +415,21 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
   }
 }
 
+// Phase timestamps of one CTA per 64 (variant builds with -DPCT_LINEAR_TRACE only; read back with
+// pct_linear_debug_trace): 0 start, 1 set-up done, 2 first K step stored, 3 last K step stored,
+// 4 accumulator complete, 5 epilogue done -- taken by thread 0 (a loader / epilogue thread).
+#ifdef PCT_LINEAR_TRACE
+__device__ long long g_linear_trace[8 * 4096];
+#define PCT_TRACE(slot)                                                                         \
+  do {                                                                                          \
+    const unsigned cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                  \
+    if (threadIdx.x == 0 && (cta_ & 63u) == 0 && (cta_ >> 6) < 4096u)                           \
+      g_linear_trace[(cta_ >> 6) * 8 + (slot)] = clock64();                                     \
+  } while (0)
+#else
+#define PCT_TRACE(slot) do { } while (0)
+#endif
+
 template <bool BF16>
 __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* smem) {
   using P = Prec<BF16>;
@@ -410,6 +440,7 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
   const int lane = tid & 31;
   const int n0 = blockIdx.x * kBlockN;
   const int m0 = blockIdx.y * kBlockM;
+  PCT_TRACE(0);
   const int n_tile = min(kBlockN, a.N - n0);
 
   // barriers, kStages each: stage free (its MMAs are done) | x pieces stored | W pieces landed;
@@ -451,6 +482,7 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
 
   const int n_steps = a.K / P::kStepK;
   const uint32_t smem0 = smem_u32(smem);
+  PCT_TRACE(1);
 
   if (warp == kLoaderWarps) {
     // ---- issuer: one thread feeds the tensor core ----------------------------------------------
@@ -495,30 +527,39 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
     };
     if (lane == 0)
       for (int step = 0; step < kStages && step < n_steps; ++step) fetch_w(step);
-    // pull this tile's activations (whole rows: one contiguous block) and residual rows towards
-    // L2 now, so the loaders' and the epilogue's dependent loads see L2 latency, not DRAM latency
+    // Pull the tile's residual / gate rows towards L2 shortly before the epilogue reads them (a few
+    // K steps before the end of the main loop: issued at the start they compete with the loaders'
+    // first loads, measured).  The rows of x are NOT prefetched: with the loaders' own look-ahead a
+    // whole-tile prefetch only queues in front of the loads that are needed first
+    // (profiles/r02_linear_trace_prefetch.log).
     const int tile_rows = min(kBlockM, a.rows - m0);
-    if (tile_rows > 0) {
-      const size_t x_bytes = (size_t)tile_rows * a.K * 4;
+    auto prefetch_residual = [&]() {
+      if (PCT_LIN_RPF && (a.flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE)))
+        for (int r = lane; r < tile_rows; r += 32)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                           a.residual + (size_t)(m0 + r) * a.N + n0),
+                       "r"((uint32_t)(n_tile * 4))
+                       : "memory");
+    };
+    if (PCT_LIN_XPF == 1 || (PCT_LIN_XPF == 2 && blockIdx.x == 0)) {
+      const size_t x_bytes = (size_t)max(tile_rows, 0) * a.K * 4;
       const char* xp = reinterpret_cast<const char*>(a.x + (size_t)m0 * a.K);
       for (size_t off = (size_t)lane * 32768; off < x_bytes; off += 32 * 32768) {
         const size_t nb = x_bytes - off < 32768 ? x_bytes - off : 32768;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xp + off), "r"((uint32_t)nb)
                      : "memory");
       }
-      if (a.flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE)) {
-        for (int r = lane; r < tile_rows; r += 32)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
-                           a.residual + (size_t)(m0 + r) * a.N + n0),
-                       "r"((uint32_t)(n_tile * 4))
-                       : "memory");
-      }
     }
-    if (lane == 0)
-      for (int step = kStages; step < n_steps; ++step) {
+    const int pf_step = max(kStages, n_steps - PCT_LIN_RPF_LEAD);
+    if (pf_step >= n_steps) prefetch_residual();
+    for (int step = kStages; step < n_steps; ++step) {
+      if (step == pf_step) prefetch_residual();
+      if (lane == 0) {
         mbar_wait(bar_empty + 8 * (step % kStages), ((step / kStages) - 1) & 1);
         fetch_w(step);
       }
+      __syncwarp();
+    }
   } else {
     // ---- loaders: read a K step of x, split it, store the pieces in core-matrix order ---------
     // float4 i of a piece lives at byte 16*i with i = 32*(row/8) + 8*(k/4) + row%8: eight
@@ -574,6 +615,8 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
           __syncwarp();                                                    // one arrival per warp
           if (lane == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_xfull + 8 * s) : "memory");
+          if (step == 0) PCT_TRACE(2);
+          if (step == n_steps - 1) PCT_TRACE(3);
           if (step + kAhead < n_steps) fetch_x(xq[d], step + kAhead);
         }
       }
@@ -583,8 +626,10 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
     // Row domain: this thread owns one row and walks its columns in TMEM order.
     // Line domain: a warp instruction covers 4 rows x 128 contiguous bytes of global memory.
     mbar_wait(bar_done, 0);
+    PCT_TRACE(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     linear_epilogue(a, smem, tmem, vec_bias, vec_gamma, vec_beta, warp, lane, tid, m0, n0, n_tile);
+    PCT_TRACE(5);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -943,8 +988,16 @@ struct WgradArgs {
   int steps_per_split;
 };
 
-__global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const WgradArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+// BF16 (PCT_LINEAR_BF16): both operands rounded to bf16; a K step is then 32 rows (a 16-byte chunk
+// holds 8 consecutive rows of one feature), the shared-memory geometry is the same, one piece
+// per operand and two kind::f16 MMAs per step instead of six kind::tf32.
+template <bool BF16>
+__device__ __forceinline__ void wgrad_body(const WgradArgs& a, unsigned char* smem) {
+  constexpr int kRowsPerChunk = BF16 ? 8 : 4;               // rows (K) in one 16-byte chunk
+  constexpr int kRowsPerStep = 4 * kRowsPerChunk;           // four chunk columns per stage
+  constexpr int kPieces = BF16 ? 1 : 2;
+  constexpr int kWgStage = kPieces * (kWgABytes + kWgBBytes);
+  constexpr int kAheadW = BF16 ? 1 : kWgAhead;              // the same bytes in flight either way
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -952,12 +1005,12 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
   const int k0 = blockIdx.y * kBlockN;                   // dW columns = input features
   const int n_valid = min(kBlockM, a.N - n0);
   const int k_tile = min(kBlockN, a.K - k0);
-  const int total_steps = (a.rows + kBlockK - 1) / kBlockK;
+  const int total_steps = (a.rows + kRowsPerStep - 1) / kRowsPerStep;
   const int step_lo = blockIdx.z * a.steps_per_split;
   const int n_steps = min(a.steps_per_split, total_steps - step_lo);
   if (n_steps <= 0) return;                              // uniform per CTA, before any barrier
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kWgStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kWgStage);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
   const uint32_t bar_empty = smem_u32(bars);
   const uint32_t bar_full = bar_empty + 8 * kStages;
@@ -986,29 +1039,34 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
 
   if (warp == kWgLoaderWarps) {
     if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(k_tile);
+      const uint32_t idesc = BF16 ? make_instr_desc_bf16(k_tile) : make_instr_desc(k_tile);
       for (int step = 0; step < n_steps; ++step) {
         const int s = step % kStages;
         mbar_wait(bar_full + 8 * s, (step / kStages) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem0 + s * kWgStageBytes;
+        const uint32_t sa = smem0 + s * kWgStage;
 #pragma unroll
         for (int ks = 0; ks < kBlockK / kMmaK; ++ks) {
           const uint32_t koff = ks * (kMmaK / 4) * kLbo;
-          const uint64_t d_ahi = make_smem_desc_wg(sa + koff);
-          const uint64_t d_alo = make_smem_desc_wg(sa + kWgABytes + koff);
-          const uint64_t d_bhi = make_smem_desc_wg(sa + 2 * kWgABytes + koff);
-          const uint64_t d_blo = make_smem_desc_wg(sa + 2 * kWgABytes + kWgBBytes + koff);
-          mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);
-          mma_tf32(tmem, d_ahi, d_bhi, idesc, 1u);
-          mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
+          if constexpr (BF16) {
+            mma_bf16(tmem, make_smem_desc_wg(sa + koff), make_smem_desc_wg(sa + kWgABytes + koff), idesc,
+                     (step | ks) != 0);
+          } else {
+            const uint64_t d_ahi = make_smem_desc_wg(sa + koff);
+            const uint64_t d_alo = make_smem_desc_wg(sa + kWgABytes + koff);
+            const uint64_t d_bhi = make_smem_desc_wg(sa + 2 * kWgABytes + koff);
+            const uint64_t d_blo = make_smem_desc_wg(sa + 2 * kWgABytes + kWgBBytes + koff);
+            mma_tf32(tmem, d_alo, d_bhi, idesc, (step | ks) != 0);
+            mma_tf32(tmem, d_ahi, d_bhi, idesc, 1u);
+            mma_tf32(tmem, d_ahi, d_blo, idesc, 1u);
+          }
         }
         mma_commit(bar_empty + 8 * s);
         if (step == n_steps - 1) mma_commit(bar_done);
       }
     }
   } else {
-    // ---- loaders.  Unit = 4 rows x 4 features; unit ids [0, kWgUnitsA) belong to the dY tile,
+    // ---- loaders.  Unit = 4 rows x 4 features (bf16: 8 rows x 4 features); unit ids [0, kWgUnitsA) belong to the dY tile,
     // the rest to the X tile; within a tile, id = featureGroup + groups * rowQuad, so a warp reads
     // 512 contiguous bytes of one row per load.
     const float* src[kWgPer];     // first of the unit's 4 features, row 0 (nullptr: past the edge)
@@ -1028,22 +1086,22 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
       src[j] = !ok ? nullptr : is_a ? a.gy + n0 + 4 * g : a.x + k0 + 4 * g;
       ld[j] = is_a ? a.N : a.K;
       // features 4g..4g+3 are rows (4g+i)%8 of 8-row group (4g)/8; the row quad is the k-chunk
-      dst[j] = (is_a ? 0 : 2 * kWgABytes) + (g >> 1) * kWgSbo + rq[j] * kCoreBytes + (g & 1) * 64;
+      dst[j] = (is_a ? 0 : kPieces * kWgABytes) + (g >> 1) * kWgSbo + rq[j] * kCoreBytes + (g & 1) * 64;
       lo_off[j] = is_a ? kWgABytes : kWgBBytes;
       if (u >= kWgUnits) dst[j] = 0xffffffffu;
     }
-    float4 q[kWgAhead][kWgPer][4];
+    float4 q[kAheadW][kWgPer][kRowsPerChunk];
     // bias gradient = column sums of dY: the threads that load dY blocks keep running sums of
     // their four features (first k tile only, so that every (row, feature) is counted once)
     const bool sum_bias = a.gb != nullptr && blockIdx.y == 0 && tid < kWgUnitsA && src[0] != nullptr;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto fetch = [&](float4 (*d)[4], int step) {
-      const int row0 = (step_lo + step) * kBlockK;
+    auto fetch = [&](float4 (*d)[kRowsPerChunk], int step) {
+      const int row0 = (step_lo + step) * kRowsPerStep;
 #pragma unroll
       for (int j = 0; j < kWgPer; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = row0 + 4 * rq[j] + i;
+        for (int i = 0; i < kRowsPerChunk; ++i) {
+          const int row = row0 + kRowsPerChunk * rq[j] + i;
           d[j][i] = (src[j] && row < a.rows)
                         ? __ldg(reinterpret_cast<const float4*>(src[j] + (size_t)row * ld[j]))
                         : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1057,19 +1115,19 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
       *reinterpret_cast<float4*>(lo) = l;
     };
 #pragma unroll
-    for (int d = 0; d < kWgAhead; ++d)
+    for (int d = 0; d < kAheadW; ++d)
       if (d < n_steps) fetch(q[d], d);
-    for (int step0 = 0; step0 < n_steps; step0 += kWgAhead) {
+    for (int step0 = 0; step0 < n_steps; step0 += kAheadW) {
 #pragma unroll
-      for (int d = 0; d < kWgAhead; ++d) {
+      for (int d = 0; d < kAheadW; ++d) {
         const int step = step0 + d;
         if (step < n_steps) {
           const int s = step % kStages;
           if (step >= kStages) mbar_wait(bar_empty + 8 * s, ((step / kStages) - 1) & 1);
-          unsigned char* stage = smem + s * kWgStageBytes;
+          unsigned char* stage = smem + s * kWgStage;
           if (sum_bias) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < kRowsPerChunk; ++i)
               bsum.x += q[d][0][i].x, bsum.y += q[d][0][i].y, bsum.z += q[d][0][i].z,
                   bsum.w += q[d][0][i].w;
           }
@@ -1079,16 +1137,28 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
               unsigned char* hi = stage + dst[j];
               unsigned char* lo = hi + lo_off[j];
               const float4* r = q[d][j];      // r[i] = features 4g..4g+3 of row i: transpose
-              split_store(hi, lo, r[0].x, r[1].x, r[2].x, r[3].x);
-              split_store(hi + 16, lo + 16, r[0].y, r[1].y, r[2].y, r[3].y);
-              split_store(hi + 32, lo + 32, r[0].z, r[1].z, r[2].z, r[3].z);
-              split_store(hi + 48, lo + 48, r[0].w, r[1].w, r[2].w, r[3].w);
+              if constexpr (BF16) {
+                uint4* c = reinterpret_cast<uint4*>(hi);
+                c[0] = pack_bf16x8(make_float4(r[0].x, r[1].x, r[2].x, r[3].x),
+                                   make_float4(r[4].x, r[5].x, r[6].x, r[7].x));
+                c[1] = pack_bf16x8(make_float4(r[0].y, r[1].y, r[2].y, r[3].y),
+                                   make_float4(r[4].y, r[5].y, r[6].y, r[7].y));
+                c[2] = pack_bf16x8(make_float4(r[0].z, r[1].z, r[2].z, r[3].z),
+                                   make_float4(r[4].z, r[5].z, r[6].z, r[7].z));
+                c[3] = pack_bf16x8(make_float4(r[0].w, r[1].w, r[2].w, r[3].w),
+                                   make_float4(r[4].w, r[5].w, r[6].w, r[7].w));
+              } else {
+                split_store(hi, lo, r[0].x, r[1].x, r[2].x, r[3].x);
+                split_store(hi + 16, lo + 16, r[0].y, r[1].y, r[2].y, r[3].y);
+                split_store(hi + 32, lo + 32, r[0].z, r[1].z, r[2].z, r[3].z);
+                split_store(hi + 48, lo + 48, r[0].w, r[1].w, r[2].w, r[3].w);
+              }
             }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + 8 * s) : "memory");
-          if (step + kWgAhead < n_steps) fetch(q[d], step + kWgAhead);
+          if (step + kAheadW < n_steps) fetch(q[d], step + kAheadW);
         }
       }
     }
@@ -1129,6 +1199,16 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
                  "r"((uint32_t)kBlockN)
                  : "memory");
   }
+}
+
+__global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const WgradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  wgrad_body<false>(a, smem);
+}
+
+__global__ void __launch_bounds__(kWgThreads, 2) wgrad_bf16_kernel(const WgradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  wgrad_body<true>(a, smem);
 }
 
 bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
@@ -1180,6 +1260,13 @@ int pct_linear_pack_weight_bf16(const float* w, void* packed, int in_features, i
   pct::count_launch();
   return (int)cudaGetLastError();
 }
+
+#ifdef PCT_LINEAR_TRACE
+// variant builds only (scripts/linear_trace.py): the phase timestamps of the last launch
+int pct_linear_debug_trace(long long* host_out, int n_values) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_linear_trace, (size_t)n_values * sizeof(long long));
+}
+#endif
 
 int pct_linear_forward(const float* x, const void* w_packed, const float* bias,
                        const float* residual, const float* ln_gamma, const float* ln_beta,
@@ -1285,7 +1372,15 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
 
 int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
                      int in_features, int out_features, void* cuda_stream) {
+  return pct_linear_wgrad_ex(grad_y, x, grad_w, grad_bias, rows, in_features, out_features, 0u,
+                             cuda_stream);
+}
+
+int pct_linear_wgrad_ex(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
+                        int in_features, int out_features, unsigned flags, void* cuda_stream) {
   if (!grad_y || !x || !grad_w) return PCT_MSDA_E_NULL_POINTER;
+  if (flags & ~PCT_LINEAR_BF16) return PCT_MSDA_E_UNSUPPORTED;
+  const bool bf16 = flags & PCT_LINEAR_BF16;
   if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
   if (misaligned(grad_y) || misaligned(x) || misaligned(grad_w) || misaligned(grad_bias))
     return PCT_MSDA_E_MISALIGNED;
@@ -1305,11 +1400,15 @@ int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* 
     e = cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kWgSmemBytes);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kWgSmemBytes);
+    if (e != cudaSuccess) return (int)e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   // split the rows so that about two CTAs per SM are busy; at least 8 K steps per slice
   const int tiles = ((out_features + kBlockM - 1) / kBlockM) * ((in_features + kBlockN - 1) / kBlockN);
-  const int total_steps = (rows + kBlockK - 1) / kBlockK;
+  const int rows_per_step = bf16 ? 32 : kBlockK;
+  const int total_steps = (rows + rows_per_step - 1) / rows_per_step;
   int splits = (2 * 148 + tiles - 1) / tiles;
   if (splits > (total_steps + 7) / 8) splits = (total_steps + 7) / 8;
   if (splits < 1) splits = 1;
@@ -1318,7 +1417,10 @@ int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* 
   splits = (total_steps + steps_per_split - 1) / steps_per_split;
   WgradArgs a{grad_y, x, grad_w, grad_bias, rows, in_features, out_features, steps_per_split};
   dim3 grid((out_features + kBlockM - 1) / kBlockM, (in_features + kBlockN - 1) / kBlockN, splits);
-  wgrad_tf32x3_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
+  if (bf16)
+    wgrad_bf16_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
+  else
+    wgrad_tf32x3_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
   pct::count_launch();
   return (int)cudaGetLastError();
 }

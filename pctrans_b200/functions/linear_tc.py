@@ -14,8 +14,9 @@ Operand precision (``PRECISION``): the default is the reference's fp32 bar (3xTF
 same kernels run with their operands rounded to bf16 (``PCT_LINEAR_BF16``: one ``kind::f16`` MMA
 instead of three ``kind::tf32`` per K step, fp32 accumulation, fp32 tensors in memory, the same
 fused epilogues), which is what autocast computes for a Linear except that the result is not
-rounded to bf16; forward and input-gradient GEMMs take the bf16 operands, weight gradients stay
-3xTF32.  The mode of a forward call is remembered for its backward.
+rounded to bf16; forward, input-gradient and weight-gradient GEMMs take the bf16 operands
+(``BF16_WGRAD = False`` keeps the weight gradients on the 3xTF32 kernel).  The mode of a forward
+call is remembered for its backward.
 
 Scope: CUDA fp32 tensors with in/out features multiples of 16 (32 for the bf16 operands).  Anything
 else (CPU tensors, bf16 tensors, fp16 autocast, odd sizes) is simply not this kernel's job and goes
@@ -34,6 +35,8 @@ from .. import _cabi
 ENABLED = True            # process-wide switch (tests flip it to compare against torch)
 PRECISION = "auto"        # "fp32": 3xTF32 always (not eligible under autocast); "bf16": bf16 operands
                           # always; "auto": bf16 operands under bf16 autocast, 3xTF32 otherwise
+BF16_WGRAD = True         # bf16-operand calls also take their weight gradient with bf16 operands (as
+                          # autocast does); False keeps the weight gradients on the 3xTF32 kernel
 _EPOCH = 0                # bumped by invalidate(): every cached packed weight becomes stale
 
 
@@ -134,7 +137,7 @@ class TensorCoreLinearFunction(Function):
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             # dW = dY^T @ X split over the rows; the bias gradient rides on the same pass over dY
-            gw, gb = _wgrad(g, x2, want_b)
+            gw, gb = _wgrad(g, x2, want_b, ctx.bf16)
         elif want_b:
             gb = g.sum(0)
         if ctx.has_res and ctx.needs_input_grad[3]:
@@ -174,7 +177,7 @@ class LinearResidualLayerNormFunction(Function):
             gx = _gemm(g, weight, k, ctx.bf16, transposed=True).view(ctx.x_shape)
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            gw, gb = _wgrad(g, x2, want_b)
+            gw, gb = _wgrad(g, x2, want_b, ctx.bf16)
         elif want_b:
             gb = g.sum(0)
         gres = g.view(*ctx.x_shape[:-1], n) if ctx.needs_input_grad[3] else None
@@ -192,14 +195,17 @@ def _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias):
                                                      [True, True, True])
 
 
-def _wgrad(g, x2, want_bias):
+def _wgrad(g, x2, want_bias, bf16=False):
     """(dW, db): split-K tensor-core kernel (fp32 reductions, order varies run to run) -- or, under
-    ``torch.use_deterministic_algorithms(True)``, torch's deterministic GEMM and column sum."""
+    ``torch.use_deterministic_algorithms(True)``, torch's deterministic GEMM and column sum.
+    ``bf16``: the forward ran with bf16 operands; so does the weight gradient unless
+    ``BF16_WGRAD`` is off."""
     if torch.are_deterministic_algorithms_enabled():
         return g.t() @ x2, (g.sum(0) if want_bias else None)
+    bf16 = bf16 and BF16_WGRAD
     if want_bias:
-        return _cabi.linear_wgrad(g, x2, with_bias=True)
-    return _cabi.linear_wgrad(g, x2), None
+        return _cabi.linear_wgrad(g, x2, with_bias=True, bf16=bf16)
+    return _cabi.linear_wgrad(g, x2, bf16=bf16), None
 
 
 class FFNFunction(Function):
@@ -228,10 +234,10 @@ class FFNFunction(Function):
         c, f = w1.shape[1], w1.shape[0]
         gy = grad_y.reshape(-1, c).contiguous()
         g, g_lnw, g_lnb = _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias)
-        gw2, gb2 = _wgrad(g, h, True)
+        gw2, gb2 = _wgrad(g, h, True, ctx.bf16)
         # d(hidden) = (g @ W2) masked by the ReLU, straight out of the GEMM's epilogue
         gh = _gemm(g, w2, f, ctx.bf16, transposed=True, gate=h)
-        gw1, gb1 = _wgrad(gh, x2, True)
+        gw1, gb1 = _wgrad(gh, x2, True, ctx.bf16)
         # d(src) = gh @ W1 + g (the residual branch), the add fused as well
         gx = _gemm(gh, w1, c, ctx.bf16, transposed=True, residual=g)
         return gx.view(ctx.src_shape), gw1, gb1, gw2, gb2, g_lnw, g_lnb, None, None

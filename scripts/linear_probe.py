@@ -100,6 +100,9 @@ def main():
             rec["err_wgrad"] = rel(_cabi.linear_wgrad(gy, x), gy.double().t() @ x.double())
             rec["us_wgrad_tc"] = timeit(lambda: _cabi.linear_wgrad(gy, x))
             rec["us_wgrad_torch_fp32"] = timeit(lambda: gy.t() @ x)
+            if k % 32 == 0:
+                rec["err_wgrad_bf16"] = rel(_cabi.linear_wgrad(gy, x, bf16=True), gy.double().t() @ x.double())
+                rec["us_wgrad_bf16"] = timeit(lambda: _cabi.linear_wgrad(gy, x, bf16=True))
         out.append(rec)
         print(json.dumps(rec), flush=True)
 

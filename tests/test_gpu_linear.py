@@ -459,6 +459,23 @@ def test_bf16_operand_forward_epilogues_match_fp64_of_rounded_operands(rows, k, 
         assert _rel(mean.view(-1), (ref_b + res.double()).mean(1)) < 1e-5
 
 
+@pytest.mark.parametrize("rows,k,n", [
+    (1, 32, 16), (100, 32, 48), (1000, 256, 96), (4116, 128, 288), (5376, 256, 1024),
+    (3000, 1024, 256), (86016, 256, 256)])
+def test_bf16_operand_weight_gradient_matches_fp64_of_rounded_operands(rows, k, n):
+    from pctrans_b200 import _cabi
+    x, _, _, _ = _case(rows, k, n, seed=3)
+    gy = torch.randn(rows, n, generator=torch.Generator().manual_seed(4)).cuda()
+    ref = _r16(gy).t() @ _r16(x)
+    gw = _cabi.linear_wgrad(gy, x, bf16=True)
+    assert gw.shape == (n, k)
+    assert _rel(gw, ref) < 1e-5
+    assert _rel(gw, gy.double().t() @ x.double()) < 2e-2
+    gw2, gb = _cabi.linear_wgrad(gy, x, with_bias=True, bf16=True)
+    assert _rel(gw2, ref) < 1e-5
+    assert _rel(gb, gy.double().sum(0)) < 1e-5           # the bias gradient sums the unrounded grad_y
+
+
 def test_bf16_operand_bad_arguments_are_error_codes():
     from pctrans_b200 import _cabi
     x, w, _, _ = _case(64, 48, 32)
@@ -471,8 +488,9 @@ def test_bf16_operand_bad_arguments_are_error_codes():
 
 def test_bf16_operands_under_autocast_with_gradients():
     """Under bf16 autocast the Functions run the bf16-operand kernels forward and for the input
-    gradient (exact against fp64 GEMMs of the rounded operands), remember the mode for a backward
-    called outside the autocast region, and keep the weight gradient at fp32 accuracy."""
+    and weight gradients (exact against fp64 GEMMs of the rounded operands) and remember the mode
+    for a backward called outside the autocast region; BF16_WGRAD = False keeps the weight gradient
+    on the 3xTF32 kernel."""
     from pctrans_b200 import _cabi
     from pctrans_b200.functions import linear_tc
     x, w, b, res = _case(3000, 256, 192, seed=21)
@@ -490,8 +508,17 @@ def test_bf16_operands_under_autocast_with_gradients():
     y.backward(gy)                                        # outside the autocast region
     g = gy.double() * (ref > 0)
     assert _rel(x.grad, _r16(g.float()) @ _r16(w)) < 1e-5
-    assert _rel(w.grad, g.t() @ x.double()) < 1e-5       # 3xTF32 weight gradient
+    assert _rel(w.grad, _r16(g.float()).t() @ _r16(x)) < 1e-5    # bf16-operand weight gradient
+    assert _rel(w.grad, g.t() @ x.double()) < 2e-2
     assert _rel(b.grad, g.sum(0)) < 1e-5
+    linear_tc.BF16_WGRAD = False
+    try:
+        w.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            linear_tc.linear(x, w, b, relu=True).backward(gy)
+        assert _rel(w.grad, g.t() @ x.double()) < 1e-5
+    finally:
+        linear_tc.BF16_WGRAD = True
     # the same call outside autocast is the 3xTF32 kernel
     y32 = linear_tc.linear(x.detach(), w.detach(), b.detach(), relu=True)
     assert _rel(y32, (x.double() @ w.double().t() + b.double()).relu()) < 1e-5
