@@ -53,6 +53,16 @@ extern "C" {
                                      `w_packed` must come from pct_linear_pack_weight_bf16;
                                      in_features % 32 == 0 (forward); also accepted by pct_linear_wgrad_ex. */
 
+/* bf16 tensors in global memory (only together with PCT_LINEAR_BF16; the pointer keeps its
+ * `float*` type in the signature and is read / written as bf16).  Rounding an fp32 tensor to bf16 is
+ * what the bf16 operand path does on load anyway, so storing an intermediate that is only consumed
+ * as a GEMM operand or as a gate in bf16 changes no result -- it halves that tensor's traffic.  Used
+ * for the FFN's hidden activation and its gradient (PD/msdeformattn.py:107-120). */
+#define PCT_LINEAR_X_BF16 0x40u    /* x (rows, in) is bf16                  forward, wgrad_ex */
+#define PCT_LINEAR_Y_BF16 0x80u    /* y (rows, out) is written as bf16      forward (pre_norm stays fp32) */
+#define PCT_LINEAR_RES_BF16 0x100u /* the residual / gate tensor is bf16    forward */
+#define PCT_LINEAR_GY_BF16 0x200u  /* grad_y (rows, out) is bf16            wgrad_ex */
+
 /* Constraints everywhere: in_features % 16 == 0, out_features % 16 == 0; x, packed weight, residual,
  * y, pre_norm, grad_y, grad_w, grad_bias 16-byte aligned (bias / LayerNorm vectors: 4-byte). */
 

@@ -36,7 +36,7 @@ LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_line
                   "pct_linear_pack_weight_bf16", "pct_linear_forward",
                   "pct_linear_forward_train", "pct_linear_wgrad", "pct_linear_wgrad_ex", "pct_linear_layernorm_backward")
 LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM, LINEAR_GATE, LINEAR_ROWMASK = 0x1, 0x2, 0x4, 0x8, 0x10
-LINEAR_BF16 = 0x20
+LINEAR_BF16, LINEAR_X_BF16, LINEAR_Y_BF16, LINEAR_RES_BF16, LINEAR_GY_BF16 = 0x20, 0x40, 0x80, 0x100, 0x200
 E_UNSUPPORTED = 1007
 FLAG_FORCE_GENERIC = 0x1
 FLAG_BF16_ACCUM = 0x8
@@ -315,10 +315,13 @@ def linear_pack_weight(weight, bf16: bool = False):
 
 def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weight=None,
                    ln_bias=None, ln_eps: float = 1e-5, relu: bool = False, out=None,
-                   save_for_backward: bool = False, gate=None, row_mask=None, bf16: bool = False):
+                   save_for_backward: bool = False, gate=None, row_mask=None, bf16: bool = False,
+                   out_dtype=None):
     """y = epilogue(x @ W^T + bias) on the tensor cores (3xTF32); x (rows, in) fp32 contiguous.
     ``bf16``: operands rounded to bf16 on their way into the tensor cores (PCT_LINEAR_BF16);
-    ``w_packed`` must then come from ``linear_pack_weight(w, bf16=True)``.
+    ``w_packed`` must then come from ``linear_pack_weight(w, bf16=True)``.  In that mode ``x``, the
+    residual / gate and (``out_dtype=torch.bfloat16``) the result may be bf16 tensors
+    (PCT_LINEAR_X_BF16 / RES_BF16 / Y_BF16); LayerNorm's saved input and statistics stay fp32.
     With ``save_for_backward`` (LayerNorm epilogue only) returns (y, pre_norm, mean, rstd).
     ``gate`` (rows, out): y is zeroed where gate <= 0 (ReLU backward fused into a dgrad GEMM).
     ``row_mask`` (rows,) bool / uint8: rows with a non-zero entry are written as zeros."""
@@ -338,13 +341,26 @@ def linear_forward(x, w_packed, out_features, bias=None, residual=None, ln_weigh
             raise ValueError("row_mask must be a contiguous (rows,) bool / uint8 tensor")
         residual = row_mask
         flags |= LINEAR_ROWMASK
-    y = out if out is not None else torch.empty((rows, n), dtype=x.dtype, device=x.device)
+    if out is not None:
+        out_dtype = out.dtype
+    elif out_dtype is None:
+        out_dtype = torch.float32
+    low = [t for t in (x, residual if row_mask is None else None) if t is not None and t.dtype == torch.bfloat16]
+    if (low or out_dtype == torch.bfloat16) and not bf16:
+        raise TypeError("bf16 tensors need the bf16 operand kernel (bf16=True)")
+    if x.dtype == torch.bfloat16:
+        flags |= LINEAR_X_BF16
+    if row_mask is None and residual is not None and residual.dtype == torch.bfloat16:
+        flags |= LINEAR_RES_BF16
+    if out_dtype == torch.bfloat16:
+        flags |= LINEAR_Y_BF16
+    y = out if out is not None else torch.empty((rows, n), dtype=out_dtype, device=x.device)
     ptr = lambda t: t.data_ptr() if t is not None else None
     pre = mean = rstd = None
     if save_for_backward:
-        pre = torch.empty_like(y)
-        mean = torch.empty((rows, 1), dtype=x.dtype, device=x.device)
-        rstd = torch.empty((rows, 1), dtype=x.dtype, device=x.device)
+        pre = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+        mean = torch.empty((rows, 1), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((rows, 1), dtype=torch.float32, device=x.device)
     with torch.cuda.device_of(x):
         check(load().pct_linear_forward_train(
             x.data_ptr(), w_packed.data_ptr(), ptr(bias), ptr(residual), ptr(ln_weight),
@@ -378,11 +394,18 @@ def linear_wgrad(grad_y, x, with_bias: bool = False, bf16: bool = False):
     grad_y.sum(0) from the same pass."""
     rows, n = grad_y.shape
     k = x.shape[1]
-    gw = torch.empty((n, k), dtype=x.dtype, device=x.device)
-    gb = torch.empty((n,), dtype=x.dtype, device=x.device) if with_bias else None
+    gw = torch.empty((n, k), dtype=torch.float32, device=x.device)
+    gb = torch.empty((n,), dtype=torch.float32, device=x.device) if with_bias else None
+    flags = LINEAR_BF16 if bf16 else 0
+    if x.dtype == torch.bfloat16:
+        flags |= LINEAR_X_BF16
+    if grad_y.dtype == torch.bfloat16:
+        flags |= LINEAR_GY_BF16
+    if flags & (LINEAR_X_BF16 | LINEAR_GY_BF16) and not bf16:
+        raise TypeError("bf16 tensors need the bf16 operand kernel (bf16=True)")
     with torch.cuda.device_of(x):
         check(load().pct_linear_wgrad_ex(grad_y.data_ptr(), x.data_ptr(), gw.data_ptr(),
                                          gb.data_ptr() if with_bias else None, rows, k, n,
-                                         LINEAR_BF16 if bf16 else 0, _stream_ptr(x.device)),
+                                         flags, _stream_ptr(x.device)),
               "pct_linear_wgrad")
     return (gw, gb) if with_bias else gw

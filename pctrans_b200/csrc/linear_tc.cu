@@ -143,6 +143,20 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float4& a, const float4& b) {
   return r;
 }
 
+// four bf16 (8 bytes, element 0 lowest) -> fp32; exact
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 u) {
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+
+// four fp32 -> four bf16 (round to nearest even), element 0 lowest
+__device__ __forceinline__ uint2 pack_bf16x4(const float4& a) {
+  uint2 r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(a.y), "f"(a.x));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(a.w), "f"(a.z));
+  return r;
+}
+
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -244,6 +258,7 @@ struct LinearArgs {
 // 32w .. 32w+31 of the tile).  Row domain: a thread owns one row and walks its columns in TMEM
 // order.  Line domain: a warp instruction covers 4 rows x 128 contiguous bytes of global memory;
 // the two are bridged by a per-warp 32 x 36-float patch at the start of shared memory.
+template <bool IO16 = false>   // the bf16-in-memory options: own instantiation of the bf16 kernel
 __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned char* smem, uint32_t tmem,
                                                 const float* vec_bias, const float* vec_gamma,
                                                 const float* vec_beta, int warp, int lane, int tid,
@@ -252,6 +267,7 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
   const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
   const bool relu = a.flags & PCT_LINEAR_RELU, has_res = a.flags & PCT_LINEAR_RESIDUAL;
   const bool has_gate = a.flags & PCT_LINEAR_GATE;   // `residual` holds the gate tensor instead
+  const bool res_bf16 = IO16 && (a.flags & PCT_LINEAR_RES_BF16), y_bf16 = IO16 && (a.flags & PCT_LINEAR_Y_BF16);
   // PCT_LINEAR_ROWMASK: `residual` holds one byte per row; rows with a non-zero byte are written
   // as zeros (the masked_fill after value_proj, mod.py:100-101) -- row domain: a thread owns a row
   const int my_row = m0 + warp * 32 + lane;
@@ -271,15 +287,27 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int r = 4 * j + l_row;
-      if (l_c4 < cw && r < rows_left)
-        res[j] = __ldg(
-            reinterpret_cast<const float4*>(a.residual + warp_off + (size_t)r * a.N + c + l_c4));
+      if (l_c4 < cw && r < rows_left) {
+        const size_t at = warp_off + (size_t)r * a.N + c + l_c4;
+        if (res_bf16) {   // raw bits now, widened where they are used: a conversion here would
+                          // wait for every load in turn
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(
+              reinterpret_cast<const unsigned short*>(a.residual) + at));
+          res[j].x = __uint_as_float(u.x), res[j].y = __uint_as_float(u.y);
+        } else {
+          res[j] = __ldg(reinterpret_cast<const float4*>(a.residual + at));
+        }
+      }
     }
+  };
+  auto res_value = [&](int j) {
+    return res_bf16 ? bf16x4_to_float4(make_uint2(__float_as_uint(res[j].x), __float_as_uint(res[j].y)))
+                    : res[j];
   };
   auto add_residual = [&](int cw) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4) = res[j];
+      *reinterpret_cast<float4*>(patch + (4 * j + l_row) * kPatchStride + l_c4) = res_value(j);
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; ++q)
@@ -290,7 +318,8 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
     __syncwarp();
   };
   // v (row domain) -> y block, through the patch
-  auto store_block = [&](float* dst_base, int c, int cw, bool gated = false) {
+  auto store_block = [&](float* dst_base, int c, int cw, bool gated = false, bool as_bf16 = false,
+                         const uint2* gate_raw = nullptr) {
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       if (4 * q < cw)
@@ -305,15 +334,21 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
     if (gated) {   // res[] holds the gate block in exactly this (line-domain) arrangement
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        t[j].x = res[j].x > 0.f ? t[j].x : 0.f, t[j].y = res[j].y > 0.f ? t[j].y : 0.f;
-        t[j].z = res[j].z > 0.f ? t[j].z : 0.f, t[j].w = res[j].w > 0.f ? t[j].w : 0.f;
+        const float4 gt = gate_raw ? bf16x4_to_float4(gate_raw[j]) : res_value(j);
+        t[j].x = gt.x > 0.f ? t[j].x : 0.f, t[j].y = gt.y > 0.f ? t[j].y : 0.f;
+        t[j].z = gt.z > 0.f ? t[j].z : 0.f, t[j].w = gt.w > 0.f ? t[j].w : 0.f;
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int r = 4 * j + l_row;
-      if (l_c4 < cw && r < rows_left)
-        *reinterpret_cast<float4*>(dst_base + warp_off + (size_t)r * a.N + c + l_c4) = t[j];
+      if (l_c4 < cw && r < rows_left) {
+        const size_t at = warp_off + (size_t)r * a.N + c + l_c4;
+        if (as_bf16)
+          *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(dst_base) + at) = pack_bf16x4(t[j]);
+        else
+          *reinterpret_cast<float4*>(dst_base + at) = t[j];
+      }
     }
   };
   auto load_acc = [&](int c, int cw) {
@@ -335,7 +370,42 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
       }
   };
 
-  if (!(a.flags & PCT_LINEAR_LAYERNORM)) {
+  if (has_gate && res_bf16) {
+    // bf16 gate (the FFN's hidden activation, dgrad of linear2): raw gate blocks are fetched TWO
+    // blocks ahead into two small register buffers (8 x 8 bytes each) -- one block ahead leaves
+    // most of the load latency exposed, and this epilogue reads as many bytes as it writes
+    uint2 g0[8], g1[8];
+    auto fetch_gate = [&](uint2* dst, int c) {
+      const int cw = min(32, c_hi - c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = 4 * j + l_row;
+        if (l_c4 < cw && r < rows_left)
+          dst[j] = __ldg(reinterpret_cast<const uint2*>(
+              reinterpret_cast<const unsigned short*>(a.residual) + warp_off + (size_t)r * a.N + c + l_c4));
+      }
+    };
+    auto block = [&](int c, const uint2* gate) {
+      const int cw = min(32, c_hi - c);
+      load_acc(c, cw);
+      add_bias(c, cw);
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      store_block(a.y, c, cw, true, y_bf16, gate);
+    };
+    if (c_lo < c_hi) fetch_gate(g0, c_lo);
+    if (c_lo + 32 < c_hi) fetch_gate(g1, c_lo + 32);
+    for (int c = c_lo; c < c_hi; c += 64) {
+      block(c, g0);
+      if (c + 64 < c_hi) fetch_gate(g0, c + 64);
+      if (c + 32 < c_hi) {
+        block(c + 32, g1);
+        if (c + 96 < c_hi) fetch_gate(g1, c + 96);
+      }
+    }
+  } else if (!(a.flags & PCT_LINEAR_LAYERNORM)) {
     if ((has_res || has_gate) && c_lo < c_hi) fetch_residual(c_lo, min(32, c_hi - c_lo));
     for (int c = c_lo; c < c_hi; c += 32) {
       const int cw = min(32, c_hi - c);
@@ -353,7 +423,7 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      store_block(a.y, c, cw, has_gate);
+      store_block(a.y, c, cw, has_gate, y_bf16);
       if (has_gate && c + 32 < c_hi) fetch_residual(c + 32, min(32, c_hi - c - 32));
     }
   } else {
@@ -410,7 +480,7 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
       }
-      store_block(a.y, c, cw);
+      store_block(a.y, c, cw, false, y_bf16);
     }
   }
 }
@@ -430,8 +500,9 @@ __device__ long long g_linear_trace[8 * 4096];
 #define PCT_TRACE(slot) do { } while (0)
 #endif
 
-template <bool BF16>
+template <bool BF16, bool IO16 = false>
 __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* smem) {
+  static_assert(BF16 || !IO16, "bf16 tensors only with the bf16 kernel");
   using P = Prec<BF16>;
   constexpr int kStages = P::kNumStages, kStageBytes = P::kStage, kWStepBytes = P::kWStep;
   constexpr int kAhead = P::kXAhead;
@@ -534,11 +605,13 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
     // (profiles/r02_linear_trace_prefetch.log).
     const int tile_rows = min(kBlockM, a.rows - m0);
     auto prefetch_residual = [&]() {
+      const int esz = (a.flags & PCT_LINEAR_RES_BF16) ? 2 : 4;
       if (PCT_LIN_RPF && (a.flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE)))
         for (int r = lane; r < tile_rows; r += 32)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
-                           a.residual + (size_t)(m0 + r) * a.N + n0),
-                       "r"((uint32_t)(n_tile * 4))
+                           reinterpret_cast<const char*>(a.residual) +
+                           ((size_t)(m0 + r) * a.N + n0) * esz),
+                       "r"((uint32_t)(n_tile * esz))
                        : "memory");
     };
     if (PCT_LIN_XPF == 1 || (PCT_LIN_XPF == 2 && blockIdx.x == 0)) {
@@ -566,24 +639,36 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
     // consecutive threads fill one core matrix and a warp reads 8 rows x 64 contiguous bytes.
     const int r8 = tid & 7, kc = (tid >> 3) & 3, rg = tid >> 5;
     constexpr int kPerThread = kBlockM * kBlockK / 4 / (kLoaderWarps * 32);
-    const float* xrow[kPerThread];
+    // PCT_LINEAR_X_BF16 (bf16 kernel only): x is already bf16 in global memory -- the thread's
+    // 16-byte chunk of a stage is copied as it is (half the bytes, no conversion)
+    const bool xb = IO16 && (a.flags & PCT_LINEAR_X_BF16);
+    const int x_esz = xb ? 2 : 4;
+    const char* xrow[kPerThread];
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
       const int row = m0 + (rg + kLoaderWarps * j) * 8 + r8;
-      xrow[j] = row < a.rows ? a.x + (size_t)row * a.K + kc * (P::kStepK / 4) : nullptr;
+      xrow[j] = row < a.rows ? reinterpret_cast<const char*>(a.x) +
+                                   ((size_t)row * a.K + kc * (P::kStepK / 4)) * x_esz
+                             : nullptr;
     }
     // kAhead K steps in flight: the loads are DRAM-latency bound.  A thread's share of a row is one
     // 16-byte chunk of the stage: 4 floats (3xTF32) or 8 floats rounded to bf16
     constexpr int kQ = BF16 ? 2 : 1;
     float4 xq[kAhead][kPerThread * kQ];
     auto fetch_x = [&](float4* dst, int step) {
+      const size_t at = (size_t)step * P::kStepK * x_esz;
 #pragma unroll
-      for (int j = 0; j < kPerThread; ++j)
+      for (int j = 0; j < kPerThread; ++j) {
+        if (xb) {
+          dst[j * kQ] = xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + at))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
 #pragma unroll
-        for (int h = 0; h < kQ; ++h)
-          dst[j * kQ + h] =
-              xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + step * P::kStepK) + h)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int h = 0; h < kQ; ++h)
+            dst[j * kQ + h] = xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + at) + h)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
     };
 #pragma unroll
     for (int d = 0; d < kAhead; ++d)
@@ -600,8 +685,11 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
 #pragma unroll
           for (int j = 0; j < kPerThread; ++j) {
             if constexpr (BF16) {
-              reinterpret_cast<uint4*>(a_hi)[tid + kLoaderWarps * 32 * j] =
-                  pack_bf16x8(xq[d][2 * j], xq[d][2 * j + 1]);
+              if (xb)
+                a_hi[tid + kLoaderWarps * 32 * j] = xq[d][2 * j];
+              else
+                reinterpret_cast<uint4*>(a_hi)[tid + kLoaderWarps * 32 * j] =
+                    pack_bf16x8(xq[d][2 * j], xq[d][2 * j + 1]);
             } else {
               const float4 x4 = xq[d][j];
               float4 h, l;
@@ -628,7 +716,7 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
     mbar_wait(bar_done, 0);
     PCT_TRACE(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    linear_epilogue(a, smem, tmem, vec_bias, vec_gamma, vec_beta, warp, lane, tid, m0, n0, n_tile);
+    linear_epilogue<IO16>(a, smem, tmem, vec_bias, vec_gamma, vec_beta, warp, lane, tid, m0, n0, n_tile);
     PCT_TRACE(5);
   }
 
@@ -650,6 +738,12 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
 __global__ void __launch_bounds__(kThreads, 2) linear_bf16_kernel(const LinearArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   linear_body<true>(a, smem);
+}
+
+// ... and with some of x / y / residual bf16 in global memory (PCT_LINEAR_X_BF16 / Y_BF16 / RES_BF16)
+__global__ void __launch_bounds__(kThreads, 2) linear_bf16_io16_kernel(const LinearArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  linear_body<true, true>(a, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -980,6 +1074,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_wg(uint32_t saddr) {
 }
 
 struct WgradArgs {
+  unsigned flags;    // PCT_LINEAR_X_BF16 / PCT_LINEAR_GY_BF16: that operand is bf16 in global memory
   const float* gy;   // (rows, N)
   const float* x;    // (rows, K)
   float* gw;         // (N, K), zero on entry
@@ -991,8 +1086,12 @@ struct WgradArgs {
 // BF16 (PCT_LINEAR_BF16): both operands rounded to bf16; a K step is then 32 rows (a 16-byte chunk
 // holds 8 consecutive rows of one feature), the shared-memory geometry is the same, one piece
 // per operand and two kind::f16 MMAs per step instead of six kind::tf32.
-template <bool BF16>
+// GY16 / X16 (bf16 kernel only): that operand is bf16 in global memory (PCT_LINEAR_GY_BF16 /
+// PCT_LINEAR_X_BF16): its units load four bf16 (8 bytes) per row, kept raw until the step is
+// stored (a conversion next to the load would wait for every load in turn) and widened exactly.
+template <bool BF16, bool GY16 = false, bool X16 = false>
 __device__ __forceinline__ void wgrad_body(const WgradArgs& a, unsigned char* smem) {
+  static_assert(BF16 || !(GY16 || X16), "bf16 tensors only with the bf16 kernel");
   constexpr int kRowsPerChunk = BF16 ? 8 : 4;               // rows (K) in one 16-byte chunk
   constexpr int kRowsPerStep = 4 * kRowsPerChunk;           // four chunk columns per stage
   constexpr int kPieces = BF16 ? 1 : 2;
@@ -1069,7 +1168,8 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& a, unsigned char* sm
     // ---- loaders.  Unit = 4 rows x 4 features (bf16: 8 rows x 4 features); unit ids [0, kWgUnitsA) belong to the dY tile,
     // the rest to the X tile; within a tile, id = featureGroup + groups * rowQuad, so a warp reads
     // 512 contiguous bytes of one row per load.
-    const float* src[kWgPer];     // first of the unit's 4 features, row 0 (nullptr: past the edge)
+    const char* src[kWgPer];      // first of the unit's 4 features, row 0 (nullptr: past the edge)
+    bool s16[kWgPer];             // the unit's operand is bf16 in global memory
     int rq[kWgPer];               // row quad within the step
     uint32_t dst[kWgPer];         // byte offset of the unit's first chunk within the hi piece
     uint32_t lo_off[kWgPer];      // distance from the hi piece to the lo piece
@@ -1083,8 +1183,12 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& a, unsigned char* sm
       const int g = v % groups;
       rq[j] = v / groups;
       const bool ok = u < kWgUnits && 4 * g < (is_a ? n_valid : k_tile);
-      src[j] = !ok ? nullptr : is_a ? a.gy + n0 + 4 * g : a.x + k0 + 4 * g;
-      ld[j] = is_a ? a.N : a.K;
+      s16[j] = is_a ? GY16 : X16;
+      const int esz = s16[j] ? 2 : 4;
+      src[j] = !ok ? nullptr
+                   : is_a ? reinterpret_cast<const char*>(a.gy) + (size_t)(n0 + 4 * g) * esz
+                          : reinterpret_cast<const char*>(a.x) + (size_t)(k0 + 4 * g) * esz;
+      ld[j] = (is_a ? a.N : a.K) * esz;      // row pitch in bytes
       // features 4g..4g+3 are rows (4g+i)%8 of 8-row group (4g)/8; the row quad is the k-chunk
       dst[j] = (is_a ? 0 : kPieces * kWgABytes) + (g >> 1) * kWgSbo + rq[j] * kCoreBytes + (g & 1) * 64;
       lo_off[j] = is_a ? kWgABytes : kWgBBytes;
@@ -1102,9 +1206,15 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& a, unsigned char* sm
 #pragma unroll
         for (int i = 0; i < kRowsPerChunk; ++i) {
           const int row = row0 + kRowsPerChunk * rq[j] + i;
-          d[j][i] = (src[j] && row < a.rows)
-                        ? __ldg(reinterpret_cast<const float4*>(src[j] + (size_t)row * ld[j]))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool in = src[j] && row < a.rows;
+          if ((GY16 || X16) && s16[j]) {
+            const uint2 u = in ? __ldg(reinterpret_cast<const uint2*>(src[j] + (size_t)row * ld[j]))
+                               : make_uint2(0u, 0u);
+            d[j][i] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), 0.f, 0.f);
+          } else {
+            d[j][i] = in ? __ldg(reinterpret_cast<const float4*>(src[j] + (size_t)row * ld[j]))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
     };
     auto split_store = [&](unsigned char* hi, unsigned char* lo, float x0, float x1, float x2, float x3) {
@@ -1125,6 +1235,16 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& a, unsigned char* sm
           const int s = step % kStages;
           if (step >= kStages) mbar_wait(bar_empty + 8 * s, ((step / kStages) - 1) & 1);
           unsigned char* stage = smem + s * kWgStage;
+          if constexpr (GY16 || X16) {
+#pragma unroll
+            for (int j = 0; j < kWgPer; ++j)
+              if (s16[j]) {
+#pragma unroll
+                for (int i = 0; i < kRowsPerChunk; ++i)
+                  q[d][j][i] = bf16x4_to_float4(
+                      make_uint2(__float_as_uint(q[d][j][i].x), __float_as_uint(q[d][j][i].y)));
+              }
+          }
           if (sum_bias) {
 #pragma unroll
             for (int i = 0; i < kRowsPerChunk; ++i)
@@ -1206,9 +1326,10 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_tf32x3_kernel(const Wgrad
   wgrad_body<false>(a, smem);
 }
 
+template <bool GY16, bool X16>
 __global__ void __launch_bounds__(kWgThreads, 2) wgrad_bf16_kernel(const WgradArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  wgrad_body<true>(a, smem);
+  wgrad_body<true, GY16, X16>(a, smem);
 }
 
 bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
@@ -1292,7 +1413,13 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
   if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
   if ((flags & PCT_LINEAR_LAYERNORM) && out_features > kBlockN) return PCT_MSDA_E_UNSUPPORTED;
   if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM | PCT_LINEAR_GATE |
-                PCT_LINEAR_ROWMASK | PCT_LINEAR_BF16))
+                PCT_LINEAR_ROWMASK | PCT_LINEAR_BF16 | PCT_LINEAR_X_BF16 | PCT_LINEAR_Y_BF16 |
+                PCT_LINEAR_RES_BF16))
+    return PCT_MSDA_E_UNSUPPORTED;
+  // bf16 tensors in global memory only with the bf16 kernel; a bf16 residual only where one is read
+  if ((flags & (PCT_LINEAR_X_BF16 | PCT_LINEAR_Y_BF16 | PCT_LINEAR_RES_BF16)) && !(flags & PCT_LINEAR_BF16))
+    return PCT_MSDA_E_UNSUPPORTED;
+  if ((flags & PCT_LINEAR_RES_BF16) && !(flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_GATE)))
     return PCT_MSDA_E_UNSUPPORTED;
   if ((flags & PCT_LINEAR_BF16) && in_features % Prec<true>::kStepK) return PCT_MSDA_E_BAD_SHAPE;
   if ((flags & PCT_LINEAR_GATE) && (flags & (PCT_LINEAR_RESIDUAL | PCT_LINEAR_LAYERNORM)))
@@ -1330,9 +1457,15 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
       e = cudaFuncSetAttribute(linear_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Prec<true>::kSmem);
       if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(linear_bf16_io16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Prec<true>::kSmem);
+      if (e != cudaSuccess) return (int)e;
       if (dev >= 0 && dev < 64) bf16_attr[dev] = true;
     }
-    linear_bf16_kernel<<<grid, kThreads, Prec<true>::kSmem, (cudaStream_t)cuda_stream>>>(a);
+    if (flags & (PCT_LINEAR_X_BF16 | PCT_LINEAR_Y_BF16 | PCT_LINEAR_RES_BF16))
+      linear_bf16_io16_kernel<<<grid, kThreads, Prec<true>::kSmem, (cudaStream_t)cuda_stream>>>(a);
+    else
+      linear_bf16_kernel<<<grid, kThreads, Prec<true>::kSmem, (cudaStream_t)cuda_stream>>>(a);
     pct::count_launch();
     return (int)cudaGetLastError();
   }
@@ -1379,8 +1512,9 @@ int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* 
 int pct_linear_wgrad_ex(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
                         int in_features, int out_features, unsigned flags, void* cuda_stream) {
   if (!grad_y || !x || !grad_w) return PCT_MSDA_E_NULL_POINTER;
-  if (flags & ~PCT_LINEAR_BF16) return PCT_MSDA_E_UNSUPPORTED;
+  if (flags & ~(PCT_LINEAR_BF16 | PCT_LINEAR_X_BF16 | PCT_LINEAR_GY_BF16)) return PCT_MSDA_E_UNSUPPORTED;
   const bool bf16 = flags & PCT_LINEAR_BF16;
+  if (!bf16 && (flags & (PCT_LINEAR_X_BF16 | PCT_LINEAR_GY_BF16))) return PCT_MSDA_E_UNSUPPORTED;
   if (rows < 1 || bad_dims(in_features, out_features)) return PCT_MSDA_E_BAD_SHAPE;
   if (misaligned(grad_y) || misaligned(x) || misaligned(grad_w) || misaligned(grad_bias))
     return PCT_MSDA_E_MISALIGNED;
@@ -1400,9 +1534,11 @@ int pct_linear_wgrad_ex(const float* grad_y, const float* x, float* grad_w, floa
     e = cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              kWgSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             kWgSmemBytes);
-    if (e != cudaSuccess) return (int)e;
+    for (auto* k : {wgrad_bf16_kernel<false, false>, wgrad_bf16_kernel<true, false>,
+                    wgrad_bf16_kernel<false, true>, wgrad_bf16_kernel<true, true>}) {
+      e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+    }
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   // split the rows so that about two CTAs per SM are busy; at least 8 K steps per slice
@@ -1415,11 +1551,14 @@ int pct_linear_wgrad_ex(const float* grad_y, const float* x, float* grad_w, floa
   if (splits > 65535) splits = 65535;
   const int steps_per_split = (total_steps + splits - 1) / splits;
   splits = (total_steps + steps_per_split - 1) / steps_per_split;
-  WgradArgs a{grad_y, x, grad_w, grad_bias, rows, in_features, out_features, steps_per_split};
+  WgradArgs a{flags, grad_y, x, grad_w, grad_bias, rows, in_features, out_features, steps_per_split};
   dim3 grid((out_features + kBlockM - 1) / kBlockM, (in_features + kBlockN - 1) / kBlockN, splits);
-  if (bf16)
-    wgrad_bf16_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
-  else
+  if (bf16) {
+    auto* k = (flags & PCT_LINEAR_GY_BF16)
+                  ? ((flags & PCT_LINEAR_X_BF16) ? wgrad_bf16_kernel<true, true> : wgrad_bf16_kernel<true, false>)
+                  : ((flags & PCT_LINEAR_X_BF16) ? wgrad_bf16_kernel<false, true> : wgrad_bf16_kernel<false, false>);
+    k<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
+  } else
     wgrad_tf32x3_kernel<<<grid, kWgThreads, kWgSmemBytes, st>>>(a);
   pct::count_launch();
   return (int)cudaGetLastError();

@@ -35,6 +35,7 @@ from .. import _cabi
 ENABLED = True            # process-wide switch (tests flip it to compare against torch)
 PRECISION = "auto"        # "fp32": 3xTF32 always (not eligible under autocast); "bf16": bf16 operands
                           # always; "auto": bf16 operands under bf16 autocast, 3xTF32 otherwise
+BF16_HIDDEN = True        # bf16-operand FFN blocks keep the hidden activation and its gradient in bf16
 BF16_WGRAD = True         # bf16-operand calls also take their weight gradient with bf16 operands (as
                           # autocast does); False keeps the weight gradients on the 3xTF32 kernel
 _EPOCH = 0                # bumped by invalidate(): every cached packed weight becomes stale
@@ -77,7 +78,7 @@ def bf16_operands() -> bool:
     """Whether a tensor-core Linear called now rounds its operands to bf16 (see ``PRECISION``)."""
     if PRECISION == "bf16":
         return True
-    return (PRECISION == "auto" and torch.is_autocast_enabled()
+    return (PRECISION == "auto" and torch.is_autocast_enabled("cuda")
             and torch.get_autocast_dtype("cuda") == torch.bfloat16)
 
 
@@ -90,7 +91,7 @@ def eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
     if bf16_operands():
         # both GEMM directions run with bf16 operands: K of the forward and of the input gradient
         return weight.shape[0] % 32 == 0 and weight.shape[1] % 32 == 0
-    return not torch.is_autocast_enabled()
+    return not torch.is_autocast_enabled("cuda")
 
 
 def _gemm(x2, weight, n, bf16, transposed=False, **epilogue):
@@ -200,9 +201,11 @@ def _wgrad(g, x2, want_bias, bf16=False):
     ``torch.use_deterministic_algorithms(True)``, torch's deterministic GEMM and column sum.
     ``bf16``: the forward ran with bf16 operands; so does the weight gradient unless
     ``BF16_WGRAD`` is off."""
+    bf16 = bf16 and BF16_WGRAD and not torch.are_deterministic_algorithms_enabled()
+    if not bf16:   # the 3xTF32 kernel and torch read fp32 (a bf16 hidden activation is widened)
+        g, x2 = g.float(), x2.float()
     if torch.are_deterministic_algorithms_enabled():
         return g.t() @ x2, (g.sum(0) if want_bias else None)
-    bf16 = bf16 and BF16_WGRAD
     if want_bias:
         return _cabi.linear_wgrad(g, x2, with_bias=True, bf16=bf16)
     return _cabi.linear_wgrad(g, x2, bf16=bf16), None
@@ -218,7 +221,11 @@ class FFNFunction(Function):
     def forward(ctx, src, w1, b1, w2, b2, ln_weight, ln_bias, eps, bf16=False):
         c, f = w1.shape[1], w1.shape[0]
         x2 = src.reshape(-1, c).contiguous()
-        h = _gemm(x2, w1, f, bf16, bias=b1.detach(), relu=True)
+        # bf16 operands: the hidden activation is only ever a GEMM operand or a gate, both of which
+        # round it to bf16 anyway -- it is stored as bf16 (half the traffic of the block's largest
+        # tensor, no result changes); likewise its gradient in the backward
+        low = torch.bfloat16 if (bf16 and BF16_HIDDEN) else None
+        h = _gemm(x2, w1, f, bf16, bias=b1.detach(), relu=True, out_dtype=low)
         y, pre, mean, rstd = _gemm(
             h, w2, c, bf16, bias=b2.detach(), residual=x2, ln_weight=ln_weight.detach(),
             ln_bias=ln_bias.detach(), ln_eps=eps, save_for_backward=True)
@@ -236,7 +243,7 @@ class FFNFunction(Function):
         g, g_lnw, g_lnb = _layernorm_backward(gy, pre, mean, rstd, ln_weight, ln_bias)
         gw2, gb2 = _wgrad(g, h, True, ctx.bf16)
         # d(hidden) = (g @ W2) masked by the ReLU, straight out of the GEMM's epilogue
-        gh = _gemm(g, w2, f, ctx.bf16, transposed=True, gate=h)
+        gh = _gemm(g, w2, f, ctx.bf16, transposed=True, gate=h, out_dtype=h.dtype)
         gw1, gb1 = _wgrad(gh, x2, True, ctx.bf16)
         # d(src) = gh @ W1 + g (the residual branch), the add fused as well
         gx = _gemm(gh, w1, c, ctx.bf16, transposed=True, residual=g)
@@ -256,6 +263,15 @@ def ffn_block(src, linear1, linear2, norm):
     if ok and needs_grad:
         return FFNFunction.apply(src, linear1.weight, linear1.bias, linear2.weight, linear2.bias,
                                  norm.weight, norm.bias, norm.eps, bf16_operands())
+    if ok and bf16_operands() and BF16_HIDDEN:
+        # inference with bf16 operands: the same two kernels with the hidden activation kept in bf16
+        c, f = linear1.weight.shape[1], linear1.weight.shape[0]
+        x2 = src.reshape(-1, c).contiguous()
+        h = _gemm(x2, linear1.weight, f, True, bias=linear1.bias.detach(), relu=True,
+                  out_dtype=torch.bfloat16)
+        y = _gemm(h, linear2.weight, c, True, bias=linear2.bias.detach(), residual=x2,
+                  ln_weight=norm.weight.detach(), ln_bias=norm.bias.detach(), ln_eps=norm.eps)
+        return y.view(src.shape)
     hidden = linear(src, linear1.weight, linear1.bias, relu=True)
     return linear_residual_layernorm(hidden, linear2.weight, linear2.bias, src, norm)
 

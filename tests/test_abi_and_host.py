@@ -51,6 +51,10 @@ def test_abi_scalar_entry_points_without_gpu():
     assert lib.pct_linear_packed_bytes(256, 256) == 16 * 32768
     assert lib.pct_linear_packed_bytes(256, 288) == 2 * 16 * 32768
     assert lib.pct_linear_packed_bytes(250, 256) == 0 and lib.pct_linear_packed_bytes(256, 8) == 0
+    # bf16 operands: 32-element K steps x one 16 KB piece
+    assert lib.pct_linear_packed_bytes_bf16(256, 256) == 8 * 16384
+    assert lib.pct_linear_packed_bytes_bf16(1024, 288) == 2 * 32 * 16384
+    assert lib.pct_linear_packed_bytes_bf16(48, 256) == 0      # in_features % 32 != 0
     assert _cabi.kernel_family(32, 33, 4, torch.float32) == 0   # L*P > 128 sample table
     # argument validation happens before any CUDA call
     assert lib.pct_msda_forward(None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 7, None) == 1003
@@ -129,3 +133,32 @@ def test_synth_shapes_and_reference_points():
     value, sh, lsi, loc, attn = synth.make_inputs(2, synth.CVPPP_448, M=8, D=16, P=4, seed=0)
     assert value.shape == (2, 4116, 8, 16) and loc.shape == (2, 4116, 8, 3, 4, 2)
     assert torch.allclose(attn.sum((-1, -2)), torch.ones(2, 4116, 8), atol=1e-5)
+
+
+def test_linear_precision_policy_without_gpu():
+    """Host logic of functions/linear_tc.py: which operand precision a tensor-core Linear would
+    take (PRECISION, torch.autocast) and that CPU tensors are never eligible (they go to
+    torch.nn.functional.linear as in the reference)."""
+    from pctrans_b200.functions import linear_tc
+    assert linear_tc.PRECISION == "auto" and linear_tc.BF16_WGRAD
+    assert not linear_tc.bf16_operands()
+    if torch.cuda.is_available():       # without CUDA torch disables "cuda" autocast regions
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            assert linear_tc.bf16_operands()
+    with torch.autocast("cuda", dtype=torch.float16):
+        assert not linear_tc.bf16_operands()
+    linear_tc.PRECISION = "bf16"
+    try:
+        assert linear_tc.bf16_operands()
+    finally:
+        linear_tc.PRECISION = "auto"
+    linear_tc.PRECISION = "fp32"
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            assert not linear_tc.bf16_operands()
+    finally:
+        linear_tc.PRECISION = "auto"
+    lin = torch.nn.Linear(32, 32)
+    x = torch.randn(4, 32)
+    assert not linear_tc.eligible(x, lin.weight)
+    assert torch.equal(linear_tc.linear(x, lin.weight, lin.bias, relu=True), torch.relu(lin(x)))

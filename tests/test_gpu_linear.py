@@ -570,3 +570,80 @@ def test_encoder_under_bf16_autocast_runs_own_kernels_and_tracks_fp32(mode):
                   "encoder.layers.1.self_attn.output_proj.weight", "encoder.layers.2.norm2.weight"):
             den = float(g32[k].double().norm())
             assert float((g16[k].double() - g32[k].double()).norm()) / den < 5e-2, k
+
+
+def test_bf16_tensors_in_global_memory_change_no_result():
+    """PCT_LINEAR_X_BF16 / Y_BF16 / RES_BF16 / GY_BF16: a tensor that is bf16 in memory gives exactly
+    what the fp32 tensor holding the same (rounded) values gives; a bf16 result is the fp32 result
+    rounded once."""
+    from pctrans_b200 import _cabi
+    rows, k, n = 3000, 1024, 256
+    x, w, b, res = _case(rows, k, n, seed=31)
+    wp = _cabi.linear_pack_weight(w, bf16=True)
+    x16, res16 = x.bfloat16(), res.bfloat16()
+    y_ref = _cabi.linear_forward(x16.float(), wp, n, b, res16.float(), relu=True, bf16=True)
+    y = _cabi.linear_forward(x16, wp, n, b, res16, relu=True, bf16=True)
+    assert y.dtype == torch.float32 and torch.equal(y, y_ref)
+    y_low = _cabi.linear_forward(x16, wp, n, b, res16, relu=True, bf16=True, out_dtype=torch.bfloat16)
+    assert y_low.dtype == torch.bfloat16 and torch.equal(y_low, y_ref.bfloat16())
+    gate = torch.randn(rows, n, generator=torch.Generator().manual_seed(7)).cuda()
+    g_ref = _cabi.linear_forward(x, wp, n, b, gate=gate, bf16=True)
+    assert torch.equal(_cabi.linear_forward(x, wp, n, b, gate=gate.bfloat16(), bf16=True), g_ref)
+    # LayerNorm epilogue with a bf16 x: statistics and the saved input stay fp32
+    gamma, beta = torch.randn(n).cuda(), torch.randn(n).cuda()
+    a1 = _cabi.linear_forward(x16, wp, n, b, res, gamma, beta, 1e-5, save_for_backward=True, bf16=True)
+    a0 = _cabi.linear_forward(x16.float(), wp, n, b, res, gamma, beta, 1e-5, save_for_backward=True, bf16=True)
+    assert all(t1.dtype == torch.float32 and torch.equal(t1, t0) for t1, t0 in zip(a1, a0))
+    # weight gradient: either operand (or both) bf16 in memory
+    gy = torch.randn(rows, n, generator=torch.Generator().manual_seed(8)).cuda()
+    ref = _r16(gy).t() @ _r16(x)
+    for gy_in, x_in in ((gy.bfloat16(), x), (gy, x16), (gy.bfloat16(), x16)):
+        gw, gb = _cabi.linear_wgrad(gy_in, x_in, with_bias=True, bf16=True)
+        assert gw.dtype == torch.float32 and _rel(gw, ref) < 1e-5
+        assert _rel(gb, gy_in.double().sum(0)) < 1e-5
+    # bf16 tensors without the bf16 kernel are refused
+    with pytest.raises(TypeError):
+        _cabi.linear_forward(x16, _cabi.linear_pack_weight(w), n)
+    with pytest.raises(TypeError):
+        _cabi.linear_wgrad(gy.bfloat16(), x)
+
+
+def test_ffn_block_bf16_hidden_activation_changes_only_the_bias_gradient():
+    """Under bf16 autocast the FFN block stores its hidden activation and that activation's
+    gradient in bf16 (BF16_HIDDEN): every GEMM rounds those operands anyway, so the output is
+    bit-identical to the fp32-storage run and the gradients agree to fp32-reduction noise; only the
+    first bias gradient sums rounded values."""
+    from pctrans_b200.functions import linear_tc
+    torch.manual_seed(5)
+    lin1, lin2 = torch.nn.Linear(256, 1024).cuda(), torch.nn.Linear(1024, 256).cuda()
+    norm = torch.nn.LayerNorm(256).cuda()
+    src = torch.randn(2, 2500, 256, device="cuda", requires_grad=True)
+    gy = torch.randn(2, 2500, 256, device="cuda")
+    params = [src, lin1.weight, lin1.bias, lin2.weight, lin2.bias, norm.weight, norm.bias]
+
+    def run(hidden_bf16):
+        linear_tc.BF16_HIDDEN = hidden_bf16
+        for p in params:
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = linear_tc.ffn_block(src, lin1, lin2, norm)
+            with torch.no_grad():
+                y_inf = linear_tc.ffn_block(src.detach(), lin1, lin2, norm)
+        y.backward(gy)
+        return y.detach(), y_inf, [p.grad.clone() for p in params]
+
+    try:
+        y1, yi1, g1 = run(True)
+        y0, yi0, g0 = run(False)
+    finally:
+        linear_tc.BF16_HIDDEN = True
+    assert torch.equal(y1, y0) and torch.equal(yi1, yi0) and torch.equal(yi1, y1)
+    for a, b_, name in zip(g1, g0, ("src", "w1", "b1", "w2", "b2", "ln_w", "ln_b")):
+        assert _rel(a, b_.double()) < (5e-3 if name == "b1" else 1e-5), name
+    # and both track the fp32 block within the bf16 bar
+    for p in params:
+        p.grad = None
+    y32 = linear_tc.ffn_block(src, lin1, lin2, norm)
+    y32.backward(gy)
+    assert _rel(y1, y32.detach().double()) < 2e-2
+    assert _rel(g1[0], src.grad.double()) < 2e-2
