@@ -415,8 +415,8 @@ def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dis
     forward + backward of a training step; with `dist` the parameter gradients (4.39 M floats at
     d256) are all-reduced over NCCL on a side stream, overlapped with the tail of the backward and
     waited for where the optimizer would consume them.  `bf16_autocast`: the forward runs under
-    torch.autocast(bfloat16) -- the Linears' forward / input-gradient GEMMs take bf16 operands on
-    the own tensor-core kernels (PCT_LINEAR_BF16), tensors and the op stay fp32."""
+    torch.autocast(bfloat16) -- the Linears' GEMMs (forward, input and weight gradient) take bf16
+    operands on the own tensor-core kernels (PCT_LINEAR_BF16); the op stays fp32."""
     import contextlib
     amp = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if bf16_autocast else contextlib.nullcontext
     from pctrans_b200 import encoder as enc, synth
@@ -471,8 +471,9 @@ def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dis
     return {
         "workload": f"{ENCODER_LAYERS}-layer MSDeformAttn encoder training step (fwd+bwd), {pyr_name} pyramid, "
                     f"{batch} images/GPU, d_model {d_model}, "
-                    + ("bf16 autocast (own tensor-core Linears with bf16 operands forward / dgrad, 3xTF32 "
-                       "wgrad, fp32 tensors, fused-prologue op)" if bf16_autocast else
+                    + ("bf16 autocast (own tensor-core Linears with bf16 operands forward / dgrad / wgrad, "
+                       "fp32 accumulation and tensors except the FFN's hidden activation, fused-prologue "
+                       "op on fp32 values)" if bf16_autocast else
                        "fp32 (tensor-core 3xTF32 Linears, fused-prologue op)")
                     + (f", NCCL all-reduce of {n_params} param grads in {n_buckets} buckets on a side "
                        "stream, overlapped with the backward" if dist is not None else ""),
