@@ -647,3 +647,59 @@ def test_ffn_block_bf16_hidden_activation_changes_only_the_bias_gradient():
     y32.backward(gy)
     assert _rel(y1, y32.detach().double()) < 2e-2
     assert _rel(g1[0], src.grad.double()) < 2e-2
+
+
+@pytest.mark.parametrize("rows,k,n", [(1, 32, 16), (127, 64, 48), (129, 256, 192), (1000, 1024, 96),
+                                      (4116, 128, 288), (333, 1024, 1024)])
+def test_bf16_tensors_in_memory_on_ragged_shapes(rows, k, n):
+    """Partial row tiles, column tiles narrower than 32 and 2-tile outputs through the
+    bf16-in-memory instantiations: every combination of bf16 x / residual / gate / result equals
+    the all-fp32-tensor call on the same (rounded) values."""
+    from pctrans_b200 import _cabi
+    x, w, b, res = _case(rows, k, n, seed=41)
+    wp = _cabi.linear_pack_weight(w, bf16=True)
+    x16, res16 = x.bfloat16(), res.bfloat16()
+    gate16 = (res - 0.3).bfloat16()
+    for xin in (x16.float(), x16):
+        for rin in (res16.float(), res16):
+            ref = _cabi.linear_forward(x16.float(), wp, n, b, res16.float(), bf16=True)
+            assert torch.equal(_cabi.linear_forward(xin, wp, n, b, rin, bf16=True), ref)
+            low = _cabi.linear_forward(xin, wp, n, b, rin, bf16=True, out_dtype=torch.bfloat16)
+            assert torch.equal(low, ref.bfloat16())
+        gref = _cabi.linear_forward(x16.float(), wp, n, b, gate=gate16.float(), relu=True, bf16=True)
+        for gin in (gate16.float(), gate16):
+            assert torch.equal(_cabi.linear_forward(xin, wp, n, b, gate=gin, relu=True, bf16=True), gref)
+            low = _cabi.linear_forward(xin, wp, n, b, gate=gin, relu=True, bf16=True, out_dtype=torch.bfloat16)
+            assert torch.equal(low, gref.bfloat16())
+    gy = torch.randn(rows, n, generator=torch.Generator().manual_seed(9)).cuda()
+    gw = _cabi.linear_wgrad(gy.bfloat16(), x16, with_bias=True, bf16=True)
+    assert _rel(gw[0], _r16(gy).t() @ _r16(x)) < 1e-5 and _rel(gw[1], _r16(gy).sum(0)) < 1e-5
+
+
+def test_bf16_memory_flags_need_the_bf16_kernel_error_codes():
+    """C ABI: PCT_LINEAR_X_BF16 / Y_BF16 / RES_BF16 / GY_BF16 without PCT_LINEAR_BF16, or a bf16
+    residual flag with nothing read through the residual slot, are PCT_MSDA_E_UNSUPPORTED."""
+    from pctrans_b200 import _cabi
+    lib = _cabi.load()
+    x, w, b, res = _case(64, 32, 32)
+    wp = _cabi.linear_pack_weight(w, bf16=True)
+    y = torch.empty(64, 32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fwd(flags, residual=None):
+        return lib.pct_linear_forward(x.data_ptr(), wp.data_ptr(), b.data_ptr(),
+                                      residual.data_ptr() if residual is not None else None, None, None,
+                                      1e-5, y.data_ptr(), 64, 32, 32, flags, st)
+    BF, X16, Y16, R16, G16 = (_cabi.LINEAR_BF16, _cabi.LINEAR_X_BF16, _cabi.LINEAR_Y_BF16,
+                              _cabi.LINEAR_RES_BF16, _cabi.LINEAR_GY_BF16)
+    assert fwd(BF) == 0
+    bad = fwd(X16)
+    assert bad != 0 and fwd(Y16) == bad and fwd(R16 | _cabi.LINEAR_RESIDUAL, res) == bad
+    assert fwd(BF | R16) == bad                       # no residual / gate to read
+    assert fwd(BF | G16) == bad                       # a weight-gradient flag
+    gw = torch.empty(32, 32, device="cuda")
+    wg = lambda flags: lib.pct_linear_wgrad_ex(res.data_ptr(), x.data_ptr(), gw.data_ptr(), None, 64, 32, 32, flags, st)
+    assert wg(0) == 0 and wg(BF) == 0 and wg(X16) == bad and wg(G16) == bad and wg(BF | Y16) == bad
+    torch.cuda.synchronize()
+    assert lib.pct_msda_error_string(bad).decode()
+
