@@ -27,6 +27,10 @@ echo
 echo "## linear_tf32x3_kernel: tcgen05 MMA (UTCHMMA), TMEM loads/stores (LDTM/STTM), bulk copies (UBLKCP)"
 excerpt 'linear_tf32x3_kernel' 'UTCHMMA|LDTM|STTM|UBLKCP|UTCBAR|SYNCS' 20
 echo
+echo "## linear_bf16_kernel / wgrad_bf16_kernel: the same MMAs with bf16 operands (kind::f16), bf16x2 packing of the loaded activations"
+excerpt 'linear_bf16_kernel' 'UTCHMMA|F2FP|UBLKCP' 10
+excerpt 'wgrad_bf16_kernelILb0ELb0' 'UTCHMMA|F2FP' 6
+echo
 echo "## linear_tf32x3_pair_kernel: cta_group::2 MMAs"
 excerpt 'linear_tf32x3_pair_kernel' 'UTCHMMA' 6
 rm -f "$TMP"
