@@ -484,12 +484,16 @@ def encoder_train_record(dev, pyr_name, batch, d_model=256, steps=8, warm=3, dis
     }
 
 
-def decoder_infer_record(dev, batch=8, steps=10, warm=3):
+def decoder_infer_record(dev, batch=8, steps=10, warm=3, bf16_operands=False):
     """BASELINE config 2: MSDeformAttnPixelDecoder.forward_features (PD/msdeformattn.py:314-360),
     inference, batch 8, CVPPP 512x512 ResNet features; the outputs are compared in the same run with
     the same decoder (same weights) whose op is the reference's grid_sample formulation
-    (func.py:52-72) on the GPU."""
+    (func.py:52-72) on the GPU.  `bf16_operands`: the decoder pins its encoder to fp32 as the
+    reference does (autocast disabled, PD:314-320); with this flag the timed run sets
+    linear_tc.PRECISION = "bf16" (bf16 GEMM operands on the own kernels, fp32 tensors and op) and is
+    held to BASELINE's bf16 bar against the fp32 reference formulation."""
     from pctrans_b200 import encoder as enc
+    from pctrans_b200.functions import linear_tc
     from pctrans_b200.modules import ms_deform_attn as mod_file
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     from _gridsample import grid_sample_core
@@ -504,16 +508,20 @@ def decoder_infer_record(dev, batch=8, steps=10, warm=3):
         with torch.no_grad():
             return dec.forward_features(feats)
 
-    for _ in range(warm):
-        ours = run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        ours = run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    linear_tc.PRECISION = "bf16" if bf16_operands else "auto"
+    try:
+        for _ in range(warm):
+            ours = run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ours = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        linear_tc.PRECISION = "auto"
 
     class _RefCore:   # the reference's CPU/debug formulation as the op, on the GPU
         @staticmethod
@@ -549,7 +557,9 @@ def decoder_infer_record(dev, batch=8, steps=10, warm=3):
     torch.cuda.empty_cache()
     return {
         "workload": f"MSDeformAttnPixelDecoder.forward_features, inference, batch {batch}, 512x512 input "
-                    "(res2..res5 features), d_model 256, 6 encoder layers, fp32",
+                    "(res2..res5 features), d_model 256, 6 encoder layers, "
+                    + ("bf16 GEMM operands in the encoder's Linears (own kernels), fp32 tensors"
+                       if bf16_operands else "fp32"),
         "ms_per_step": ms, "images_per_s": batch / (ms * 1e-3),
         "queries_per_s": batch * lq * ENCODER_LAYERS / (ms * 1e-3),
         "queries_are": "query-layers: N * Lq * 6 layers per forward",
@@ -558,9 +568,11 @@ def decoder_infer_record(dev, batch=8, steps=10, warm=3):
         # the encoder memory within 1e-5; mask_features passes through the FPN's
         # cuDNN convolutions (TF32 by default, as in the reference) whose operand rounding turns
         # the 5e-7 input difference into ~1e-5 noise, so it is held to 1e-4
-        "tolerance": {"encoder_maps": 1e-5, "mask_features": 1e-4},
-        "within_tolerance": (max(errs["encoder_lowest_map"], errs["multi_scale_max"]) <= 1e-5
-                             and errs["mask_features"] <= 1e-4),
+        "tolerance": ({"encoder_maps": 2e-2, "mask_features": 2e-2} if bf16_operands
+                      else {"encoder_maps": 1e-5, "mask_features": 1e-4}),
+        "within_tolerance": (max(errs.values()) <= 2e-2 if bf16_operands else
+                             (max(errs["encoder_lowest_map"], errs["multi_scale_max"]) <= 1e-5
+                              and errs["mask_features"] <= 1e-4)),
     }
 
 
@@ -581,6 +593,7 @@ def sub_records(dev, peak, args):
     guarded("cfg4_bbbc_encoder6_train_b32_bf16_autocast",
             lambda: encoder_train_record(dev, "bbbc", 32, bf16_autocast=True))
     guarded("cfg2_decoder_infer_b8", lambda: decoder_infer_record(dev))
+    guarded("cfg2_decoder_infer_b8_bf16_operands", lambda: decoder_infer_record(dev, bf16_operands=True))
     return recs
 
 
