@@ -37,6 +37,12 @@
 #ifndef PCT_LIN_RPF_LEAD
 #define PCT_LIN_RPF_LEAD 4   // ... this many K steps before the end of the main loop
 #endif
+#ifndef PCT_LIN_STAGGER_PER_STEP
+#define PCT_LIN_STAGGER_PER_STEP 200 // ns per K step: start delay of the second CTA of every SM (first wave)
+#endif
+#ifndef PCT_LIN_STAGGER_FIXED
+#define PCT_LIN_STAGGER_FIXED 2000   // ns
+#endif
 #ifndef PCT_LIN_AHEAD_BF16
 #define PCT_LIN_AHEAD_BF16 4
 #endif
@@ -511,6 +517,21 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
   const int lane = tid & 31;
   const int n0 = blockIdx.x * kBlockN;
   const int m0 = blockIdx.y * kBlockM;
+  if (PCT_LIN_STAGGER_PER_STEP || PCT_LIN_STAGGER_FIXED) {
+    // Two CTAs share an SM and a tile is a load phase followed by an epilogue phase: started
+    // together they stay in phase (both loading, then both storing).  The CTAs that fill the second
+    // slot of every SM in the first wave start about half a tile late, so that one CTA's main loop
+    // runs against the other's epilogue from then on (grids of at least two full waves only;
+    // measured: 1024->256 272 -> 250 us 3xTF32, 171 -> 160 us bf16, LayerNorm 120 -> 113 us, others
+    // within 2 %, profiles/r02_linear_stagger.log).
+    unsigned nsm;
+    asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+    if (cta >= nsm && cta < 2 * nsm && gridDim.x * gridDim.y >= 4 * nsm) {
+      long long ns = PCT_LIN_STAGGER_FIXED + (long long)(a.K / Prec<BF16>::kStepK) * PCT_LIN_STAGGER_PER_STEP;
+      for (; ns > 0; ns -= 100000) __nanosleep((unsigned)(ns < 100000 ? ns : 100000));
+    }
+  }
   PCT_TRACE(0);
   const int n_tile = min(kBlockN, a.N - n0);
 
