@@ -1,5 +1,8 @@
-// linear_tc.cu -- fp32 Linear on the tcgen05 tensor cores (3xTF32 split), with the encoder layer's
-// epilogues fused: bias, ReLU, residual add, LayerNorm.  C ABI in include/pct_linear.h.
+// linear_tc.cu -- fp32 Linear on the tcgen05 tensor cores (3xTF32 split, or bf16 operands with
+// PCT_LINEAR_BF16: struct Prec below), with the encoder layer's epilogues fused: bias, ReLU,
+// residual add, ReLU gate, row mask, LayerNorm.  C ABI in include/pct_linear.h.  The description
+// that follows is the 3xTF32 instantiation; the bf16 one differs in the K step (32 elements, one
+// rounded piece per operand, two kind::f16 MMAs) and may read / write bf16 tensors.
 //
 // One CTA computes a 128-row x (<=256)-column tile of y = x @ W^T:
 //   * the accumulator is a 128-lane x 256-column fp32 block of tensor memory (TMEM);
@@ -20,7 +23,8 @@
 //     shared-memory patch so that every warp access covers whole 128-byte lines: the kernel is
 //     bound by load/store-pipe wavefronts, not by the tensor core (profiles/r01_linear_*).
 // Two CTAs fit per SM (96 KB of shared memory, 256 TMEM columns each), so one CTA's loads and
-// epilogue overlap the other's MMAs.
+// epilogue overlap the other's MMAs; in the first wave the second CTA of an SM starts half a phase
+// late (PCT_LIN_STAGGER_*) so that the pair stays out of phase.
 #include "../../include/pct_linear.h"
 #include "../../include/pct_msda.h"
 
