@@ -104,6 +104,61 @@ int main(void) {
     printf("FAIL tolerance\n");
     return 1;
   }
+  /* bf16 operands (PCT_LINEAR_BF16) from C: K = 96 is a multiple of 32; against a double loop over
+   * the operands rounded to bf16 on the host (round to nearest even) the fp32-accumulated result
+   * has to be as tight as above; the bias gradient sums the unrounded grad_y */
+  {
+    size_t pb = pct_linear_packed_bytes_bf16(K, N);
+    void* dp16 = NULL;
+    if (!pb || cudaMalloc(&dp16, pb) != cudaSuccess) {
+      printf("FAIL bf16 allocation\n");
+      return 1;
+    }
+    CHECK(pct_linear_pack_weight_bf16(dw, dp16, K, N, NULL));
+    CHECK(pct_linear_forward(dx, dp16, db, dres, NULL, NULL, 0.f, dy, ROWS, K, N,
+                             PCT_LINEAR_RESIDUAL | PCT_LINEAR_BF16, NULL));
+    CHECK(pct_linear_wgrad_ex(dgy, dx, dgw, dgb, ROWS, K, N, PCT_LINEAR_BF16, NULL));
+    if (pct_linear_forward(dx, dp16, db, NULL, NULL, NULL, 0.f, dy, ROWS, K, N, PCT_LINEAR_X_BF16, NULL) !=
+        PCT_MSDA_E_UNSUPPORTED) {
+      printf("FAIL bf16 flag error code\n");
+      return 1;
+    }
+    CHECK(cudaDeviceSynchronize());
+    cudaMemcpy(y, dy, 4 * ROWS * N, cudaMemcpyDeviceToHost);
+    cudaMemcpy(gw, dgw, 4 * N * K, cudaMemcpyDeviceToHost);
+    float *x16 = malloc(4 * ROWS * K), *w16 = malloc(4 * N * K), *g16 = malloc(4 * ROWS * N);
+#define RN_BF16(dst, src, count)                                                     \
+  for (int i_ = 0; i_ < (count); ++i_) {                                             \
+    union { float f; uint32_t u; } v_;                                               \
+    v_.f = (src)[i_];                                                                \
+    v_.u = (v_.u + 0x7fffu + ((v_.u >> 16) & 1u)) & 0xffff0000u;                     \
+    (dst)[i_] = v_.f;                                                                \
+  }
+    RN_BF16(x16, x, ROWS * K)
+    RN_BF16(w16, w, N * K)
+    RN_BF16(g16, gy, ROWS * N)
+    double e_y = 0, r_y = 0, e_w = 0, r_w = 0;
+    for (int r = 0; r < ROWS; ++r)
+      for (int n = 0; n < N; ++n) {
+        double acc = (double)b[n] + res[r * N + n];
+        for (int k = 0; k < K; ++k) acc += (double)x16[r * K + k] * w16[n * K + k];
+        e_y = fmax(e_y, fabs(acc - y[r * N + n]));
+        r_y = fmax(r_y, fabs(acc));
+      }
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) {
+        double acc = 0;
+        for (int r = 0; r < ROWS; ++r) acc += (double)g16[r * N + n] * x16[r * K + k];
+        e_w = fmax(e_w, fabs(acc - gw[n * K + k]));
+        r_w = fmax(r_w, fabs(acc));
+      }
+    printf("bf16 operands: linear+residual rel err %.2e, wgrad %.2e (vs rounded operands)\n", e_y / r_y,
+           e_w / r_w);
+    if (e_y / r_y > 1e-5 || e_w / r_w > 1e-5) {
+      printf("FAIL bf16 tolerance\n");
+      return 1;
+    }
+  }
   printf("C_LINEAR_CLIENT PASS\n");
   return 0;
 }
