@@ -96,6 +96,20 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
                              float* ln_rstd, int rows, int in_features, int out_features,
                              unsigned flags, void* cuda_stream);
 
+/* Two Linears that read the same input as ONE GEMM, without a concatenated copy of anything
+ * (sampling_offsets and attention_weights both project the query, OPS/modules/ms_deform_attn.py:102-104):
+ *   forward:         x_b = NULL, in_b = 0;   [y_a (rows, out_a) | y_b (rows, out_b)] = x_a @ W^T + bias
+ *                    with W (out_a + out_b, in_a) the row-concatenation of the two weights (packed as one)
+ *                    and bias the concatenation of the two biases; out_a % 32 == 0;
+ *   input gradient:  y_b = NULL, out_b = 0;  y_a (rows, out_a) = [x_a (rows, in_a) | x_b (rows, in_b)] @ W^T
+ *                    with W the packed transpose of that concatenated weight, x_a / x_b the two output
+ *                    gradients; in_a a multiple of the K step (16, or 32 with PCT_LINEAR_BF16).
+ * flags: PCT_LINEAR_RELU, PCT_LINEAR_RESIDUAL (single y only), PCT_LINEAR_BF16.  fp32 tensors. */
+int pct_linear_forward_split(const float* x_a, const float* x_b, int in_a, int in_b,
+                             const void* w_packed, const float* bias, const float* residual,
+                             float* y_a, float* y_b, int out_a, int out_b, int rows, unsigned flags,
+                             void* cuda_stream);
+
 /* grad_w (out, in) = grad_y (rows, out)^T @ x (rows, in): the weight gradient of the Linear, same
  * 3xTF32 arithmetic, the row dimension split over CTAs and combined with fp32 reductions (so, like
  * the reference's atomicAdd backward, not bit-reproducible run to run).  grad_w is fully
@@ -110,6 +124,14 @@ int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* 
  * gradient.  flags = 0 is pct_linear_wgrad. */
 int pct_linear_wgrad_ex(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
                         int in_features, int out_features, unsigned flags, void* cuda_stream);
+
+/* Weight gradient of two Linears that read the same x (see pct_linear_forward_split): grad_y is the
+ * pair [grad_y_a (rows, out_a) | grad_y_b (rows, out_b)], grad_w (out_a + out_b, in) and grad_bias
+ * (out_a + out_b,) are the row-concatenations of the two gradients.  out_a % 4 == 0, out_b % 4 == 0;
+ * flags: PCT_LINEAR_BF16, PCT_LINEAR_X_BF16.  out_b = 0 is pct_linear_wgrad_ex. */
+int pct_linear_wgrad_split(const float* grad_y_a, const float* grad_y_b, int out_a, int out_b,
+                           const float* x, float* grad_w, float* grad_bias, int rows, int in_features,
+                           unsigned flags, void* cuda_stream);
 
 /* Backward of the LayerNorm fused into pct_linear_forward_train (PD/msdeformattn.py:107-126: the two
  * `norm(residual + linear(x))` blocks of an encoder layer), one pass over the rows:

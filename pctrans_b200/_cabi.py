@@ -34,7 +34,8 @@ EXPORTS = (
 )
 LINEAR_EXPORTS = ("pct_linear_packed_bytes", "pct_linear_pack_weight", "pct_linear_packed_bytes_bf16",
                   "pct_linear_pack_weight_bf16", "pct_linear_forward",
-                  "pct_linear_forward_train", "pct_linear_wgrad", "pct_linear_wgrad_ex", "pct_linear_layernorm_backward")
+                  "pct_linear_forward_train", "pct_linear_forward_split", "pct_linear_wgrad", "pct_linear_wgrad_ex",
+                  "pct_linear_wgrad_split", "pct_linear_layernorm_backward")
 LINEAR_RELU, LINEAR_RESIDUAL, LINEAR_LAYERNORM, LINEAR_GATE, LINEAR_ROWMASK = 0x1, 0x2, 0x4, 0x8, 0x10
 LINEAR_BF16, LINEAR_X_BF16, LINEAR_Y_BF16, LINEAR_RES_BF16, LINEAR_GY_BF16 = 0x20, 0x40, 0x80, 0x100, 0x200
 E_UNSUPPORTED = 1007
@@ -120,6 +121,10 @@ def load():
         lib.pct_linear_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
         lib.pct_linear_wgrad_ex.restype = i32
         lib.pct_linear_wgrad_ex.argtypes = [vp, vp, vp, vp, i32, i32, i32, u32, vp]
+        lib.pct_linear_wgrad_split.restype = i32
+        lib.pct_linear_wgrad_split.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, i32, u32, vp]
+        lib.pct_linear_forward_split.restype = i32
+        lib.pct_linear_forward_split.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, u32, vp]
         lib.pct_linear_layernorm_backward.restype = i32
         lib.pct_linear_layernorm_backward.argtypes = [vp] * 8 + [i32, i32, vp]
         lib.pct_linear_forward_train.restype = i32
@@ -409,3 +414,45 @@ def linear_wgrad(grad_y, x, with_bias: bool = False, bf16: bool = False):
                                          flags, _stream_ptr(x.device)),
               "pct_linear_wgrad")
     return (gw, gb) if with_bias else gw
+
+
+def linear_forward_pair(x, w_packed, out_a, out_b, bias=None, bf16: bool = False):
+    """(y_a, y_b) = split of ``x @ W^T + bias`` with W (out_a + out_b, in) packed as one weight: two
+    Linears on the same input as one GEMM, two dense results (pct_linear_forward_split)."""
+    rows, k = x.shape
+    ya = torch.empty((rows, out_a), dtype=torch.float32, device=x.device)
+    yb = torch.empty((rows, out_b), dtype=torch.float32, device=x.device)
+    with torch.cuda.device_of(x):
+        check(load().pct_linear_forward_split(
+            x.data_ptr(), None, k, 0, w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+            None, ya.data_ptr(), yb.data_ptr(), out_a, out_b, rows, LINEAR_BF16 if bf16 else 0,
+            _stream_ptr(x.device)), "pct_linear_forward_split")
+    return ya, yb
+
+
+def linear_forward_cat(x_a, x_b, w_packed, out_features, residual=None, bf16: bool = False):
+    """``[x_a | x_b] @ W^T (+ residual)`` without materialising the concatenation: the input gradient of
+    two Linears on the same input, W the packed transpose of their row-concatenated weight."""
+    rows = x_a.shape[0]
+    y = torch.empty((rows, out_features), dtype=torch.float32, device=x_a.device)
+    flags = (LINEAR_BF16 if bf16 else 0) | (LINEAR_RESIDUAL if residual is not None else 0)
+    with torch.cuda.device_of(x_a):
+        check(load().pct_linear_forward_split(
+            x_a.data_ptr(), x_b.data_ptr(), x_a.shape[1], x_b.shape[1], w_packed.data_ptr(), None,
+            residual.data_ptr() if residual is not None else None, y.data_ptr(), None, out_features, 0,
+            rows, flags, _stream_ptr(x_a.device)), "pct_linear_forward_split")
+    return y
+
+
+def linear_wgrad_pair(grad_y_a, grad_y_b, x, bf16: bool = False):
+    """(grad_w, grad_b) of the row-concatenated weight / bias of two Linears on the same input."""
+    rows, k = x.shape
+    na, nb = grad_y_a.shape[1], grad_y_b.shape[1]
+    gw = torch.empty((na + nb, k), dtype=torch.float32, device=x.device)
+    gb = torch.empty((na + nb,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device_of(x):
+        check(load().pct_linear_wgrad_split(
+            grad_y_a.data_ptr(), grad_y_b.data_ptr(), na, nb, x.data_ptr(), gw.data_ptr(), gb.data_ptr(),
+            rows, k, LINEAR_BF16 if bf16 else 0, _stream_ptr(x.device)), "pct_linear_wgrad_split")
+    return gw, gb
+

@@ -262,13 +262,20 @@ struct LinearArgs {
   float eps;
   int rows, K, N;
   unsigned flags;
+  // SPLIT instantiations (pct_linear_forward_split / _cat): x is the K-concatenation of two dense
+  // tensors [x (rows, k_split) | x2 (rows, K - k_split)], y the N-concatenation [y (rows, n_split) |
+  // y2 (rows, N - n_split)]; 0 = that side is a single tensor.  k_split is a multiple of the K step,
+  // n_split of 32 (the epilogue's column block).
+  const float* x2;
+  float* y2;
+  int k_split, n_split;
 };
 
 // Epilogue of one 128 x n_tile accumulator, run by the four loader warps (warp w owns rows
 // 32w .. 32w+31 of the tile).  Row domain: a thread owns one row and walks its columns in TMEM
 // order.  Line domain: a warp instruction covers 4 rows x 128 contiguous bytes of global memory;
 // the two are bridged by a per-warp 32 x 36-float patch at the start of shared memory.
-template <bool IO16 = false>   // the bf16-in-memory options: own instantiation of the bf16 kernel
+template <bool IO16 = false, bool SPLIT = false>   // bf16-in-memory options / split tensors: own instantiations
 __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned char* smem, uint32_t tmem,
                                                 const float* vec_bias, const float* vec_gamma,
                                                 const float* vec_beta, int warp, int lane, int tid,
@@ -353,11 +360,19 @@ __device__ __forceinline__ void linear_epilogue(const LinearArgs& a, unsigned ch
     for (int j = 0; j < 8; ++j) {
       const int r = 4 * j + l_row;
       if (l_c4 < cw && r < rows_left) {
-        const size_t at = warp_off + (size_t)r * a.N + c + l_c4;
+        size_t at = warp_off + (size_t)r * a.N + c + l_c4;
+        float* dst = dst_base;
+        if (SPLIT && a.n_split && dst_base == a.y) {   // block-uniform: n_split is a multiple of 32
+          const int gc = n0 + c;                       // first column of the block in [y | y2]
+          const bool second = gc >= a.n_split;
+          dst = second ? a.y2 : a.y;
+          at = (size_t)(m0 + warp * 32 + r) * (second ? a.N - a.n_split : a.n_split) +
+               (second ? gc - a.n_split : gc) + l_c4;
+        }
         if (as_bf16)
-          *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(dst_base) + at) = pack_bf16x4(t[j]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(dst) + at) = pack_bf16x4(t[j]);
         else
-          *reinterpret_cast<float4*>(dst_base + at) = t[j];
+          *reinterpret_cast<float4*>(dst + at) = t[j];
       }
     }
   };
@@ -510,9 +525,10 @@ __device__ long long g_linear_trace[8 * 4096];
 #define PCT_TRACE(slot) do { } while (0)
 #endif
 
-template <bool BF16, bool IO16 = false>
+template <bool BF16, bool IO16 = false, bool SPLIT = false>
 __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* smem) {
   static_assert(BF16 || !IO16, "bf16 tensors only with the bf16 kernel");
+  static_assert(!(IO16 && SPLIT), "split tensors are fp32");
   using P = Prec<BF16>;
   constexpr int kStages = P::kNumStages, kStageBytes = P::kStage, kWStepBytes = P::kWStep;
   constexpr int kAhead = P::kXAhead;
@@ -680,8 +696,36 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
     // 16-byte chunk of the stage: 4 floats (3xTF32) or 8 floats rounded to bf16
     constexpr int kQ = BF16 ? 2 : 1;
     float4 xq[kAhead][kPerThread * kQ];
+    // SPLIT: the K steps below k_split come from x (row pitch k_split), the rest from x2
+    const int ks_steps = (SPLIT && a.k_split) ? a.k_split / P::kStepK : 0;
+    const char* xrow2[SPLIT ? kPerThread : 1];
+    if constexpr (SPLIT) {
+      if (ks_steps) {
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+          const int row = m0 + (rg + kLoaderWarps * j) * 8 + r8;
+          if (row < a.rows) {
+            xrow[j] = reinterpret_cast<const char*>(a.x) + ((size_t)row * a.k_split + kc * (P::kStepK / 4)) * 4;
+            xrow2[j] = reinterpret_cast<const char*>(a.x2) +
+                       ((size_t)row * (a.K - a.k_split) + kc * (P::kStepK / 4)) * 4;
+          }
+        }
+      }
+    }
     auto fetch_x = [&](float4* dst, int step) {
-      const size_t at = (size_t)step * P::kStepK * x_esz;
+      size_t at = (size_t)step * P::kStepK * x_esz;
+      if constexpr (SPLIT) {
+        if (ks_steps && step >= ks_steps) {
+          at = (size_t)(step - ks_steps) * P::kStepK * 4;
+#pragma unroll
+          for (int j = 0; j < kPerThread; ++j)
+#pragma unroll
+            for (int h = 0; h < kQ; ++h)
+              dst[j * kQ + h] = xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow2[j] + at) + h)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          return;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < kPerThread; ++j) {
         if (xb) {
@@ -741,7 +785,7 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
     mbar_wait(bar_done, 0);
     PCT_TRACE(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    linear_epilogue<IO16>(a, smem, tmem, vec_bias, vec_gamma, vec_beta, warp, lane, tid, m0, n0, n_tile);
+    linear_epilogue<IO16, SPLIT>(a, smem, tmem, vec_bias, vec_gamma, vec_beta, warp, lane, tid, m0, n0, n_tile);
     PCT_TRACE(5);
   }
 
@@ -763,6 +807,17 @@ __global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_kernel(const Linear
 __global__ void __launch_bounds__(kThreads, 2) linear_bf16_kernel(const LinearArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   linear_body<true>(a, smem);
+}
+
+// split tensors (pct_linear_forward_split / _cat): x = [x | x2] along K and / or y = [y | y2] along N
+__global__ void __launch_bounds__(kThreads, 2) linear_tf32x3_split_kernel(const LinearArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  linear_body<false, false, true>(a, smem);
+}
+
+__global__ void __launch_bounds__(kThreads, 2) linear_bf16_split_kernel(const LinearArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  linear_body<true, false, true>(a, smem);
 }
 
 // ... and with some of x / y / residual bf16 in global memory (PCT_LINEAR_X_BF16 / Y_BF16 / RES_BF16)
@@ -1106,6 +1161,8 @@ struct WgradArgs {
   float* gb;         // (N,) column sums of gy, zero on entry; may be null
   int rows, K, N;
   int steps_per_split;
+  const float* gy2;  // second part of a column-concatenated grad_y, (rows, N - n_split); n_split = 0: none
+  int n_split;
 };
 
 // BF16 (PCT_LINEAR_BF16): both operands rounded to bf16; a K step is then 32 rows (a 16-byte chunk
@@ -1210,10 +1267,15 @@ __device__ __forceinline__ void wgrad_body(const WgradArgs& a, unsigned char* sm
       const bool ok = u < kWgUnits && 4 * g < (is_a ? n_valid : k_tile);
       s16[j] = is_a ? GY16 : X16;
       const int esz = s16[j] ? 2 : 4;
+      // grad_y may be the column-concatenation [gy (rows, n_split) | gy2 (rows, N - n_split)]
+      // (pct_linear_wgrad_split; n_split is a multiple of 4, so a unit lies in one of the two)
+      const int feat = n0 + 4 * g;
+      const bool second = is_a && a.n_split > 0 && feat >= a.n_split;
       src[j] = !ok ? nullptr
-                   : is_a ? reinterpret_cast<const char*>(a.gy) + (size_t)(n0 + 4 * g) * esz
+                   : is_a ? (second ? reinterpret_cast<const char*>(a.gy2) + (size_t)(feat - a.n_split) * esz
+                                    : reinterpret_cast<const char*>(a.gy) + (size_t)feat * esz)
                           : reinterpret_cast<const char*>(a.x) + (size_t)(k0 + 4 * g) * esz;
-      ld[j] = (is_a ? a.N : a.K) * esz;      // row pitch in bytes
+      ld[j] = (is_a ? (a.n_split > 0 ? (second ? a.N - a.n_split : a.n_split) : a.N) : a.K) * esz;   // row pitch in bytes
       // features 4g..4g+3 are rows (4g+i)%8 of 8-row group (4g)/8; the row quad is the k-chunk
       dst[j] = (is_a ? 0 : kPieces * kWgABytes) + (g >> 1) * kWgSbo + rq[j] * kCoreBytes + (g & 1) * 64;
       lo_off[j] = is_a ? kWgABytes : kWgBBytes;
@@ -1474,7 +1536,8 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   LinearArgs a{x, static_cast<const unsigned char*>(w_packed), bias, residual, ln_gamma, ln_beta,
-               y, pre_norm, ln_mean, ln_rstd, ln_eps, rows, in_features, out_features, flags};
+               y, pre_norm, ln_mean, ln_rstd, ln_eps, rows, in_features, out_features, flags,
+               nullptr, nullptr, 0, 0};
   dim3 grid((out_features + kBlockN - 1) / kBlockN, (unsigned)m_tiles);
   if (flags & PCT_LINEAR_BF16) {
     static bool bf16_attr[64] = {};
@@ -1528,6 +1591,51 @@ int pct_linear_forward_train(const float* x, const void* w_packed, const float* 
   return (int)cudaGetLastError();
 }
 
+int pct_linear_forward_split(const float* x_a, const float* x_b, int in_a, int in_b,
+                             const void* w_packed, const float* bias, const float* residual,
+                             float* y_a, float* y_b, int out_a, int out_b, int rows, unsigned flags,
+                             void* cuda_stream) {
+  if (!x_a || !w_packed || !y_a) return PCT_MSDA_E_NULL_POINTER;
+  if ((in_b > 0 && !x_b) || (out_b > 0 && !y_b)) return PCT_MSDA_E_NULL_POINTER;
+  if (in_b < 0 || out_b < 0) return PCT_MSDA_E_BAD_SHAPE;
+  if (flags & ~(PCT_LINEAR_RELU | PCT_LINEAR_RESIDUAL | PCT_LINEAR_BF16)) return PCT_MSDA_E_UNSUPPORTED;
+  if ((flags & PCT_LINEAR_RESIDUAL) && (!residual || out_b > 0)) return PCT_MSDA_E_UNSUPPORTED;
+  const bool bf16 = flags & PCT_LINEAR_BF16;
+  const int in_features = in_a + in_b, out_features = out_a + out_b;
+  const int kstep = bf16 ? Prec<true>::kStepK : Prec<false>::kStepK;
+  if (rows < 1 || bad_dims(in_features, out_features) || in_features % kstep) return PCT_MSDA_E_BAD_SHAPE;
+  if ((in_b > 0 && in_a % kstep) || (out_b > 0 && out_a % 32)) return PCT_MSDA_E_BAD_SHAPE;
+  if (misaligned(x_a) || misaligned(x_b) || misaligned(w_packed) || misaligned(y_a) || misaligned(y_b) ||
+      misaligned(residual) || (in_b > 0 && in_b % 4) || (out_b > 0 && out_b % 4))
+    return PCT_MSDA_E_MISALIGNED;
+  if (((uintptr_t)bias) & 3u) return PCT_MSDA_E_MISALIGNED;
+  const long long m_tiles = ((long long)rows + kBlockM - 1) / kBlockM;
+  if (m_tiles > 65535) return PCT_MSDA_E_TOO_LARGE;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(linear_tf32x3_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(linear_bf16_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Prec<true>::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  LinearArgs a{x_a, static_cast<const unsigned char*>(w_packed), bias, residual, nullptr, nullptr,
+               y_a, nullptr, nullptr, nullptr, 0.f, rows, in_features, out_features, flags,
+               x_b, y_b, in_b > 0 ? in_a : 0, out_b > 0 ? out_a : 0};
+  dim3 grid((out_features + kBlockN - 1) / kBlockN, (unsigned)m_tiles);
+  if (bf16)
+    linear_bf16_split_kernel<<<grid, kThreads, Prec<true>::kSmem, (cudaStream_t)cuda_stream>>>(a);
+  else
+    linear_tf32x3_split_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)cuda_stream>>>(a);
+  pct::count_launch();
+  return (int)cudaGetLastError();
+}
+
 int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
                      int in_features, int out_features, void* cuda_stream) {
   return pct_linear_wgrad_ex(grad_y, x, grad_w, grad_bias, rows, in_features, out_features, 0u,
@@ -1536,6 +1644,17 @@ int pct_linear_wgrad(const float* grad_y, const float* x, float* grad_w, float* 
 
 int pct_linear_wgrad_ex(const float* grad_y, const float* x, float* grad_w, float* grad_bias, int rows,
                         int in_features, int out_features, unsigned flags, void* cuda_stream) {
+  return pct_linear_wgrad_split(grad_y, nullptr, out_features, 0, x, grad_w, grad_bias, rows, in_features,
+                                flags, cuda_stream);
+}
+
+int pct_linear_wgrad_split(const float* grad_y, const float* grad_y_b, int out_a, int out_b, const float* x,
+                           float* grad_w, float* grad_bias, int rows, int in_features, unsigned flags,
+                           void* cuda_stream) {
+  if (out_b < 0 || (out_b > 0 && (!grad_y_b || out_a % 4 || out_b % 4 || misaligned(grad_y_b))))
+    return out_b > 0 && !grad_y_b ? PCT_MSDA_E_NULL_POINTER : PCT_MSDA_E_BAD_SHAPE;
+  if (out_b > 0 && (flags & PCT_LINEAR_GY_BF16)) return PCT_MSDA_E_UNSUPPORTED;
+  const int out_features = out_a + out_b;
   if (!grad_y || !x || !grad_w) return PCT_MSDA_E_NULL_POINTER;
   if (flags & ~(PCT_LINEAR_BF16 | PCT_LINEAR_X_BF16 | PCT_LINEAR_GY_BF16)) return PCT_MSDA_E_UNSUPPORTED;
   const bool bf16 = flags & PCT_LINEAR_BF16;
@@ -1576,7 +1695,8 @@ int pct_linear_wgrad_ex(const float* grad_y, const float* x, float* grad_w, floa
   if (splits > 65535) splits = 65535;
   const int steps_per_split = (total_steps + splits - 1) / splits;
   splits = (total_steps + steps_per_split - 1) / steps_per_split;
-  WgradArgs a{flags, grad_y, x, grad_w, grad_bias, rows, in_features, out_features, steps_per_split};
+  WgradArgs a{flags, grad_y, x, grad_w, grad_bias, rows, in_features, out_features, steps_per_split,
+              grad_y_b, out_b > 0 ? out_features - out_b : 0};
   dim3 grid((out_features + kBlockM - 1) / kBlockM, (in_features + kBlockN - 1) / kBlockN, splits);
   if (bf16) {
     auto* k = (flags & PCT_LINEAR_GY_BF16)

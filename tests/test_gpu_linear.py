@@ -703,3 +703,38 @@ def test_bf16_memory_flags_need_the_bf16_kernel_error_codes():
     torch.cuda.synchronize()
     assert lib.pct_msda_error_string(bad).decode()
 
+
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("rows,k,na,nb", [(1000, 256, 192, 96), (4116, 128, 192, 96), (129, 64, 32, 16),
+                                          (5376, 256, 256, 64)])
+def test_pair_of_linears_on_one_input_as_one_gemm(rows, k, na, nb, bf16):
+    """pct_linear_forward_split / pct_linear_wgrad_split: sampling_offsets and attention_weights
+    (mod.py:102-104) as one GEMM with two dense outputs, one input-gradient GEMM over the pair of
+    output gradients and one weight-gradient GEMM -- against the two separate Linears."""
+    from pctrans_b200 import _cabi
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(rows, k, generator=g).cuda()
+    wa, wb = (torch.randn(na, k, generator=g) / k ** 0.5).cuda(), (torch.randn(nb, k, generator=g) / k ** 0.5).cuda()
+    ba, bb = torch.randn(na, generator=g).cuda(), torch.randn(nb, generator=g).cuda()
+    wcat = torch.cat((wa, wb), 0)
+    r = _r16 if bf16 else (lambda t: t.double())
+    ya, yb = _cabi.linear_forward_pair(x, _cabi.linear_pack_weight(wcat, bf16=bf16), na, nb,
+                                       torch.cat((ba, bb)), bf16=bf16)
+    assert _rel(ya, r(x) @ r(wa).t() + ba.double()) < 1e-5
+    assert _rel(yb, r(x) @ r(wb).t() + bb.double()) < 1e-5
+    # each output column is the same dot product as in the separate Linear: bit-identical
+    assert torch.equal(ya, _cabi.linear_forward(x, _cabi.linear_pack_weight(wa, bf16=bf16), na, ba, bf16=bf16))
+    assert torch.equal(yb, _cabi.linear_forward(x, _cabi.linear_pack_weight(wb, bf16=bf16), nb, bb, bf16=bf16))
+    ga = torch.randn(rows, na, generator=g).cuda()
+    gb_ = torch.randn(rows, nb, generator=g).cuda()
+    res = torch.randn(rows, k, generator=g).cuda()
+    gx_ref = r(ga) @ r(wa) + r(gb_) @ r(wb)
+    kstep = 32 if bf16 else 16                 # the pair's widths are the K of the input gradient
+    if na % kstep == 0 and (na + nb) % kstep == 0:
+        wt = _cabi.linear_pack_weight(wcat.t().contiguous(), bf16=bf16)
+        assert _rel(_cabi.linear_forward_cat(ga, gb_, wt, k, bf16=bf16), gx_ref) < 1e-5
+        assert _rel(_cabi.linear_forward_cat(ga, gb_, wt, k, residual=res, bf16=bf16), gx_ref + res.double()) < 1e-5
+    gw, gbias = _cabi.linear_wgrad_pair(ga, gb_, x, bf16=bf16)
+    assert _rel(gw[:na], r(ga).t() @ r(x)) < 1e-5 and _rel(gw[na:], r(gb_).t() @ r(x)) < 1e-5
+    assert _rel(gbias, torch.cat((ga, gb_), 1).double().sum(0)) < 1e-5
+
