@@ -94,6 +94,80 @@ def eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
     return not torch.is_autocast_enabled("cuda")
 
 
+def _tag(t: torch.Tensor):
+    return (t._version if not t.is_inference() else -1, t.data_ptr())
+
+
+def packed_pair(w_a, w_b, b_a, b_b, transposed: bool, bf16: bool):
+    """Packed operand of the row-concatenated weight ``[w_a; w_b]`` (or of its transpose) and the
+    concatenated bias, cached like ``packed_weight`` (on ``w_a``, keyed on all four tensors)."""
+    slot = w_a.__dict__.setdefault("_pct_packed_pair", {})
+    tag = (_tag(w_a), _tag(w_b), _tag(b_a), _tag(b_b), id(w_b), w_a.device, _EPOCH)
+    hit = slot.get((transposed, bf16))
+    if hit is not None and hit[0] == tag:
+        return hit[1], hit[2]
+    w = torch.cat((w_a.detach(), w_b.detach()), 0)
+    packed = _cabi.linear_pack_weight(w.t().contiguous() if transposed else w, bf16=bf16)
+    bias = torch.cat((b_a.detach(), b_b.detach())) if not transposed else None
+    slot[(transposed, bf16)] = (tag, packed, bias)
+    return packed, bias
+
+
+def pair_eligible(x, lin_a: torch.nn.Linear, lin_b: torch.nn.Linear) -> bool:
+    """Two Linears on the same input can run as one GEMM (``linear_pair``): both eligible, biases
+    present, the first width a multiple of 32 (output split) and both widths fit the K step of the
+    input-gradient GEMM; not under deterministic algorithms (the pair's weight gradient is split-K)."""
+    if lin_a.bias is None or lin_b.bias is None or torch.are_deterministic_algorithms_enabled():
+        return False
+    if not (eligible(x, lin_a.weight) and eligible(x, lin_b.weight)):
+        return False
+    na, nb = lin_a.weight.shape[0], lin_b.weight.shape[0]
+    kstep = 32 if bf16_operands() else 16
+    return na % 32 == 0 and na % kstep == 0 and (na + nb) % kstep == 0
+
+
+class LinearPairFunction(Function):
+    """``(x @ W_a^T + b_a, x @ W_b^T + b_b)`` as one GEMM with two dense results; backward: one
+    input-gradient GEMM over the pair of output gradients, one weight-gradient GEMM.  For
+    ``sampling_offsets`` / ``attention_weights`` of MSDeformAttn, which both project the query
+    (OPS/modules/ms_deform_attn.py:102-104): three kernels and an add fewer per layer and step."""
+
+    @staticmethod
+    def forward(ctx, x, w_a, b_a, w_b, b_b, bf16=False):
+        na, nb, k = w_a.shape[0], w_b.shape[0], w_a.shape[1]
+        x2 = x.reshape(-1, k).contiguous()
+        packed, bias = packed_pair(w_a, w_b, b_a, b_b, False, bf16)
+        ya, yb = _cabi.linear_forward_pair(x2, packed, na, nb, bias, bf16=bf16)
+        ctx.bf16 = bf16
+        ctx.x_shape = x.shape
+        ctx.save_for_backward(x2, w_a, w_b, b_a, b_b)
+        return ya.view(*x.shape[:-1], na), yb.view(*x.shape[:-1], nb)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_a, grad_b):
+        x2, w_a, w_b, b_a, b_b = ctx.saved_tensors
+        na, nb, k = w_a.shape[0], w_b.shape[0], w_a.shape[1]
+        ga = grad_a.reshape(-1, na).contiguous()
+        gb = grad_b.reshape(-1, nb).contiguous()
+        gx = gwa = gwb = gba = gbb = None
+        if ctx.needs_input_grad[0]:
+            packed_t, _ = packed_pair(w_a, w_b, b_a, b_b, True, ctx.bf16)
+            gx = _cabi.linear_forward_cat(ga, gb, packed_t, k, bf16=ctx.bf16).view(ctx.x_shape)
+        if any(ctx.needs_input_grad[1:5]):
+            gw, gbias = _cabi.linear_wgrad_pair(ga, gb, x2, bf16=ctx.bf16 and BF16_WGRAD)
+            gwa, gwb, gba, gbb = gw[:na], gw[na:], gbias[:na], gbias[na:]
+        return gx, gwa, gba, gwb, gbb, None
+
+
+def linear_pair(x, lin_a: torch.nn.Linear, lin_b: torch.nn.Linear):
+    """``(lin_a(x), lin_b(x))`` -- one tensor-core GEMM when ``pair_eligible``, two otherwise."""
+    if pair_eligible(x, lin_a, lin_b):
+        return LinearPairFunction.apply(x, lin_a.weight, lin_a.bias, lin_b.weight, lin_b.bias,
+                                        bf16_operands())
+    return linear(x, lin_a.weight, lin_a.bias), linear(x, lin_b.weight, lin_b.bias)
+
+
 def _gemm(x2, weight, n, bf16, transposed=False, **epilogue):
     """``epilogue(x2 @ weight^T)`` (or ``x2 @ weight`` with ``transposed``: the input gradient)."""
     return _cabi.linear_forward(x2, packed_weight(weight, transposed, bf16), n, bf16=bf16, **epilogue)

@@ -152,8 +152,13 @@ class MSDeformAttn(nn.Module):
                              .format(reference_points.shape[-1]))
         m, lv, pt = self.n_heads, self.n_levels, self.n_points
         value = self._values(input_flatten, input_padding_mask)
-        offsets = self._proj(self.sampling_offsets, query).view(n, len_q, m, lv, pt, 2)
-        logits = self._proj(self.attention_weights, query).view(n, len_q, m, lv * pt)
+        if self.tensor_core_linears:
+            # both project the query: one GEMM with two dense results when the widths allow it
+            offsets, logits = linear_tc.linear_pair(query, self.sampling_offsets, self.attention_weights)
+        else:
+            offsets, logits = self.sampling_offsets(query), self.attention_weights(query)
+        offsets = offsets.view(n, len_q, m, lv, pt, 2)
+        logits = logits.view(n, len_q, m, lv * pt)
 
         if self.fused_prologue and MSDeformAttnFusedFunction.supported(value, reference_points, lv, pt):
             out = MSDeformAttnFusedFunction.apply(

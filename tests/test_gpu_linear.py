@@ -738,3 +738,46 @@ def test_pair_of_linears_on_one_input_as_one_gemm(rows, k, na, nb, bf16):
     assert _rel(gw[:na], r(ga).t() @ r(x)) < 1e-5 and _rel(gw[na:], r(gb_).t() @ r(x)) < 1e-5
     assert _rel(gbias, torch.cat((ga, gb_), 1).double().sum(0)) < 1e-5
 
+
+@pytest.mark.parametrize("amp", [False, True])
+def test_linear_pair_function_matches_two_linears(amp):
+    """linear_pair (one GEMM forward, one input-gradient GEMM, one weight-gradient GEMM) against the
+    two separate tensor-core Linears: identical outputs, gradients within fp32 reduction noise; the
+    MSDeformAttn module takes it for sampling_offsets / attention_weights."""
+    from pctrans_b200 import _cabi
+    from pctrans_b200.functions import linear_tc
+    torch.manual_seed(3)
+    la, lb = torch.nn.Linear(256, 192).cuda(), torch.nn.Linear(256, 96).cuda()
+    x = torch.randn(2, 1500, 256, device="cuda", requires_grad=True)
+    ga, gb = torch.randn(2, 1500, 192, device="cuda"), torch.randn(2, 1500, 96, device="cuda")
+    params = [x, la.weight, la.bias, lb.weight, lb.bias]
+
+    def run(pair):
+        for p in params:
+            p.grad = None
+        n0 = _cabi.launch_count()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            assert linear_tc.pair_eligible(x, la, lb)
+            if pair:
+                ya, yb = linear_tc.linear_pair(x, la, lb)
+            else:
+                ya, yb = linear_tc.linear(x, la.weight, la.bias), linear_tc.linear(x, lb.weight, lb.bias)
+        torch.autograd.backward((ya, yb), (ga, gb))
+        return ya.detach(), yb.detach(), [p.grad.clone() for p in params], _cabi.launch_count() - n0
+
+    run(True)
+    ya1, yb1, g1, n1 = run(True)
+    run(False)
+    ya0, yb0, g0, n0 = run(False)
+    assert torch.equal(ya1, ya0) and torch.equal(yb1, yb0)
+    assert n1 < n0                                     # fewer kernels
+    for a, b_, name in zip(g1, g0, ("x", "w_a", "b_a", "w_b", "b_b")):
+        assert _rel(a, b_.double()) < 1e-5, name
+    # in-place weight updates are seen by the pair's cached operand
+    with torch.no_grad():
+        la.weight.mul_(2.0)
+        lb.bias.add_(1.0)
+    ya2, yb2 = linear_tc.linear_pair(x.detach(), la, lb)
+    assert _rel(ya2 - la.bias, 2.0 * (ya0 - la.bias).double()) < (2e-2 if amp else 1e-5)
+    assert _rel(yb2, (yb0 + 1.0).double()) < (2e-2 if amp else 1e-5)
+
