@@ -47,6 +47,9 @@
 #ifndef PCT_LIN_STAGGER_FIXED
 #define PCT_LIN_STAGGER_FIXED 2000   // ns
 #endif
+#ifndef PCT_LIN_L2PF
+#define PCT_LIN_L2PF 256 // L2 prefetch hint of the loaders' x loads: 0 none, 128 / 256 bytes
+#endif
 #ifndef PCT_LIN_AHEAD_BF16
 #define PCT_LIN_AHEAD_BF16 4
 #endif
@@ -165,6 +168,23 @@ __device__ __forceinline__ uint2 pack_bf16x4(const float4& a) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.x) : "f"(a.y), "f"(a.x));
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r.y) : "f"(a.w), "f"(a.z));
   return r;
+}
+
+// 16-byte read-only load of an activation chunk (optionally with an L2 prefetch-size hint)
+__device__ __forceinline__ float4 ldg_x(const void* p) {
+#if PCT_LIN_L2PF == 256
+  float4 v;
+  asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#elif PCT_LIN_L2PF == 128
+  float4 v;
+  asm volatile("ld.global.nc.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const float4*>(p));
+#endif
 }
 
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -729,12 +749,12 @@ __device__ __forceinline__ void linear_body(const LinearArgs& a, unsigned char* 
 #pragma unroll
       for (int j = 0; j < kPerThread; ++j) {
         if (xb) {
-          dst[j * kQ] = xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + at))
+          dst[j * kQ] = xrow[j] ? ldg_x(xrow[j] + at)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
 #pragma unroll
           for (int h = 0; h < kQ; ++h)
-            dst[j * kQ + h] = xrow[j] ? __ldg(reinterpret_cast<const float4*>(xrow[j] + at) + h)
+            dst[j * kQ + h] = xrow[j] ? ldg_x(xrow[j] + at + 16 * h)
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
