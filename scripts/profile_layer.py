@@ -31,3 +31,8 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(5): step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+# every CUDA kernel of the five steps, by total time (no cuBLAS / cuDNN GEMM may appear in the layer)
+kern = [e for e in prof.key_averages() if e.device_type.name == "CUDA"] if hasattr(prof.key_averages()[0], "device_type") else []
+print("\nCUDA kernels (5 steps):")
+for e in sorted(kern, key=lambda e: -e.device_time_total):
+    print(f"{e.device_time_total / 5:9.1f} us/step  x{e.count / 5:4.1f}  {e.key[:120]}")
